@@ -1,0 +1,145 @@
+/*
+ * triple_accel_b200.h -- C ABI of libtriple_accel_b200.so
+ *
+ * A B200 (sm_100a) batched edit-distance engine that keeps the contracts of the Rust crate `triple_accel`
+ * (reference @ 0f2119a, v0.4.0).  The reference has no FFI: its boundary is the crate's public Rust functions
+ * (re-exported at src/lib.rs:126-127).  Each entry point below names the reference function whose contract it
+ * implements; INTEGRATION.md shows the Rust shim (`extern "C"` block + safe wrappers with the crate's names) a
+ * maintainer would add.  Plain pointers and sizes only; nothing is retained after a call returns.
+ *
+ * Batch layout ("CSR"): a batch of n byte strings is one contiguous byte buffer plus n+1 u64 offsets;
+ * string i is bytes[off[i] .. off[i+1]).  Pair i is (a_i, b_i).
+ *
+ * Threading: a ta_ctx owns one CUDA device, its streams and staging buffers; calls on one ctx are serialised by
+ * an internal mutex.  Use one ctx per thread (or per process, one process per GPU) for concurrency.
+ *
+ * Errors: 0 = success; negative = error (ta_strerror).  Contract violations that the reference turns into
+ * panics are reported as error codes (the Rust shim panics on them):  TA_ERR_LEN_MISMATCH <-> assert at
+ * src/hamming.rs:38,318;  TA_ERR_BAD_COSTS <-> asserts at src/levenshtein.rs:44-52,69.
+ * "Not within k" is a value (TA_NONE), not an error (src/levenshtein.rs:428-430, 539-541, 860-862, 1166-1168).
+ * There is no CPU fallback: without a usable CUDA device every compute entry point fails with TA_ERR_CUDA.
+ */
+#ifndef TRIPLE_ACCEL_B200_H
+#define TRIPLE_ACCEL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TA_ABI_VERSION 1
+
+/* Option::None for a distance (Option<u32> in src/levenshtein.rs:342, 677, 714-720) */
+#define TA_NONE 0xFFFFFFFFu
+
+enum {
+    TA_OK = 0,
+    TA_ERR_CUDA = -1,         /* CUDA runtime failure (ta_last_error has the text) */
+    TA_ERR_LEN_MISMATCH = -2, /* hamming: a_i and b_i differ in length (src/hamming.rs:38, 318) */
+    TA_ERR_BAD_COSTS = -3,    /* EditCosts::new / check_search asserts (src/levenshtein.rs:44-52, 69) */
+    TA_ERR_BAD_ARG = -4,      /* null pointer, non-monotone offsets, bad enum value */
+    TA_ERR_TOO_LARGE = -5,    /* a string exceeds TA_MAX_STRING_LEN, or cost arithmetic would overflow u32 */
+    TA_ERR_NOMEM = -6         /* host allocation failed */
+};
+
+/* (len_a + len_b) * max(cost) must stay below 2^30 so that u32 cells never wrap */
+#define TA_MAX_STRING_LEN (1u << 21)
+
+/* EditCosts (src/levenshtein.rs:20-26).  transpose == 0 encodes transpose_cost: None
+ * (Some(t) requires t > 0, src/levenshtein.rs:47-48). */
+typedef struct {
+    uint8_t mismatch, gap, start_gap, transpose;
+} ta_costs;
+
+/* LEVENSHTEIN_COSTS (src/levenshtein.rs:76-81), RDAMERAU_COSTS (src/levenshtein.rs:84-89) */
+#define TA_LEVENSHTEIN_COSTS_INIT {1, 1, 0, 0}
+#define TA_RDAMERAU_COSTS_INIT {1, 1, 0, 1}
+
+/* Match (src/lib.rs:134-142): start inclusive, end exclusive, k = cost of the match */
+typedef struct {
+    uint64_t start, end;
+    uint32_t k, _pad;
+} ta_match;
+
+/* SearchType (src/lib.rs:170-174) */
+enum { TA_SEARCH_ALL = 0, TA_SEARCH_BEST = 1 };
+
+typedef struct ta_ctx ta_ctx;
+
+/* ---- lifetime -------------------------------------------------------------------------------------------- */
+int ta_abi_version(void);
+/* Create a context on CUDA device `device` (one context per GPU; one process per GPU in multi-GPU runs). */
+int ta_init(int device, ta_ctx **out);
+void ta_shutdown(ta_ctx *ctx);
+const char *ta_strerror(int code);
+const char *ta_last_error(ta_ctx *ctx); /* text of the last CUDA error seen by this ctx */
+int ta_device(ta_ctx *ctx);
+/* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
+uint64_t ta_launch_count(ta_ctx *ctx);
+
+/* Pinned host memory for fast H2D/D2H of batch buffers (optional: any host pointer is accepted). */
+void *ta_host_alloc(size_t bytes);
+void ta_host_free(void *p);
+/* Free arrays returned by ta_levenshtein_search_batch. */
+void ta_free(void *p);
+
+/* EditCosts::new validity (src/levenshtein.rs:38-60) / check_search (src/levenshtein.rs:67-71): 1 = valid */
+int ta_costs_valid(ta_costs c);
+int ta_costs_valid_search(ta_costs c);
+
+/* ---- host-buffer batch entry points (H2D + kernels + D2H inside the call) ---------------------------------- */
+
+/* hamming (src/hamming.rs:390-392) == hamming_naive (src/hamming.rs:36-47) per pair.
+ * out[i] = number of positions where a_i and b_i differ.  TA_ERR_LEN_MISMATCH if any pair differs in length. */
+int ta_hamming_batch(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b, const uint64_t *b_off,
+                     size_t n, uint32_t *out);
+
+/* levenshtein_simd_k_with_opts(a, b, k, false, costs) (src/levenshtein.rs:714-827), bit-exact with the scalar
+ * levenshtein_naive_k_with_opts (src/levenshtein.rs:376-545): out[i] = d if d <= k else TA_NONE.
+ * k = 0xFFFFFFFF gives levenshtein() / rdamerau() (src/levenshtein.rs:1397-1399, 1419-1423). */
+int ta_levenshtein_k_batch(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b,
+                           const uint64_t *b_off, size_t n, uint32_t k, ta_costs costs, uint32_t *out);
+
+/* levenshtein_exp / levenshtein_exp_with_opts / rdamerau_exp (src/levenshtein.rs:1445-1454, 1480-1494,
+ * 1516-1526): exact distance by running the k-bounded routine with k = 30, 60, 120, ... on the pairs that are
+ * still TA_NONE.  Never returns TA_NONE. */
+int ta_levenshtein_exp_batch(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b,
+                             const uint64_t *b_off, size_t n, ta_costs costs, uint32_t *out);
+
+/* levenshtein_search_simd_with_opts(needle, haystack_i, k, search_type, costs, anchored)
+ * (src/levenshtein.rs:1911-2155), bit-exact with levenshtein_search_naive_with_opts (src/levenshtein.rs:1589-1838)
+ * for every haystack of the batch.  *out_matches receives all matches, haystack by haystack, in the order the
+ * reference iterator yields them; matches of haystack i are (*out_matches)[(*out_match_off)[i] ..
+ * (*out_match_off)[i+1]).  Both arrays are malloc'd by the library: release with ta_free.
+ * levenshtein_search(needle, haystack) (src/levenshtein.rs:2508-2513) is k = ta_search_default_k(needle_len),
+ * TA_SEARCH_BEST, unit costs, anchored = 0. */
+int ta_levenshtein_search_batch(ta_ctx *ctx, const uint8_t *needle, size_t needle_len, const uint8_t *hay,
+                                const uint64_t *hay_off, size_t n, uint32_t k, int search_type, ta_costs costs,
+                                int anchored, ta_match **out_matches, uint64_t **out_match_off);
+uint32_t ta_search_default_k(size_t needle_len); /* src/levenshtein.rs:1873 */
+
+/* ---- device-resident entry points (kernel-only; all pointers are device pointers on ctx's device) ---------- */
+/* `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  Calls are asynchronous.
+ * `max_len` is an upper bound on the length of any string in the batch (picks the kernel variant). */
+int ta_hamming_batch_dev(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b,
+                         const uint64_t *b_off, size_t n, uint32_t *out, void *stream);
+int ta_levenshtein_k_batch_dev(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b,
+                               const uint64_t *b_off, size_t n, uint32_t k, ta_costs costs, uint32_t max_len,
+                               uint32_t *out, void *stream);
+/* Synchronises `stream` and reports a deferred contract violation seen by a *_dev kernel (e.g. a Hamming
+ * length mismatch), clearing it. */
+int ta_dev_status(ta_ctx *ctx, void *stream);
+
+/* ---- single-pair conveniences with the crate's exact shapes (batch of one through the same kernels) -------- */
+int ta_hamming(ta_ctx *ctx, const uint8_t *a, size_t a_len, const uint8_t *b, size_t b_len, uint32_t *out);
+int ta_levenshtein_simd_k_with_opts(ta_ctx *ctx, const uint8_t *a, size_t a_len, const uint8_t *b, size_t b_len,
+                                    uint32_t k, ta_costs costs, uint32_t *out);
+int ta_levenshtein_exp_with_opts(ta_ctx *ctx, const uint8_t *a, size_t a_len, const uint8_t *b, size_t b_len,
+                                 ta_costs costs, uint32_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRIPLE_ACCEL_B200_H */

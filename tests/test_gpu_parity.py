@@ -1,0 +1,312 @@
+"""GPU parity tests: the CUDA path through the C ABI vs the CPU oracle (bit-exact) and vs the reference's own
+known-answer vectors (tests/golden/kat.json).  Run on the B200 box with `pytest -m gpu`."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+import _oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+KAT = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "kat.json")))
+NONE = 0xFFFFFFFF
+
+COST_MODELS = [(1, 1, 0, 0), (1, 1, 0, 1), (1, 1, 2, 0), (2, 1, 2, 0), (2, 3, 0, 0), (3, 1, 0, 0), (2, 2, 1, 3),
+               (3, 2, 0, 2), (1, 1, 1, 1), (5, 4, 3, 0)]
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import triple_accel_b200 as ta
+    e = ta.Engine(0)
+    yield e
+    e.close()
+
+
+def _ids(recs):
+    return ["%s@%s" % (r["fn"], r["src"].split(" ")[0]) for r in recs]
+
+
+def _pack(strs):
+    from triple_accel_b200 import pack
+    return pack(strs)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# known-answer vectors of the reference, through the single-pair C-ABI functions
+HAMMING = [r for r in KAT if r["fn"] in ("hamming", "hamming_naive", "hamming_simd_parallel", "hamming_simd_movemask")]
+DIST = [r for r in KAT if r["fn"] in ("levenshtein", "levenshtein_naive", "levenshtein_naive_with_opts", "rdamerau",
+                                      "levenshtein_exp", "levenshtein_exp_with_opts", "rdamerau_exp",
+                                      "levenshtein_naive_k", "levenshtein_simd_k", "levenshtein_naive_k_with_opts",
+                                      "levenshtein_simd_k_with_opts")]
+SEARCH = [r for r in KAT if r["fn"].startswith("levenshtein_search")]
+
+
+@pytest.mark.parametrize("r", HAMMING, ids=_ids(HAMMING))
+def test_kat_hamming(eng, r):
+    assert eng.hamming(bytes.fromhex(r["a"]), bytes.fromhex(r["b"])) == r["expect"]["dist"]
+
+
+@pytest.mark.parametrize("r", DIST, ids=_ids(DIST))
+def test_kat_distance(eng, r):
+    import triple_accel_b200 as ta
+    a, b = bytes.fromhex(r["a"]), bytes.fromhex(r["b"])
+    fn = r["fn"]
+    rd = fn.startswith("rdamerau")
+    c = r.get("costs", [1, 1, 0, 1] if rd else [1, 1, 0, 0])
+    costs = ta.EditCosts(c[0], c[1], c[2], c[3] or None)
+    if fn in ("levenshtein_exp", "levenshtein_exp_with_opts", "rdamerau_exp"):
+        assert eng.levenshtein_exp_with_opts(a, b, False, costs)[0] == r["expect"]["dist"]
+        return
+    k = r.get("k", 0xFFFFFFFF)  # levenshtein()/rdamerau()/naive: k = u32::MAX
+    res = eng.levenshtein_simd_k_with_opts(a, b, k, False, costs)
+    if r["expect"].get("none"):
+        assert res is None
+    else:
+        assert res is not None and res[0] == r["expect"]["dist"]
+
+
+@pytest.mark.parametrize("r", SEARCH, ids=_ids(SEARCH))
+def test_kat_search(eng, r):
+    import triple_accel_b200 as ta
+    needle, hay = bytes.fromhex(r["a"]), bytes.fromhex(r["b"])
+    if "k" in r:
+        c = r["costs"]
+        got = eng.levenshtein_search_simd_with_opts(needle, hay, r["k"], r["search_type"],
+                                                    ta.EditCosts(c[0], c[1], c[2], c[3] or None), r["anchored"])
+    else:
+        got = eng.levenshtein_search(needle, hay)
+    got = [tuple(m) for m in got]
+    if r["expect"].get("first_only"):
+        got = got[:1]
+    assert got == [(m["start"], m["end"], m["k"]) for m in r["expect"]["matches"]]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# error behaviour of the boundary
+def test_hamming_length_mismatch_panics(eng):
+    with pytest.raises(AssertionError):
+        eng.hamming(b"abc", b"ab")  # reference: assert at src/hamming.rs:38
+    a, ao = _pack([b"abcd", b"xy"])
+    b, bo = _pack([b"abcd", b"xyz"])
+    with pytest.raises(AssertionError):
+        eng.hamming_batch(a, ao, b, bo)
+
+
+def test_bad_costs_rejected(eng):
+    from triple_accel_b200 import _ffi
+    lib = _ffi.load()
+    import ctypes as C
+    out = C.c_uint32()
+    rc = lib.ta_levenshtein_simd_k_with_opts(eng._h, b"a", 1, b"b", 1, 1, _ffi.ta_costs(0, 1, 0, 0), C.byref(out))
+    assert rc == _ffi.TA_ERR_BAD_COSTS
+    mp, op = C.POINTER(_ffi.ta_match)(), C.POINTER(C.c_uint64)()
+    off = np.array([0, 1], np.uint64)
+    rc = lib.ta_levenshtein_search_batch(eng._h, b"ab", 2, b"b", off.ctypes.data, 1, 1, 0, _ffi.ta_costs(2, 2, 0, 3), 0,
+                                         C.byref(mp), C.byref(op))
+    assert rc == _ffi.TA_ERR_BAD_COSTS  # check_search, src/levenshtein.rs:69
+
+
+def test_empty_batch(eng):
+    z8, z64 = np.zeros(0, np.uint8), np.zeros(1, np.uint64)
+    assert len(eng.hamming_batch(z8, z64, z8, z64)) == 0
+    assert len(eng.levenshtein_k_batch(z8, z64, z8, z64, 3)) == 0
+    assert len(eng.levenshtein_exp_batch(z8, z64, z8, z64)) == 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# randomised differential tests against the oracle
+def _rand_strs(rng, n, lo, hi, alpha):
+    return [bytes(rng.randrange(alpha) for _ in range(rng.randrange(lo, hi + 1))) for _ in range(n)]
+
+
+def _mutate(rng, s, e, alpha, swap=True):
+    s = bytearray(s)
+    for _ in range(e):
+        kind = rng.randrange(4 if swap else 3)
+        if kind == 0 and s:
+            s[rng.randrange(len(s))] = rng.randrange(alpha)
+        elif kind == 1:
+            s.insert(rng.randrange(len(s) + 1), rng.randrange(alpha))
+        elif kind == 2 and s:
+            del s[rng.randrange(len(s))]
+        elif kind == 3 and len(s) > 1:
+            p = rng.randrange(len(s) - 1)
+            s[p], s[p + 1] = s[p + 1], s[p]
+    return bytes(s)
+
+
+@pytest.mark.parametrize("lens", [(0, 0), (1, 15), (16, 16), (64, 64), (0, 200), (1000, 1100), (4096, 4096)])
+def test_hamming_random(eng, lens):
+    rng = random.Random(hash(lens) & 0xFFFF)
+    n = 3000 if lens[1] <= 256 else 200
+    A = _rand_strs(rng, n, lens[0], lens[1], 4)
+    B = [bytes((c if rng.random() < 0.7 else rng.randrange(256)) for c in s) for s in A]
+    a, ao = _pack(A)
+    b, bo = _pack(B)
+    got = eng.hamming_batch(a, ao, b, bo)
+    want = orc.hamming_batch(a, ao, b, bo)
+    assert np.array_equal(got, want)
+
+
+def test_hamming_misaligned_views(eng):
+    """strings that start at odd addresses inside the byte buffers (CSR offsets need not be aligned)"""
+    rng = random.Random(5)
+    A = _rand_strs(rng, 500, 0, 90, 256)
+    B = [bytes((c if rng.random() < 0.8 else rng.randrange(256)) for c in s) for s in A]
+    a, ao = _pack(A)
+    b, bo = _pack(B)
+    a2 = np.concatenate([np.zeros(3, np.uint8), a])  # shift a by 3 bytes, b by 0
+    got = eng.hamming_batch(a2, ao + np.uint64(3), b, bo)
+    assert np.array_equal(got, orc.hamming_batch(a, ao, b, bo))
+
+
+@pytest.mark.parametrize("costs", COST_MODELS, ids=[str(c) for c in COST_MODELS])
+def test_lev_k_random_short(eng, costs):
+    """short strings over small alphabets (many ties, transpositions and empty strings), every k regime"""
+    rng = random.Random(sum(costs))
+    A, B = [], []
+    for _ in range(4000):
+        alpha = rng.choice([2, 3, 4, 26])
+        A.append(bytes(rng.randrange(alpha) for _ in range(rng.randrange(0, 24))))
+        B.append(bytes(rng.randrange(alpha) for _ in range(rng.randrange(0, 24))))
+    a, ao = _pack(A)
+    b, bo = _pack(B)
+    for k in (0, 1, 2, 3, 5, 8, 16, 30, 100, 0xFFFFFFFF):
+        got = eng.levenshtein_k_batch(a, ao, b, bo, k, costs)
+        want = orc.levenshtein_k_batch(a, ao, b, bo, k, costs)
+        bad = np.nonzero(got != want)[0]
+        assert len(bad) == 0, (k, costs, A[bad[0]], B[bad[0]], int(got[bad[0]]), int(want[bad[0]]))
+
+
+@pytest.mark.parametrize("length,k", [(128, 8), (128, 16), (512, 16), (300, 30), (1024, 30), (100, 64), (77, 200),
+                                      (2000, 5)])
+@pytest.mark.parametrize("costs", [(1, 1, 0, 0), (1, 1, 0, 1), (2, 1, 3, 0), (2, 2, 1, 3)], ids=str)
+def test_lev_k_mutated(eng, length, k, costs):
+    """the BASELINE shapes at reduced batch size: mutated pairs (within k) and unrelated pairs (None)"""
+    rng = random.Random(length * 131 + k)
+    n = 600 if length <= 512 else 150
+    A = _rand_strs(rng, n, max(0, length - 3), length, 256)
+    B = [(_mutate(rng, s, rng.randrange(0, k + 3), 256) if rng.random() < 0.8 else
+          bytes(rng.randrange(256) for _ in range(len(s)))) for s in A]
+    a, ao = _pack(A)
+    b, bo = _pack(B)
+    got = eng.levenshtein_k_batch(a, ao, b, bo, k, costs)
+    want = orc.levenshtein_k_batch(a, ao, b, bo, k, costs, threads=8)
+    bad = np.nonzero(got != want)[0]
+    assert len(bad) == 0, (len(bad), A[bad[0]], B[bad[0]], int(got[bad[0]]), int(want[bad[0]]))
+    # swapped argument order gives the same answers (the reference swaps so that a is the shorter string)
+    got2 = eng.levenshtein_k_batch(b, bo, a, ao, k, costs)
+    assert np.array_equal(got2, want)
+
+
+@pytest.mark.parametrize("costs", [(1, 1, 0, 0), (1, 1, 0, 1), (1, 1, 2, 0), (3, 2, 0, 2)], ids=str)
+def test_lev_full_matrix(eng, costs):
+    """levenshtein() / rdamerau(): k = u32::MAX, the band is the whole matrix"""
+    rng = random.Random(99)
+    A = _rand_strs(rng, 300, 0, 200, 5)
+    B = _rand_strs(rng, 300, 0, 200, 5)
+    a, ao = _pack(A)
+    b, bo = _pack(B)
+    got = eng.levenshtein_k_batch(a, ao, b, bo, 0xFFFFFFFF, costs)
+    want = orc.levenshtein_k_batch(a, ao, b, bo, 0xFFFFFFFF, costs, threads=8)
+    assert np.array_equal(got, want)
+    assert not (got == NONE).any()
+
+
+@pytest.mark.parametrize("costs", [(1, 1, 0, 0), (1, 1, 0, 1), (2, 1, 2, 0)], ids=str)
+def test_lev_exp(eng, costs):
+    rng = random.Random(17)
+    A = _rand_strs(rng, 400, 0, 300, 256)
+    B = []
+    for s in A:
+        r = rng.random()
+        if r < 0.5:
+            B.append(_mutate(rng, s, rng.randrange(0, 6), 256))
+        elif r < 0.8:
+            B.append(_mutate(rng, s, rng.randrange(20, 90), 256))  # needs k = 60, 120 rounds
+        else:
+            B.append(bytes(rng.randrange(256) for _ in range(rng.randrange(0, 300))))
+    a, ao = _pack(A)
+    b, bo = _pack(B)
+    got = eng.levenshtein_exp_batch(a, ao, b, bo, costs)
+    want = orc.levenshtein_exp_batch(a, ao, b, bo, costs, threads=8)
+    assert np.array_equal(got, want)
+
+
+def test_nul_bytes_and_high_bytes(eng):
+    """the reference guards its zero-padded SIMD windows with NUL-byte cases (tests/basic_tests.rs:503-537)"""
+    rng = random.Random(3)
+    A = [bytes(rng.choice([0, 0, 255, 1]) for _ in range(rng.randrange(0, 40))) for _ in range(1500)]
+    B = [bytes(rng.choice([0, 0, 255, 1]) for _ in range(rng.randrange(0, 40))) for _ in range(1500)]
+    a, ao = _pack(A)
+    b, bo = _pack(B)
+    for costs in ((1, 1, 0, 0), (1, 1, 0, 1)):
+        for k in (2, 7, 0xFFFFFFFF):
+            assert np.array_equal(eng.levenshtein_k_batch(a, ao, b, bo, k, costs),
+                                  orc.levenshtein_k_batch(a, ao, b, bo, k, costs))
+
+
+SEARCH_MODELS = [(1, 1, 0, 0), (1, 1, 0, 1), (1, 1, 2, 0), (2, 1, 2, 0), (3, 1, 0, 0), (2, 2, 1, 3), (1, 2, 0, 2)]
+
+
+@pytest.mark.parametrize("costs", SEARCH_MODELS, ids=[str(c) for c in SEARCH_MODELS])
+@pytest.mark.parametrize("anchored", [False, True])
+def test_search_random(eng, costs, anchored):
+    rng = random.Random(sum(costs) + anchored)
+    for trial in range(6):
+        alpha = rng.choice([2, 3, 4, 20])
+        nlen = rng.choice([1, 2, 3, 5, 8, 13, 32, 40])
+        needle = bytes(rng.randrange(alpha) for _ in range(nlen))
+        hays = []
+        for _ in range(120):
+            h = bytearray(rng.randrange(alpha) for _ in range(rng.randrange(0, 120)))
+            if rng.random() < 0.5 and len(h) > nlen:
+                p = rng.randrange(len(h) - nlen)
+                h[p:p + nlen] = _mutate(rng, needle, rng.randrange(0, 3), alpha)
+            hays.append(bytes(h))
+        hay, hoff = _pack(hays)
+        for k in (0, 1, 2, nlen // 2 + 1, 3 * nlen):
+            for st in (0, 1):
+                got, goff = eng.levenshtein_search_batch(needle, hay, hoff, k, st, costs, anchored)
+                want, woff = orc.levenshtein_search_batch(needle, hay, hoff, k, st, costs, anchored, threads=8)
+                assert np.array_equal(goff, woff), (needle, k, st, costs, anchored)
+                assert np.array_equal(got, want), (needle, k, st, costs, anchored)
+
+
+def test_search_planted_long_haystacks(eng):
+    """cfg 4 shape at reduced size: needle 32, haystacks of 4096 bytes 1..255, k = 3, planted hits"""
+    from triple_accel_b200 import synth
+    needle, hay, hoff = synth.needle_haystacks(600, 4096, 32, plant_frac=0.05, max_edits=3, seed=7)
+    for st in (0, 1):
+        got, goff = eng.levenshtein_search_batch(needle, hay, hoff, 3, st)
+        want, woff = orc.levenshtein_search_batch(needle, hay, hoff, 3, st, threads=8)
+        assert np.array_equal(goff, woff) and np.array_equal(got, want)
+        assert goff[-1] >= 20  # the planted needles are found
+
+
+def test_device_resident_entry_points(eng):
+    import torch
+    from triple_accel_b200 import synth
+    a, ao, b, bo = synth.mutated_pairs(20000, 128, 8, seed=5)
+    dev = torch.device("cuda", eng.device)
+    ta_, tao, tb, tbo = (torch.from_numpy(x.view(np.int64) if x.dtype == np.uint64 else x).to(dev) for x in (a, ao, b, bo))
+    out = torch.empty(20000, dtype=torch.int32, device=dev)
+    eng.levenshtein_k_batch_dev(ta_, tao, tb, tbo, 8, (1, 1, 0, 0), 136, out)
+    eng.dev_status()
+    want = orc.levenshtein_k_batch(a, ao, b, bo, 8, threads=8)
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), want)
+    # hamming on the equal-length prefix pairs
+    a2, ao2, b2, bo2 = synth.hamming_pairs(10000, 64, seed=9)
+    t = [torch.from_numpy(x.view(np.int64) if x.dtype == np.uint64 else x).to(dev) for x in (a2, ao2, b2, bo2)]
+    out2 = torch.empty(10000, dtype=torch.int32, device=dev)
+    eng.hamming_batch_dev(t[0], t[1], t[2], t[3], out2)
+    eng.dev_status()
+    assert np.array_equal(out2.cpu().numpy().view(np.uint32), orc.hamming_batch(a2, ao2, b2, bo2))
+    # a length mismatch on the device path is reported by ta_dev_status
+    eng.hamming_batch_dev(t[0], t[1], tb, tbo, out2)
+    with pytest.raises(AssertionError):
+        eng.dev_status()

@@ -1,0 +1,12 @@
+"""triple_accel_b200 -- B200 (sm_100a) batched edit-distance engine with the `triple_accel` crate's interface.
+
+The product is libtriple_accel_b200.so (C ABI in include/triple_accel_b200.h, CUDA sources in csrc/).  This
+package is the Python host mirror of the crate's public names used by the tests and the bench.
+"""
+from .api import (EditCosts, EditType, Engine, LEVENSHTEIN_COSTS, Match, RDAMERAU_COSTS, SearchType, TA_NONE,
+                  TripleAccelError, default_engine, hamming, hamming_batch, levenshtein, levenshtein_exp,
+                  levenshtein_exp_batch, levenshtein_exp_with_opts, levenshtein_k_batch, levenshtein_search,
+                  levenshtein_search_batch, levenshtein_search_simd, levenshtein_search_simd_with_opts,
+                  levenshtein_simd_k, levenshtein_simd_k_with_opts, pack, rdamerau, rdamerau_exp)
+
+__all__ = [n for n in dir() if not n.startswith("_")]

@@ -1,0 +1,306 @@
+"""Host-side mirror of the `triple_accel` crate's public interface over the C ABI.
+
+Names, argument meaning and error behaviour follow the reference (src/lib.rs:126-127 re-exports):
+contract violations that the crate turns into panics raise AssertionError here; "not within k" is None.
+Single-pair functions are batches of one through the same CUDA kernels; the `*_batch` functions are the
+measured path (CSR numpy arrays in host memory) and `*_dev` take device-resident torch tensors.
+"""
+import ctypes as C
+import os
+from collections import namedtuple
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import TA_NONE, ta_costs, ta_match
+
+# src/lib.rs:134-142 -- start inclusive, end exclusive
+Match = namedtuple("Match", ["start", "end", "k"])
+
+
+class SearchType:  # src/lib.rs:170-174
+    All = 0
+    Best = 1
+
+
+class EditType:  # src/lib.rs:147-154
+    Match, Mismatch, AGap, BGap, Transpose = range(5)
+
+
+class EditCosts:
+    """src/levenshtein.rs:20-60.  transpose_cost=None disables transpositions."""
+
+    __slots__ = ("mismatch_cost", "gap_cost", "start_gap_cost", "transpose_cost")
+
+    def __init__(self, mismatch_cost, gap_cost, start_gap_cost, transpose_cost=None):
+        for v in (mismatch_cost, gap_cost, start_gap_cost) + ((transpose_cost,) if transpose_cost is not None else ()):
+            if not 0 <= int(v) <= 255:
+                raise OverflowError("EditCosts fields are u8")
+        assert mismatch_cost > 0
+        assert gap_cost > 0
+        if transpose_cost is not None:
+            assert transpose_cost > 0
+            assert (transpose_cost >> 1) < mismatch_cost
+            assert (transpose_cost >> 1) < gap_cost
+        self.mismatch_cost, self.gap_cost = int(mismatch_cost), int(gap_cost)
+        self.start_gap_cost = int(start_gap_cost)
+        self.transpose_cost = None if transpose_cost is None else int(transpose_cost)
+
+    def check_search(self):  # src/levenshtein.rs:67-71
+        if self.transpose_cost is not None:
+            assert self.transpose_cost <= self.start_gap_cost + self.gap_cost
+
+    def _c(self):
+        return ta_costs(self.mismatch_cost, self.gap_cost, self.start_gap_cost, self.transpose_cost or 0)
+
+    def __repr__(self):
+        return "EditCosts(%d, %d, %d, %r)" % (self.mismatch_cost, self.gap_cost, self.start_gap_cost,
+                                               self.transpose_cost)
+
+
+LEVENSHTEIN_COSTS = EditCosts(1, 1, 0, None)  # src/levenshtein.rs:76-81
+RDAMERAU_COSTS = EditCosts(1, 1, 0, 1)  # src/levenshtein.rs:84-89
+
+
+def _as_costs(c):
+    if isinstance(c, EditCosts):
+        return c
+    c = tuple(c)
+    return EditCosts(c[0], c[1], c[2], c[3] if len(c) > 3 and c[3] else None)
+
+
+class TripleAccelError(RuntimeError):
+    def __init__(self, code, detail=""):
+        self.code = code
+        msg = _ffi.load().ta_strerror(code).decode()
+        super().__init__("%s (code %d)%s" % (msg, code, (": " + detail) if detail else ""))
+
+
+def pack(strings):
+    """list of bytes-like -> (uint8 array, uint64 offsets[n+1]) in the CSR layout the C ABI takes."""
+    off = np.zeros(len(strings) + 1, np.uint64)
+    if strings:
+        off[1:] = np.cumsum([len(s) for s in strings], dtype=np.uint64)
+    buf = np.frombuffer(b"".join(bytes(s) for s in strings), np.uint8).copy() if strings else np.zeros(0, np.uint8)
+    return buf, off
+
+
+def _u8(x):
+    if isinstance(x, (bytes, bytearray, memoryview)):
+        return np.frombuffer(bytes(x), np.uint8)
+    x = np.ascontiguousarray(x)
+    assert x.dtype == np.uint8
+    return x
+
+
+def _u64(x):
+    x = np.ascontiguousarray(x)
+    assert x.dtype == np.uint64
+    return x
+
+
+def _ptr(x):
+    return x.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    """One ta_ctx: one CUDA device, its streams and staging buffers."""
+
+    def __init__(self, device=None):
+        self._lib = _ffi.load()
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+        h = C.c_void_p()
+        rc = self._lib.ta_init(int(device), C.byref(h))
+        if rc != 0:
+            raise TripleAccelError(rc, "ta_init(device=%d) failed; this library has no CPU fallback" % device)
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ta_shutdown(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- error mapping --------------------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc == 0:
+            return
+        if rc == _ffi.TA_ERR_LEN_MISMATCH:  # the crate panics (src/hamming.rs:38, 318)
+            raise AssertionError("hamming: a.len() != b.len()")
+        if rc == _ffi.TA_ERR_BAD_COSTS:  # src/levenshtein.rs:44-52, 69
+            raise AssertionError("invalid EditCosts")
+        raise TripleAccelError(rc, self._lib.ta_last_error(self._h).decode() if rc == _ffi.TA_ERR_CUDA else "")
+
+    @property
+    def launch_count(self):
+        return int(self._lib.ta_launch_count(self._h))
+
+    # ---- host-buffer batch API ------------------------------------------------------------------------------
+    def hamming_batch(self, a, a_off, b, b_off, out=None):
+        a, b, a_off, b_off = _u8(a), _u8(b), _u64(a_off), _u64(b_off)
+        n = len(a_off) - 1
+        out = np.empty(n, np.uint32) if out is None else out
+        self._check(self._lib.ta_hamming_batch(self._h, _ptr(a), _ptr(a_off), _ptr(b), _ptr(b_off), n, _ptr(out)))
+        return out
+
+    def levenshtein_k_batch(self, a, a_off, b, b_off, k, costs=LEVENSHTEIN_COSTS, out=None):
+        """out[i] = distance if <= k else TA_NONE (0xFFFFFFFF)."""
+        a, b, a_off, b_off = _u8(a), _u8(b), _u64(a_off), _u64(b_off)
+        n = len(a_off) - 1
+        out = np.empty(n, np.uint32) if out is None else out
+        self._check(self._lib.ta_levenshtein_k_batch(self._h, _ptr(a), _ptr(a_off), _ptr(b), _ptr(b_off), n,
+                                                     int(k) & 0xFFFFFFFF, _as_costs(costs)._c(), _ptr(out)))
+        return out
+
+    def levenshtein_exp_batch(self, a, a_off, b, b_off, costs=LEVENSHTEIN_COSTS, out=None):
+        a, b, a_off, b_off = _u8(a), _u8(b), _u64(a_off), _u64(b_off)
+        n = len(a_off) - 1
+        out = np.empty(n, np.uint32) if out is None else out
+        self._check(self._lib.ta_levenshtein_exp_batch(self._h, _ptr(a), _ptr(a_off), _ptr(b), _ptr(b_off), n,
+                                                       _as_costs(costs)._c(), _ptr(out)))
+        return out
+
+    def levenshtein_search_batch(self, needle, hay, hay_off, k, search_type=SearchType.All,
+                                 costs=LEVENSHTEIN_COSTS, anchored=False):
+        """Returns (matches[total, 3] uint64 = start,end,k ; match_off[n+1])."""
+        needle, hay, hay_off = _u8(needle), _u8(hay), _u64(hay_off)
+        n = len(hay_off) - 1
+        mp, op = C.POINTER(ta_match)(), C.POINTER(C.c_uint64)()
+        rc = self._lib.ta_levenshtein_search_batch(self._h, _ptr(needle), len(needle), _ptr(hay), _ptr(hay_off), n,
+                                                   int(k) & 0xFFFFFFFF, int(search_type), _as_costs(costs)._c(),
+                                                   int(bool(anchored)), C.byref(mp), C.byref(op))
+        self._check(rc)
+        try:
+            moff = np.ctypeslib.as_array(op, shape=(n + 1,)).copy()
+            total = int(moff[n])
+            arr = np.zeros((total, 3), np.uint64)
+            if total:
+                raw = np.ctypeslib.as_array(C.cast(mp, C.POINTER(C.c_uint64)), shape=(total, 3))
+                arr[:, 0], arr[:, 1] = raw[:, 0], raw[:, 1]
+                arr[:, 2] = raw[:, 2] & np.uint64(0xFFFFFFFF)
+        finally:
+            self._lib.ta_free(mp)
+            self._lib.ta_free(op)
+        return arr, moff
+
+    # ---- device-resident API (torch tensors on this engine's device) ----------------------------------------
+    def _stream(self, stream):
+        if stream is not None:
+            return C.c_void_p(int(stream))
+        import torch
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def hamming_batch_dev(self, a, a_off, b, b_off, out, stream=None):
+        n = a_off.numel() - 1
+        self._check(self._lib.ta_hamming_batch_dev(self._h, a.data_ptr(), a_off.data_ptr(), b.data_ptr(),
+                                                   b_off.data_ptr(), n, out.data_ptr(), self._stream(stream)))
+        return out
+
+    def levenshtein_k_batch_dev(self, a, a_off, b, b_off, k, costs, max_len, out, stream=None):
+        n = a_off.numel() - 1
+        self._check(self._lib.ta_levenshtein_k_batch_dev(self._h, a.data_ptr(), a_off.data_ptr(), b.data_ptr(),
+                                                         b_off.data_ptr(), n, int(k) & 0xFFFFFFFF,
+                                                         _as_costs(costs)._c(), int(max_len), out.data_ptr(),
+                                                         self._stream(stream)))
+        return out
+
+    def dev_status(self, stream=None):
+        self._check(self._lib.ta_dev_status(self._h, self._stream(stream)))
+
+    # ---- the crate's single-pair functions ------------------------------------------------------------------
+    def hamming(self, a, b):
+        a, b = bytes(a), bytes(b)
+        out = C.c_uint32()
+        self._check(self._lib.ta_hamming(self._h, a, len(a), b, len(b), C.byref(out)))
+        return out.value
+
+    def levenshtein_simd_k_with_opts(self, a, b, k, trace_on=False, costs=LEVENSHTEIN_COSTS):
+        """src/levenshtein.rs:714-720: None, or (distance, None).  trace_on=True is not built yet."""
+        if trace_on:
+            raise NotImplementedError("traceback (trace_on=true) is a 'next' row of the scope table")
+        a, b = bytes(a), bytes(b)
+        out = C.c_uint32()
+        self._check(self._lib.ta_levenshtein_simd_k_with_opts(self._h, a, len(a), b, len(b), int(k) & 0xFFFFFFFF,
+                                                              _as_costs(costs)._c(), C.byref(out)))
+        return None if out.value == TA_NONE else (out.value, None)
+
+    def levenshtein_simd_k(self, a, b, k):  # src/levenshtein.rs:677-684
+        r = self.levenshtein_simd_k_with_opts(a, b, k, False, LEVENSHTEIN_COSTS)
+        return None if r is None else r[0]
+
+    def levenshtein(self, a, b):  # src/levenshtein.rs:1397-1399
+        return self.levenshtein_simd_k(a, b, 0xFFFFFFFF)
+
+    def rdamerau(self, a, b):  # src/levenshtein.rs:1419-1423
+        return self.levenshtein_simd_k_with_opts(a, b, 0xFFFFFFFF, False, RDAMERAU_COSTS)[0]
+
+    def levenshtein_exp_with_opts(self, a, b, trace_on=False, costs=LEVENSHTEIN_COSTS):  # :1480-1494
+        if trace_on:
+            raise NotImplementedError("traceback (trace_on=true) is a 'next' row of the scope table")
+        a, b = bytes(a), bytes(b)
+        out = C.c_uint32()
+        self._check(self._lib.ta_levenshtein_exp_with_opts(self._h, a, len(a), b, len(b), _as_costs(costs)._c(),
+                                                           C.byref(out)))
+        return out.value, None
+
+    def levenshtein_exp(self, a, b):  # src/levenshtein.rs:1445-1454
+        return self.levenshtein_exp_with_opts(a, b, False, LEVENSHTEIN_COSTS)[0]
+
+    def rdamerau_exp(self, a, b):  # src/levenshtein.rs:1516-1526
+        return self.levenshtein_exp_with_opts(a, b, False, RDAMERAU_COSTS)[0]
+
+    def levenshtein_search_simd_with_opts(self, needle, haystack, k, search_type=SearchType.All,
+                                          costs=LEVENSHTEIN_COSTS, anchored=False):
+        """src/levenshtein.rs:1911-1918.  Returns a list of Match (the crate returns a lazy iterator)."""
+        haystack = _u8(haystack)
+        off = np.array([0, len(haystack)], np.uint64)
+        arr, _ = self.levenshtein_search_batch(needle, haystack, off, k, search_type, costs, anchored)
+        return [Match(int(s), int(e), int(c)) for s, e, c in arr]
+
+    def levenshtein_search_simd(self, needle, haystack):  # src/levenshtein.rs:1866-1878
+        k = self._lib.ta_search_default_k(len(bytes(needle)))
+        return self.levenshtein_search_simd_with_opts(needle, haystack, k, SearchType.Best, LEVENSHTEIN_COSTS, False)
+
+    levenshtein_search = levenshtein_search_simd  # src/levenshtein.rs:2508-2513
+
+
+_default = None
+
+
+def default_engine():
+    global _default
+    if _default is None:
+        _default = Engine()
+    return _default
+
+
+def _forward(name):
+    def f(*args, **kw):
+        return getattr(default_engine(), name)(*args, **kw)
+    f.__name__ = name
+    f.__doc__ = getattr(Engine, name).__doc__
+    return f
+
+
+hamming = _forward("hamming")
+levenshtein = _forward("levenshtein")
+rdamerau = _forward("rdamerau")
+levenshtein_exp = _forward("levenshtein_exp")
+levenshtein_exp_with_opts = _forward("levenshtein_exp_with_opts")
+rdamerau_exp = _forward("rdamerau_exp")
+levenshtein_simd_k = _forward("levenshtein_simd_k")
+levenshtein_simd_k_with_opts = _forward("levenshtein_simd_k_with_opts")
+levenshtein_search = _forward("levenshtein_search")
+levenshtein_search_simd = _forward("levenshtein_search_simd")
+levenshtein_search_simd_with_opts = _forward("levenshtein_search_simd_with_opts")
+hamming_batch = _forward("hamming_batch")
+levenshtein_k_batch = _forward("levenshtein_k_batch")
+levenshtein_exp_batch = _forward("levenshtein_exp_batch")
+levenshtein_search_batch = _forward("levenshtein_search_batch")

@@ -1,0 +1,382 @@
+// api.cu -- C-ABI host layer of libtriple_accel_b200.so (see include/triple_accel_b200.h).
+// Device memory, streams and staging live in ta_ctx; every compute entry point runs CUDA kernels and fails with
+// TA_ERR_CUDA when no device is usable -- there is no CPU path in this library.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "ta_common.cuh"
+
+int ta_cuda_fail(ta_ctx *ctx, cudaError_t e, const char *what) {
+    if (ctx) {
+        char buf[512];
+        snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+        ctx->last_error = buf;
+    }
+    (void)cudaGetLastError();  // clear the sticky-less error state
+    return TA_ERR_CUDA;
+}
+
+int ta_dev_reserve(ta_ctx *ctx, DevBuf &b, size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (bytes <= b.cap && b.p) return TA_OK;
+    if (b.p) TA_CUDA(ctx, cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 4 + 256;  // headroom: batches of similar size do not reallocate
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        want = bytes + 256;
+        TA_CUDA(ctx, cudaMalloc(&b.p, want));
+    }
+    b.cap = want;
+    return TA_OK;
+}
+
+int ta_pin_reserve(ta_ctx *ctx, DevBuf &b, size_t bytes) {
+    if (bytes <= b.cap && b.p) return TA_OK;
+    if (b.p) TA_CUDA(ctx, cudaFreeHost(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    TA_CUDA(ctx, cudaMallocHost(&b.p, bytes + 256));
+    b.cap = bytes + 256;
+    return TA_OK;
+}
+
+extern "C" {
+
+int ta_abi_version(void) { return TA_ABI_VERSION; }
+
+const char *ta_strerror(int code) {
+    switch (code) {
+        case TA_OK: return "ok";
+        case TA_ERR_CUDA: return "CUDA error (see ta_last_error)";
+        case TA_ERR_LEN_MISMATCH: return "hamming: strings of a pair differ in length";
+        case TA_ERR_BAD_COSTS: return "invalid EditCosts";
+        case TA_ERR_BAD_ARG: return "bad argument";
+        case TA_ERR_TOO_LARGE: return "input too large for this build";
+        case TA_ERR_NOMEM: return "out of host memory";
+        default: return "unknown error";
+    }
+}
+
+int ta_init(int device, ta_ctx **out) {
+    if (!out) return TA_ERR_BAD_ARG;
+    *out = nullptr;
+    ta_ctx *ctx = new (std::nothrow) ta_ctx();
+    if (!ctx) return TA_ERR_NOMEM;
+    ctx->device = device;
+    auto fail = [&](cudaError_t e, const char *what) {
+        ta_cuda_fail(ctx, e, what);
+        fprintf(stderr, "triple_accel_b200: %s\n", ctx->last_error.c_str());
+        delete ctx;
+        return TA_ERR_CUDA;
+    };
+    cudaError_t e;
+    int count = 0;
+    if ((e = cudaGetDeviceCount(&count)) != cudaSuccess) return fail(e, "cudaGetDeviceCount");
+    if (device < 0 || device >= count) return fail(cudaErrorInvalidDevice, "ta_init(device)");
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(e, "cudaSetDevice");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(e, "cudaGetDeviceProperties");
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "stream");
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "stream");
+    for (int i = 0; i < 2; i++) {
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming)) != cudaSuccess) return fail(e, "event");
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming)) != cudaSuccess) return fail(e, "event");
+    }
+    if ((e = cudaMalloc((void **)&ctx->d_flags, 64 * sizeof(uint32_t))) != cudaSuccess) return fail(e, "cudaMalloc");
+    if ((e = cudaMemset(ctx->d_flags, 0, 64 * sizeof(uint32_t))) != cudaSuccess) return fail(e, "cudaMemset");
+    if ((e = cudaMallocHost((void **)&ctx->h_flags, 64 * sizeof(uint32_t))) != cudaSuccess) return fail(e, "cudaMallocHost");
+    memset(ctx->h_flags, 0, 64 * sizeof(uint32_t));
+    *out = ctx;
+    return TA_OK;
+}
+
+void ta_shutdown(ta_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    DevBuf *dev[] = {&ctx->d_a[0], &ctx->d_a[1], &ctx->d_b[0], &ctx->d_b[1], &ctx->d_aoff[0], &ctx->d_aoff[1],
+                     &ctx->d_boff[0], &ctx->d_boff[1], &ctx->d_out[0], &ctx->d_out[1], &ctx->d_work[0],
+                     &ctx->d_work[1], &ctx->d_work[2], &ctx->d_work[3]};
+    for (DevBuf *b : dev)
+        if (b->p) cudaFree(b->p);
+    for (DevBuf &b : ctx->h_pin)
+        if (b.p) cudaFreeHost(b.p);
+    if (ctx->d_flags) cudaFree(ctx->d_flags);
+    if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
+        if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
+    }
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    delete ctx;
+}
+
+const char *ta_last_error(ta_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+int ta_device(ta_ctx *ctx) { return ctx ? ctx->device : -1; }
+uint64_t ta_launch_count(ta_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+void *ta_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void ta_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+void ta_free(void *p) { free(p); }
+
+int ta_costs_valid(ta_costs c) {  // EditCosts::new, reference src/levenshtein.rs:44-52
+    if (c.mismatch == 0 || c.gap == 0) return 0;
+    if (c.transpose != 0) {
+        if ((c.transpose >> 1) >= c.mismatch) return 0;
+        if ((c.transpose >> 1) >= c.gap) return 0;
+    }
+    return 1;
+}
+
+int ta_costs_valid_search(ta_costs c) {  // check_search, reference src/levenshtein.rs:67-71
+    if (!ta_costs_valid(c)) return 0;
+    if (c.transpose != 0) {
+        const unsigned lim = (unsigned)c.start_gap + (unsigned)c.gap;
+        if (lim > 255 || c.transpose > lim) return 0;  // the reference adds in u8: overflow is a panic in debug
+    }
+    return 1;
+}
+
+uint32_t ta_search_default_k(size_t needle_len) {  // reference src/levenshtein.rs:1873
+    return (uint32_t)(needle_len >> 1) + ((uint32_t)needle_len & 1u);
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------
+// host-buffer batch plumbing
+namespace {
+
+struct BatchStats {
+    uint64_t a_bytes = 0, b_bytes = 0;
+    uint32_t max_len = 0;
+};
+
+// validates monotone offsets, computes totals; returns TA_OK or an error
+int scan_offsets(const uint64_t *a_off, const uint64_t *b_off, size_t n, bool need_equal, BatchStats &st) {
+    uint64_t max_len = 0;
+    bool mismatch = false;
+    for (size_t i = 0; i < n; i++) {
+        if (a_off[i + 1] < a_off[i] || b_off[i + 1] < b_off[i]) return TA_ERR_BAD_ARG;
+        const uint64_t la = a_off[i + 1] - a_off[i], lb = b_off[i + 1] - b_off[i];
+        max_len = std::max(max_len, std::max(la, lb));
+        mismatch |= la != lb;
+    }
+    if (max_len > TA_MAX_STRING_LEN) return TA_ERR_TOO_LARGE;
+    st.a_bytes = a_off[n] - a_off[0];
+    st.b_bytes = b_off[n] - b_off[0];
+    st.max_len = (uint32_t)max_len;
+    if (need_equal && mismatch) return TA_ERR_LEN_MISMATCH;
+    return TA_OK;
+}
+
+// Upload one CSR side: the byte range [off[0], off[n]) and the n+1 offsets (kept as-is; kernels index bytes
+// relative to `base - off[0]`).  Returns device pointers such that dev_bytes + off[i] is string i.
+int upload_side(ta_ctx *ctx, int slot, bool is_a, const uint8_t *bytes, const uint64_t *off, size_t n,
+                const uint8_t **dev_bytes, const uint64_t **dev_off, cudaStream_t st) {
+    DevBuf &db = is_a ? ctx->d_a[slot] : ctx->d_b[slot];
+    DevBuf &dofs = is_a ? ctx->d_aoff[slot] : ctx->d_boff[slot];
+    const uint64_t lo = off[0], hi = off[n];
+    // keep the device copy congruent to the host buffer modulo 16 so aligned strings stay aligned
+    const size_t skew = (size_t)(lo & 15);
+    int rc;
+    if ((rc = ta_dev_reserve(ctx, db, skew + (hi - lo) + 64)) != TA_OK) return rc;
+    if ((rc = ta_dev_reserve(ctx, dofs, (n + 1) * sizeof(uint64_t))) != TA_OK) return rc;
+    if (hi > lo) TA_CUDA(ctx, cudaMemcpyAsync((uint8_t *)db.p + skew, bytes + lo, hi - lo, cudaMemcpyHostToDevice, st));
+    TA_CUDA(ctx, cudaMemcpyAsync(dofs.p, off, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    *dev_bytes = (const uint8_t *)db.p + skew - lo;  // virtual base: + off[i] lands inside the buffer
+    *dev_off = (const uint64_t *)dofs.p;
+    return TA_OK;
+}
+
+// gather the indices of pairs whose result is still TA_NONE (exponential-k driver)
+__global__ void collect_none_kernel(const uint32_t *__restrict__ out, const uint32_t *__restrict__ idx_in, size_t n,
+                                    uint32_t *__restrict__ idx_out, uint32_t *__restrict__ counter) {
+    for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < n; w += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t pair = idx_in ? idx_in[w] : (uint32_t)w;
+        if (out[pair] == TA_NONE) idx_out[atomicAdd(counter, 1u)] = pair;
+    }
+}
+
+int check_costs(ta_costs c) { return ta_costs_valid(c) ? TA_OK : TA_ERR_BAD_COSTS; }
+
+// exponential search on device-resident data: k = 30, 60, ... over the pairs that are still TA_NONE
+// (reference src/levenshtein.rs:1445-1454, 1480-1494, 1516-1526)
+int exp_rounds_dev(ta_ctx *ctx, const uint8_t *da, const uint64_t *da_off, const uint8_t *db, const uint64_t *db_off,
+                   size_t n, ta_costs costs, uint32_t max_len, uint32_t *d_out, cudaStream_t st) {
+    int rc;
+    uint32_t k = 30;
+    if ((rc = ta_launch_lev_band(ctx, da, da_off, db, db_off, n, nullptr, k, costs, max_len, d_out, st)) != TA_OK) return rc;
+    if ((rc = ta_dev_reserve(ctx, ctx->d_work[0], n * sizeof(uint32_t))) != TA_OK) return rc;
+    if ((rc = ta_dev_reserve(ctx, ctx->d_work[1], n * sizeof(uint32_t))) != TA_OK) return rc;
+    uint32_t *idx[2] = {(uint32_t *)ctx->d_work[0].p, (uint32_t *)ctx->d_work[1].p};
+    const uint32_t *cur = nullptr;
+    size_t cur_n = n;
+    int flip = 0;
+    uint32_t *counter = ctx->d_flags + 1;
+    for (;;) {
+        TA_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(uint32_t), st));
+        const unsigned blocks = (unsigned)std::min<size_t>((cur_n + 255) / 256, (size_t)ctx->sm_count * 8);
+        collect_none_kernel<<<blocks, 256, 0, st>>>(d_out, cur, cur_n, idx[flip], counter);
+        ctx->launches++;
+        TA_CUDA(ctx, cudaGetLastError());
+        TA_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags + 1, counter, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        TA_CUDA(ctx, cudaStreamSynchronize(st));
+        const uint32_t remaining = ctx->h_flags[1];
+        if (remaining == 0) break;
+        if (k > 0x7FFFFFFFu) return TA_ERR_TOO_LARGE;  // cannot happen: k exceeds every cost bound long before
+        k *= 2;
+        cur = idx[flip];
+        cur_n = remaining;
+        flip ^= 1;
+        if ((rc = ta_launch_lev_band(ctx, da, da_off, db, db_off, cur_n, cur, k, costs, max_len, d_out, st)) != TA_OK)
+            return rc;
+    }
+    return TA_OK;
+}
+
+enum Op { OP_HAMMING, OP_LEV_K, OP_LEV_EXP };
+
+int run_pairs(ta_ctx *ctx, Op op, const uint8_t *a, const uint64_t *a_off, const uint8_t *b, const uint64_t *b_off,
+              size_t n, uint32_t k, ta_costs costs, uint32_t *out) {
+    if (!ctx) return TA_ERR_BAD_ARG;
+    if (n == 0) return TA_OK;
+    if (!a_off || !b_off || !out) return TA_ERR_BAD_ARG;
+    if (n > 0xFFFFFFF0ull) return TA_ERR_TOO_LARGE;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    TA_CUDA(ctx, cudaSetDevice(ctx->device));
+    BatchStats bs;
+    int rc = scan_offsets(a_off, b_off, n, op == OP_HAMMING, bs);
+    if (rc != TA_OK) return rc;
+    if ((bs.a_bytes && !a) || (bs.b_bytes && !b)) return TA_ERR_BAD_ARG;
+    cudaStream_t st = ctx->stream;
+    const uint8_t *da, *db;
+    const uint64_t *da_off, *db_off;
+    if ((rc = upload_side(ctx, 0, true, a, a_off, n, &da, &da_off, st)) != TA_OK) return rc;
+    if ((rc = upload_side(ctx, 0, false, b, b_off, n, &db, &db_off, st)) != TA_OK) return rc;
+    if ((rc = ta_dev_reserve(ctx, ctx->d_out[0], n * sizeof(uint32_t))) != TA_OK) return rc;
+    uint32_t *d_out = (uint32_t *)ctx->d_out[0].p;
+    switch (op) {
+        case OP_HAMMING: {
+            const uint32_t avg = (uint32_t)std::min<uint64_t>(bs.a_bytes / n, 0xFFFFFFFFull);
+            TA_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, sizeof(uint32_t), st));
+            rc = ta_launch_hamming(ctx, da, da_off, db, db_off, n, avg, d_out, ctx->d_flags, st);
+            break;
+        }
+        case OP_LEV_K:
+            rc = ta_launch_lev_band(ctx, da, da_off, db, db_off, n, nullptr, k, costs, bs.max_len, d_out, st);
+            break;
+        case OP_LEV_EXP:
+            rc = exp_rounds_dev(ctx, da, da_off, db, db_off, n, costs, bs.max_len, d_out, st);
+            break;
+    }
+    if (rc != TA_OK) {
+        cudaStreamSynchronize(st);
+        return rc;
+    }
+    TA_CUDA(ctx, cudaMemcpyAsync(out, d_out, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    TA_CUDA(ctx, cudaStreamSynchronize(st));
+    return TA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ta_hamming_batch(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b, const uint64_t *b_off,
+                     size_t n, uint32_t *out) {
+    ta_costs none = {1, 1, 0, 0};
+    return run_pairs(ctx, OP_HAMMING, a, a_off, b, b_off, n, 0, none, out);
+}
+
+int ta_levenshtein_k_batch(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b,
+                           const uint64_t *b_off, size_t n, uint32_t k, ta_costs costs, uint32_t *out) {
+    int rc = check_costs(costs);
+    if (rc != TA_OK) return rc;
+    return run_pairs(ctx, OP_LEV_K, a, a_off, b, b_off, n, k, costs, out);
+}
+
+int ta_levenshtein_exp_batch(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b,
+                             const uint64_t *b_off, size_t n, ta_costs costs, uint32_t *out) {
+    int rc = check_costs(costs);
+    if (rc != TA_OK) return rc;
+    return run_pairs(ctx, OP_LEV_EXP, a, a_off, b, b_off, n, 0, costs, out);
+}
+
+int ta_hamming_batch_dev(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b,
+                         const uint64_t *b_off, size_t n, uint32_t *out, void *stream) {
+    if (!ctx) return TA_ERR_BAD_ARG;
+    if (n == 0) return TA_OK;
+    if (!a_off || !b_off || !out) return TA_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    TA_CUDA(ctx, cudaSetDevice(ctx->device));
+    // mean length is unknown without reading device offsets; 64-byte strings and up use >= 4 lanes per pair
+    return ta_launch_hamming(ctx, a, a_off, b, b_off, n, 64, out, ctx->d_flags, (cudaStream_t)stream);
+}
+
+int ta_levenshtein_k_batch_dev(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b,
+                               const uint64_t *b_off, size_t n, uint32_t k, ta_costs costs, uint32_t max_len,
+                               uint32_t *out, void *stream) {
+    if (!ctx) return TA_ERR_BAD_ARG;
+    int rc = check_costs(costs);
+    if (rc != TA_OK) return rc;
+    if (n == 0) return TA_OK;
+    if (!a_off || !b_off || !out) return TA_ERR_BAD_ARG;
+    if (max_len > TA_MAX_STRING_LEN) return TA_ERR_TOO_LARGE;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    TA_CUDA(ctx, cudaSetDevice(ctx->device));
+    return ta_launch_lev_band(ctx, a, a_off, b, b_off, n, nullptr, k, costs, max_len, out, (cudaStream_t)stream);
+}
+
+int ta_dev_status(ta_ctx *ctx, void *stream) {
+    if (!ctx) return TA_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    TA_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    TA_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    TA_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, sizeof(uint32_t), st));
+    TA_CUDA(ctx, cudaStreamSynchronize(st));
+    const uint32_t f = ctx->h_flags[0];
+    return f ? -(int)f : TA_OK;
+}
+
+int ta_hamming(ta_ctx *ctx, const uint8_t *a, size_t a_len, const uint8_t *b, size_t b_len, uint32_t *out) {
+    const uint64_t ao[2] = {0, a_len}, bo[2] = {0, b_len};
+    return ta_hamming_batch(ctx, a, ao, b, bo, 1, out);
+}
+
+int ta_levenshtein_simd_k_with_opts(ta_ctx *ctx, const uint8_t *a, size_t a_len, const uint8_t *b, size_t b_len,
+                                    uint32_t k, ta_costs costs, uint32_t *out) {
+    const uint64_t ao[2] = {0, a_len}, bo[2] = {0, b_len};
+    return ta_levenshtein_k_batch(ctx, a, ao, b, bo, 1, k, costs, out);
+}
+
+int ta_levenshtein_exp_with_opts(ta_ctx *ctx, const uint8_t *a, size_t a_len, const uint8_t *b, size_t b_len,
+                                 ta_costs costs, uint32_t *out) {
+    const uint64_t ao[2] = {0, a_len}, bo[2] = {0, b_len};
+    return ta_levenshtein_exp_batch(ctx, a, ao, b, bo, 1, costs, out);
+}
+
+// search entry point lives in search.cu
+
+}  // extern "C"

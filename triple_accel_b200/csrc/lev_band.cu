@@ -1,0 +1,320 @@
+// lev_band.cu -- general k-banded anti-diagonal edit-distance DP for sm_100a (all EditCosts, any k).
+//
+// Contract (reference src/levenshtein.rs:376-545 scalar, 714-827 SIMD entry): for each pair, the weighted edit
+// distance d under EditCosts {mismatch, gap, start_gap (affine), transpose (restricted Damerau)} if d <= k,
+// else TA_NONE.  `max_k`/`unit_k` clamps and the early None follow src/levenshtein.rs:400-430.
+//
+// Design (not a port of the reference's AVX2 lanes): a group of G lanes (G = 8/16/32, several pairs per warp for
+// narrow bands) owns one pair.  Lane t holds C cells of the current anti-diagonal s = i + j in registers; cell
+// ci = t*C + c sits on diagonal d = dlo + 2*ci + p with p = (s - dlo) & 1, so consecutive anti-diagonals
+// alternate between "even" and "odd" diagonals and only ceil(W/2) cells are live per step (W = band width).
+// The band is Ukkonen's: only diagonals a path of cost <= max_k can touch,
+//     [-e, diff + e],  e = (max_k - 2*start_gap - diff*gap) / (2*gap),
+// which is about half the reference's [-unit_k, unit_k] band and gives identical answers for d <= max_k.
+// Per step each lane needs one neighbour value: on p == 0 steps the "left" cell (diagonal d-1) comes from lane
+// t-1 (__shfl_up_sync), on p == 1 steps the "up" cell (d+1) from lane t+1 (__shfl_down_sync).  Affine gaps are
+// carried as the sender-side pre-minimised values outH = min(D + open, H + gap), outV likewise, so a step costs
+// one shuffle whatever the cost model; the transposition test needs the neighbours' match flags, which ride in
+// bit 0 of the shuffled word.  Strings are staged into shared memory with 16-byte cp.async (LDGSTS) vectors.
+#include "ta_common.cuh"
+
+namespace {
+
+struct BandArgs {
+    const uint8_t *a;
+    const uint64_t *a_off;
+    const uint8_t *b;
+    const uint64_t *b_off;
+    const uint32_t *idx;  // optional indirection
+    size_t n;
+    uint32_t k;
+    uint32_t mism, gap, sgap, tcost;
+    uint32_t slot;  // shared-memory bytes reserved per string (SMEM variants)
+    uint32_t *out;
+};
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t umin3(uint32_t x, uint32_t y, uint32_t z) { return min(min(x, y), z); }
+
+template <int G, int C, bool AFFINE, bool TRANS, bool SMEM>
+__global__ void __launch_bounds__(128) lev_band_kernel(const BandArgs args) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    constexpr int GROUPS = 128 / G;
+    const int grp = threadIdx.x / G;
+    const int t = threadIdx.x % G;  // lane within the group
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (((threadIdx.x & 31) / G) * G));
+
+    const size_t w = (size_t)blockIdx.x * GROUPS + grp;
+    if (w >= args.n) return;  // whole group leaves together (shuffles below use the group mask)
+    const size_t pair = args.idx ? (size_t)args.idx[w] : w;
+
+    // ---- per-pair setup (every lane computes the same scalars) --------------------------------------------------
+    const uint64_t a0 = args.a_off[pair], a1 = args.a_off[pair + 1];
+    const uint64_t b0 = args.b_off[pair], b1 = args.b_off[pair + 1];
+    const bool swap = (a1 - a0) > (b1 - b0);  // src/levenshtein.rs:386 -- "a" is the shorter string
+    const uint8_t *ga = swap ? args.b + b0 : args.a + a0;
+    const uint8_t *gb = swap ? args.a + a0 : args.b + b0;
+    const int m = (int)(swap ? (b1 - b0) : (a1 - a0));
+    const int n = (int)(swap ? (a1 - a0) : (b1 - b0));
+    const uint32_t mism = args.mism, gap = args.gap, sgap = args.sgap, tcost = args.tcost;
+    const uint32_t diff = (uint32_t)(n - m);
+
+    // src/levenshtein.rs:400-426
+    uint32_t max_k = min((uint32_t)m * mism, ((uint32_t)m << 1) * gap + (m == 0 ? 0u : sgap + (n == m ? sgap : 0u)));
+    max_k = min(args.k, max_k + diff * gap + (n == m ? 0u : sgap));
+    const uint32_t unit_k = (max_k > sgap ? max_k - sgap : 0u) / gap;
+    if (diff > unit_k) {  // src/levenshtein.rs:428-430
+        if (t == 0) args.out[pair] = TA_NONE;
+        return;
+    }
+    if (m == 0) {  // D(0, n) = n*gap + start_gap
+        if (t == 0) {
+            const uint32_t d = (uint32_t)n * gap + (n ? sgap : 0u);
+            args.out[pair] = d <= max_k ? d : TA_NONE;
+        }
+        return;
+    }
+    // Ukkonen band; one extra diagonal each side when transpositions need the neighbours' match flags
+    const uint32_t spare = max_k >= 2 * sgap + diff * gap ? max_k - 2 * sgap - diff * gap : 0u;
+    const int e = (int)(spare / (2 * gap)) + (TRANS ? 1 : 0);
+    const int dlo = -e;
+    // host guarantees diff + 2e + 1 <= 2*G*C
+
+    // ---- stage both strings into shared memory (16-byte cp.async vectors on the aligned-down addresses) --------
+    const uint8_t *sa, *sb;
+    if (SMEM) {
+        uint8_t *slot_a = smem + (size_t)grp * 2 * args.slot;
+        uint8_t *slot_b = slot_a + args.slot;
+        const uintptr_t ua = (uintptr_t)ga, ub = (uintptr_t)gb;
+        const uint8_t *ga16 = (const uint8_t *)(ua & ~(uintptr_t)15), *gb16 = (const uint8_t *)(ub & ~(uintptr_t)15);
+        const int sha = (int)(ua & 15), shb = (int)(ub & 15);
+        const int na = (sha + m + 15) >> 4, nb = (shb + n + 15) >> 4;
+        for (int q = t; q < na; q += G) cp_async16(slot_a + 16 * q, ga16 + 16 * q);
+        for (int q = t; q < nb; q += G) cp_async16(slot_b + 16 * q, gb16 + 16 * q);
+        cp_async_wait_all();
+        __syncwarp(gmask);
+        sa = slot_a + sha;
+        sb = slot_b + shb;
+    } else {
+        sa = ga;
+        sb = gb;
+    }
+    auto A = [&](int i) -> uint32_t { return sa[__vimin_s32_relu(i, m - 1)]; };  // clamped: out-of-matrix cells
+    auto B = [&](int j) -> uint32_t { return sb[__vimin_s32_relu(j, n - 1)]; };  // never reach the result
+
+    const uint32_t open = sgap + gap;
+
+    // ---- DP state --------------------------------------------------------------------------------------------
+    uint32_t D1[C], D2[C], D3[C], D4[C];  // this lane's cells on anti-diagonals s-1 .. s-4
+    uint32_t oH[C], oV[C];                // pre-minimised gap candidates offered to the right / lower neighbour
+    uint32_t mt[C];                       // match flag of the s-1 cells (TRANS)
+    uint32_t ca[C], cb[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        D1[c] = D2[c] = D3[c] = D4[c] = TA_INF;
+        oH[c] = oV[c] = TA_INF;
+        mt[c] = 0;
+    }
+
+    // first anti-diagonal processed has (s - dlo) even
+    int s = -((-dlo) & 1);
+    // coordinates of cell c == 0 on the upcoming p == 0 step: i = (s - d)/2, j = (s + d)/2, d = dlo + 2*t*C
+    int i0 = (s - dlo) / 2 - t * C;
+    int j0 = (s + dlo) / 2 + t * C;  // (s + dlo) is even, may be negative: exact division
+#pragma unroll
+    for (int c = 0; c < C; c++) cb[c] = B(j0 + c - 1);
+#pragma unroll
+    for (int c = 0; c < C; c++) ca[c] = A(i0 - c - 1 - 1);  // the p == 0 step below shifts these by one first
+
+    const int s_end = m + n;
+    // steps with s <= s_bnd may touch the first row / column and need the boundary override
+    const int s_bnd = max(-dlo, dlo + 2 * G * C);
+
+    auto step = [&](const int p, const bool boundary) {
+        // p == 0: i advanced by one since the previous step; p == 1: j advanced by one
+        uint32_t rH, rV;
+        if (p == 0) {
+#pragma unroll
+            for (int c = C - 1; c > 0; c--) ca[c] = ca[c - 1];
+            ca[0] = A(i0 - 1);
+            uint32_t send = AFFINE ? oH[C - 1] : oV[C - 1];
+            if (TRANS) send = (min(send, TA_INF) << 1) | mt[C - 1];
+            rH = __shfl_up_sync(gmask, send, 1, G);
+            if (t == 0) rH = TRANS ? (TA_INF << 1) : TA_INF;
+            rV = 0;
+        } else {
+#pragma unroll
+            for (int c = 0; c < C - 1; c++) cb[c] = cb[c + 1];
+            cb[C - 1] = B(j0 + C - 1 - 1);
+            uint32_t send = oV[0];
+            if (TRANS) send = (min(send, TA_INF) << 1) | mt[0];
+            rV = __shfl_down_sync(gmask, send, 1, G);
+            if (t == G - 1) rV = TRANS ? (TA_INF << 1) : TA_INF;
+            rH = 0;
+        }
+        uint32_t rflag = 0;
+        if (TRANS) {
+            if (p == 0) {
+                rflag = rH & 1;
+                rH >>= 1;
+            } else {
+                rflag = rV & 1;
+                rV >>= 1;
+            }
+        }
+        uint32_t nD[C], nH[C], nV[C], nM[C];
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            uint32_t h, v, mL = 0, mU = 0;
+            if (p == 0) {
+                h = (c == 0) ? rH : (AFFINE ? oH[c - 1] : oV[c - 1]);
+                v = oV[c];
+                if (TRANS) {
+                    mL = (c == 0) ? rflag : mt[c - 1];
+                    mU = mt[c];
+                }
+            } else {
+                h = AFFINE ? oH[c] : oV[c];
+                v = (c == C - 1) ? rV : oV[c + 1];
+                if (TRANS) {
+                    mL = mt[c];
+                    mU = (c == C - 1) ? rflag : mt[c + 1];
+                }
+            }
+            const uint32_t eq = ca[c] == cb[c];
+            uint32_t d = umin3(D2[c] + (eq ? 0u : mism), h, v);
+            if (TRANS) {
+                const uint32_t tr = D4[c] + tcost;
+                if (mL & mU) d = min(d, tr);
+            }
+            uint32_t hh = h, vv = v;
+            if (boundary) {
+                const int i = i0 - c, j = j0 + c;
+                const bool bi = (i == 0) & (j >= 0), bj = (j == 0) & (i >= 0);
+                if (bi | bj) {
+                    const int q = bi ? j : i;
+                    d = (uint32_t)q * gap + (q > 0 ? sgap : 0u);
+                    hh = vv = TA_INF;
+                }
+            }
+            nD[c] = d;
+            if (AFFINE) {
+                nH[c] = min(d + open, hh + gap);
+                nV[c] = min(d + open, vv + gap);
+            } else {
+                nV[c] = d + gap;
+            }
+            nM[c] = eq;
+        }
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            if (TRANS) {
+                D4[c] = D3[c];
+                D3[c] = D2[c];
+                mt[c] = nM[c];
+            }
+            D2[c] = D1[c];
+            D1[c] = nD[c];
+            if (AFFINE) oH[c] = nH[c];
+            oV[c] = nV[c];
+        }
+    };
+
+    // phase 1: anti-diagonals that can contain first-row / first-column cells
+    for (; s <= s_end && s <= s_bnd; s += 2) {
+        step(0, true);
+        j0 += 1;
+        step(1, true);
+        i0 += 1;
+    }
+    // phase 2: interior
+    for (; s <= s_end; s += 2) {
+        step(0, false);
+        j0 += 1;
+        step(1, false);
+        i0 += 1;
+    }
+
+    // the loop ran pairs (p = 0 at s, p = 1 at s + 1); the cell (m, n) was produced on anti-diagonal m + n
+    const int pf = (s_end - dlo) & 1;
+    const int cif = ((int)diff - dlo - pf) >> 1;
+    const int tf = cif / C, cf = cif % C;
+    uint32_t val = 0;
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        // after the final pair of steps D1 = p==1 output (anti-diagonal s-1), D2 = p==0 output (s-2)
+        const uint32_t x = pf ? D1[c] : D2[c];
+        if (c == cf) val = x;
+    }
+    val = __shfl_sync(gmask, val, tf, G);
+    if (t == 0) args.out[pair] = val <= max_k ? val : TA_NONE;
+}
+
+template <int G, int C, bool AFFINE, bool TRANS>
+int launch_gc(ta_ctx *ctx, const BandArgs &args0, uint32_t max_len, cudaStream_t st) {
+    BandArgs args = args0;
+    constexpr int GROUPS = 128 / G;
+    const size_t blocks = (args.n + GROUPS - 1) / GROUPS;
+    const uint32_t slot = ((max_len + 15u) & ~15u) + 32u;  // + alignment slack of the aligned-down copy
+    const size_t smem = (size_t)GROUPS * 2 * slot;
+    if (smem <= 96 * 1024) {
+        args.slot = slot;
+        auto kern = lev_band_kernel<G, C, AFFINE, TRANS, true>;
+        if (smem > 48 * 1024)
+            TA_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)blocks, 128, smem, st>>>(args);
+    } else {
+        args.slot = 0;
+        lev_band_kernel<G, C, AFFINE, TRANS, false><<<(unsigned)blocks, 128, 0, st>>>(args);
+    }
+    ctx->launches++;
+    TA_CUDA(ctx, cudaGetLastError());
+    return TA_OK;
+}
+
+template <bool AFFINE, bool TRANS>
+int launch_w(ta_ctx *ctx, const BandArgs &args, uint32_t W, uint32_t max_len, cudaStream_t st) {
+    if (W <= 16) return launch_gc<8, 1, AFFINE, TRANS>(ctx, args, max_len, st);
+    if (W <= 32) return launch_gc<16, 1, AFFINE, TRANS>(ctx, args, max_len, st);
+    if (W <= 64) return launch_gc<32, 1, AFFINE, TRANS>(ctx, args, max_len, st);
+    if (W <= 128) return launch_gc<32, 2, AFFINE, TRANS>(ctx, args, max_len, st);
+    if (W <= 256) return launch_gc<32, 4, AFFINE, TRANS>(ctx, args, max_len, st);
+    if (W <= 512) return launch_gc<32, 8, AFFINE, TRANS>(ctx, args, max_len, st);
+    if (W <= 1024) return launch_gc<32, 16, AFFINE, TRANS>(ctx, args, max_len, st);
+    return TA_ERR_TOO_LARGE;
+}
+
+}  // namespace
+
+uint32_t ta_band_width_bound(uint32_t k, ta_costs c, uint32_t max_len) {
+    // max_k <= min(k, m*mismatch + diff*gap + start_gap) <= min(k, max_len * max(mismatch, gap) + start_gap);
+    // W = diff + 2e + 1 <= (max_k - 2*start_gap)/gap + 1  (+2 with transpositions)
+    const uint64_t ub = (uint64_t)max_len * (c.mismatch > c.gap ? c.mismatch : c.gap) + c.start_gap;
+    const uint64_t kk = k < ub ? k : ub;
+    const uint64_t unit = (kk > c.start_gap ? kk - c.start_gap : 0) / c.gap;
+    uint64_t W = unit + 1 + (c.transpose ? 2 : 0);
+    const uint64_t full = 2ull * max_len + 1 + (c.transpose ? 2 : 0);  // never wider than the whole matrix
+    if (W > full) W = full;
+    return (uint32_t)(W > 0xFFFFFFFFull ? 0xFFFFFFFFull : W);
+}
+
+int ta_launch_lev_band(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b, const uint64_t *b_off,
+                       size_t n, const uint32_t *idx, uint32_t k, ta_costs costs, uint32_t max_len, uint32_t *out,
+                       cudaStream_t st) {
+    if (n == 0) return TA_OK;
+    BandArgs args;
+    args.a = a, args.a_off = a_off, args.b = b, args.b_off = b_off, args.idx = idx, args.n = n, args.k = k;
+    args.mism = costs.mismatch, args.gap = costs.gap, args.sgap = costs.start_gap, args.tcost = costs.transpose;
+    args.slot = 0, args.out = out;
+    const uint32_t W = ta_band_width_bound(k, costs, max_len);
+    const bool affine = costs.start_gap != 0, trans = costs.transpose != 0;
+    if (affine && trans) return launch_w<true, true>(ctx, args, W, max_len, st);
+    if (affine) return launch_w<true, false>(ctx, args, W, max_len, st);
+    if (trans) return launch_w<false, true>(ctx, args, W, max_len, st);
+    return launch_w<false, false>(ctx, args, W, max_len, st);
+}

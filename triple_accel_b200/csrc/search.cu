@@ -1,0 +1,405 @@
+// search.cu -- needle-in-haystack Levenshtein search for sm_100a.
+//
+// Contract: levenshtein_search_simd_with_opts (reference src/levenshtein.rs:1911-2155) bit-exact with the scalar
+// levenshtein_search_naive_with_opts (src/levenshtein.rs:1589-1838): every end position whose best semi-global
+// alignment of the whole needle costs <= k is reported as Match{start = end - length, end, k = cost}, where
+// `length` follows the reference's tie-breaking rules cell by cell (src/levenshtein.rs:1726-1779, including the
+// comparison against length2[j-1] at :1756).  SearchType::Best is the running-minimum filter of :1792-1796
+// followed by the overlap / minimum post-pass of :1812-1835; it is applied to the (sparse) hit list.
+//
+// Kernels:
+//  * search_exact_kernel -- one thread per haystack walks the DP column by column with the exact (cost, length)
+//    rules.  DP rows live in shared memory laid out [array][row][thread] (bank = thread, conflict-free).
+//  * (lev_bitpar.cu) search_filter -- bit-parallel pre-filter for unit costs that flags the haystacks containing
+//    at least one end position with cost <= k, so the exact kernel only runs on those.
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "ta_common.cuh"
+
+// implemented in lev_bitpar.cu: flags[i] = 1 iff haystack i has an end position with unit-cost distance <= k
+int ta_launch_search_filter(ta_ctx *ctx, const uint8_t *needle_dev, uint32_t needle_len, const uint8_t *hay,
+                            const uint64_t *hay_off, size_t n, uint32_t k, bool transpose, uint32_t *idx_out,
+                            uint32_t *counter, cudaStream_t st);
+
+namespace {
+
+struct Hit {  // one reported end position
+    uint32_t hay, cost;
+    uint64_t end, len;
+};
+
+struct SearchArgs {
+    const uint8_t *needle;  // device copy
+    const uint8_t *hay;
+    const uint64_t *hay_off;
+    const uint32_t *idx;  // optional: work item w -> haystack idx[w]
+    size_t n;
+    uint32_t needle_len;
+    uint32_t k;
+    uint32_t mism, gap, sgap, tcost;
+    int anchored;
+    Hit *hits;
+    unsigned long long *hit_count;
+    unsigned long long hit_cap;
+};
+
+template <bool TRANS>
+__global__ void __launch_bounds__(64) search_exact_kernel(const SearchArgs args) {
+    extern __shared__ uint32_t sm[];
+    const uint32_t N = args.needle_len;
+    const uint32_t rows = N + 1;
+    const uint32_t T = blockDim.x;
+    const uint32_t tid = threadIdx.x;
+    // array a, row j -> sm[(a * rows + j) * T + tid]
+    auto at = [&](uint32_t a, uint32_t j) -> uint32_t & { return sm[(a * rows + j) * T + tid]; };
+    enum { CUR_DP = 0, CUR_LEN = 1, NGAP = 2, NGAP_LEN = 3, PREV_DP = 4, PREV_LEN = 5 };
+    uint8_t *sneedle = (uint8_t *)(sm + (size_t)(TRANS ? 6 : 4) * rows * T);
+    for (uint32_t q = tid; q < N; q += T) sneedle[q] = args.needle[q];
+    __syncthreads();
+
+    const size_t w = (size_t)blockIdx.x * T + tid;
+    if (w >= args.n) return;
+    const uint32_t hidx = args.idx ? args.idx[w] : (uint32_t)w;
+    const uint64_t h0 = args.hay_off[hidx], h1 = args.hay_off[hidx + 1];
+    const uint8_t *hay = args.hay + h0;
+    const uint64_t H = h1 - h0;
+    const uint32_t mism = args.mism, gap = args.gap, sgap = args.sgap, tcost = args.tcost, k = args.k;
+    const uint32_t open = sgap + gap;
+    const bool anchored = args.anchored != 0;
+
+    // src/levenshtein.rs:1650-1661
+    uint64_t iter_len = H;
+    if (anchored) {
+        const uint64_t lim = (uint64_t)N + (uint64_t)((k > sgap ? k - sgap : 0u) / gap);
+        iter_len = H < lim ? H : lim;
+    }
+
+    // column 0 (src/levenshtein.rs:1689-1691 and the initial vectors :1663-1672)
+    for (uint32_t j = 0; j <= N; j++) {
+        at(CUR_DP, j) = j * gap + (j ? sgap : 0u);
+        at(CUR_LEN, j) = 0;
+        at(NGAP, j) = TA_INF;  // u32::MAX in the reference: any opened gap is cheaper
+        at(NGAP_LEN, j) = 0;
+        if (TRANS) {
+            at(PREV_DP, j) = 0;
+            at(PREV_LEN, j) = 0;
+        }
+    }
+
+    uint32_t hc_prev = 0;
+    for (uint64_t x = 1; x <= iter_len; x++) {  // column x consumes haystack[x-1]
+        const uint32_t hc = __ldg(hay + (x - 1));
+        const uint32_t row0 = anchored ? (uint32_t)x * gap + sgap : 0u;  // :1710-1721
+        // (x-1, j-1) values before they are overwritten
+        uint32_t diag_dp = at(CUR_DP, 0), diag_len = 0;
+        // (x-2, j-2) pipeline for transpositions
+        uint32_t t1_dp = 0, t1_len = 0, t2_dp = 0, t2_len = 0;
+        if (TRANS) {
+            t1_dp = at(PREV_DP, 0);  // dp(x-2, 0)
+            t1_len = 0;
+            at(PREV_DP, 0) = diag_dp;  // becomes dp(x-1, 0) for the next column
+        }
+        at(CUR_DP, 0) = row0;
+        // (x, j-1) running values
+        uint32_t left_dp = row0, left_len = 0, hgap = TA_INF, hgap_len = 0;
+        uint32_t nprev = 0;  // needle[j-2]
+
+        for (uint32_t j = 1; j <= N; j++) {
+            const uint32_t nc = sneedle[j - 1];
+            const uint32_t up_dp = at(CUR_DP, j), up_len = at(CUR_LEN, j);  // (x-1, j)
+            const uint32_t sub = diag_dp + (nc != hc ? mism : 0u);
+            const uint32_t sub_len = diag_len + 1;
+
+            // needle gap: consume a haystack byte (:1726-1737)
+            uint32_t ng = at(NGAP, j), ngl = at(NGAP_LEN, j);
+            {
+                const uint32_t new_gap = up_dp + open, cont_gap = ng + gap;
+                if (new_gap < cont_gap) {
+                    ng = new_gap;
+                    ngl = up_len + 1;
+                } else if (new_gap > cont_gap) {
+                    ng = cont_gap;
+                    ngl = ngl + 1;
+                } else {
+                    ng = cont_gap;
+                    ngl = max(up_len, ngl) + 1;
+                }
+                ng = min(ng, TA_INF);
+            }
+            at(NGAP, j) = ng;
+            at(NGAP_LEN, j) = ngl;
+
+            // haystack gap: consume a needle byte (:1739-1750)
+            {
+                const uint32_t new_gap = left_dp + open, cont_gap = hgap + gap;
+                if (new_gap < cont_gap) {
+                    hgap = new_gap;
+                    hgap_len = left_len;
+                } else if (new_gap > cont_gap) {
+                    hgap = cont_gap;
+                    // hgap_len unchanged: haystack_gap_length[j] = haystack_gap_length[j-1]
+                } else {
+                    hgap = cont_gap;
+                    hgap_len = max(left_len, hgap_len);
+                }
+                hgap = min(hgap, TA_INF);
+            }
+
+            uint32_t dp = ng, len = ngl;  // :1752-1753
+            if (hgap < dp || (hgap == dp && left_len > len)) {  // :1755-1760 (compares length2[j-1])
+                dp = hgap;
+                len = hgap_len;
+            }
+            if (sub < dp || (sub == dp && sub_len > len)) {  // :1762-1765
+                dp = sub;
+                len = sub_len;
+            }
+            if (TRANS) {
+                // (x-2, j-2): value read two rows ago
+                const uint32_t p_dp = at(PREV_DP, j), p_len = at(PREV_LEN, j);  // dp(x-2, j), len(x-2, j)
+                if (x > 1 && j > 1 && nc == hc_prev && nprev == hc) {           // :1767-1779
+                    const uint32_t tr = t2_dp + tcost;
+                    if (tr <= dp) {
+                        dp = tr;
+                        len = t2_len + 2;
+                    }
+                }
+                t2_dp = t1_dp;
+                t2_len = t1_len;
+                t1_dp = p_dp;
+                t1_len = p_len;
+                at(PREV_DP, j) = up_dp;  // (x-1, j) becomes (x-2, j) two columns later
+                at(PREV_LEN, j) = up_len;
+            }
+            at(CUR_DP, j) = dp;
+            at(CUR_LEN, j) = len;
+            diag_dp = up_dp;
+            diag_len = up_len;
+            left_dp = dp;
+            left_len = len;
+            nprev = nc;
+        }
+        hc_prev = hc;
+
+        if (left_dp <= k) {  // :1792-1806 with the All threshold; Best is a host-side filter of this list
+            const unsigned long long slot = atomicAdd(args.hit_count, 1ull);
+            if (slot < args.hit_cap) {
+                Hit h;
+                h.hay = hidx;
+                h.cost = left_dp;
+                h.end = x;
+                h.len = left_len;
+                args.hits[slot] = h;
+            }
+        }
+    }
+}
+
+size_t exact_smem_bytes(uint32_t needle_len, bool trans, int threads) {
+    return (size_t)(trans ? 6 : 4) * (needle_len + 1) * threads * sizeof(uint32_t) + ((needle_len + 15) & ~15u);
+}
+
+}  // namespace
+
+extern "C" int ta_levenshtein_search_batch(ta_ctx *ctx, const uint8_t *needle, size_t needle_len, const uint8_t *hay,
+                                           const uint64_t *hay_off, size_t n, uint32_t k, int search_type,
+                                           ta_costs costs, int anchored, ta_match **out_matches,
+                                           uint64_t **out_match_off) {
+    if (!ctx || !out_matches || !out_match_off) return TA_ERR_BAD_ARG;
+    *out_matches = nullptr;
+    *out_match_off = nullptr;
+    if (search_type != TA_SEARCH_ALL && search_type != TA_SEARCH_BEST) return TA_ERR_BAD_ARG;
+    if (!ta_costs_valid(costs)) return TA_ERR_BAD_COSTS;
+    if (n && !hay_off) return TA_ERR_BAD_ARG;
+    if (needle_len && !needle) return TA_ERR_BAD_ARG;
+    if (n > 0xFFFFFFF0ull || needle_len > TA_MAX_STRING_LEN) return TA_ERR_TOO_LARGE;
+    const bool best = search_type == TA_SEARCH_BEST;
+
+    uint64_t *moff = (uint64_t *)calloc(n + 1, sizeof(uint64_t));
+    if (!moff) return TA_ERR_NOMEM;
+    std::vector<ta_match> result;
+    auto finish = [&]() {
+        ta_match *m = (ta_match *)malloc((result.size() ? result.size() : 1) * sizeof(ta_match));
+        if (!m) {
+            free(moff);
+            return (int)TA_ERR_NOMEM;
+        }
+        if (!result.empty()) memcpy(m, result.data(), result.size() * sizeof(ta_match));
+        *out_matches = m;
+        *out_match_off = moff;
+        return (int)TA_OK;
+    };
+
+    uint64_t max_hay = 0, total_hay = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (hay_off[i + 1] < hay_off[i]) {
+            free(moff);
+            return TA_ERR_BAD_ARG;
+        }
+        max_hay = std::max(max_hay, hay_off[i + 1] - hay_off[i]);
+    }
+    if (n) total_hay = hay_off[n] - hay_off[0];
+    if (total_hay && !hay) {
+        free(moff);
+        return TA_ERR_BAD_ARG;
+    }
+
+    if (needle_len == 0) {  // reference src/levenshtein.rs:1600-1644 -- no DP involved, pure bookkeeping
+        for (size_t i = 0; i < n; i++) {
+            if (anchored) {
+                result.push_back(ta_match{0, 0, 0, 0});
+                if (!best) {
+                    const uint64_t H = hay_off[i + 1] - hay_off[i];
+                    uint32_t cost = costs.start_gap;
+                    for (uint64_t x = 0; x < H; x++) {
+                        cost += costs.gap;
+                        if (cost <= k)
+                            result.push_back(ta_match{0, x + 1, cost, 0});
+                        else
+                            break;
+                    }
+                }
+            }
+            moff[i + 1] = result.size();
+        }
+        return finish();
+    }
+    if (!ta_costs_valid_search(costs)) {  // src/levenshtein.rs:1647
+        free(moff);
+        return TA_ERR_BAD_COSTS;
+    }
+    if (n == 0) return finish();
+
+    // ---- device work ------------------------------------------------------------------------------------------
+    std::vector<Hit> hits;
+    {
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        auto bail = [&](int rc) {
+            free(moff);
+            return rc;
+        };
+        if (cudaSetDevice(ctx->device) != cudaSuccess) return bail(ta_cuda_fail(ctx, cudaGetLastError(), "cudaSetDevice"));
+        cudaStream_t st = ctx->stream;
+        int rc;
+        const uint64_t lo = hay_off[0];
+        const size_t skew = (size_t)(lo & 15);
+        if ((rc = ta_dev_reserve(ctx, ctx->d_a[0], skew + total_hay + 64)) != TA_OK) return bail(rc);
+        if ((rc = ta_dev_reserve(ctx, ctx->d_aoff[0], (n + 1) * sizeof(uint64_t))) != TA_OK) return bail(rc);
+        if ((rc = ta_dev_reserve(ctx, ctx->d_b[0], needle_len + 64)) != TA_OK) return bail(rc);
+        cudaError_t e;
+#define S_CUDA(call)                                                    \
+    if ((e = (call)) != cudaSuccess) return bail(ta_cuda_fail(ctx, e, #call))
+        if (total_hay)
+            S_CUDA(cudaMemcpyAsync((uint8_t *)ctx->d_a[0].p + skew, hay + lo, total_hay, cudaMemcpyHostToDevice, st));
+        S_CUDA(cudaMemcpyAsync(ctx->d_aoff[0].p, hay_off, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        S_CUDA(cudaMemcpyAsync(ctx->d_b[0].p, needle, needle_len, cudaMemcpyHostToDevice, st));
+        const uint8_t *d_hay = (const uint8_t *)ctx->d_a[0].p + skew - lo;
+        const uint64_t *d_off = (const uint64_t *)ctx->d_aoff[0].p;
+        const uint8_t *d_needle = (const uint8_t *)ctx->d_b[0].p;
+
+        // optional bit-parallel pre-filter (unit costs, needle <= 64): only flagged haystacks get the exact DP
+        const bool unit = costs.mismatch == 1 && costs.gap == 1 && costs.start_gap == 0 && costs.transpose <= 1;
+        const uint32_t *d_idx = nullptr;
+        size_t work_n = n;
+        const uint32_t row0_cost = (uint32_t)needle_len * costs.gap + costs.start_gap;
+        if (unit && needle_len <= 64 && !anchored && k < needle_len) {
+            if ((rc = ta_dev_reserve(ctx, ctx->d_work[0], n * sizeof(uint32_t))) != TA_OK) return bail(rc);
+            uint32_t *counter = ctx->d_flags + 2;
+            S_CUDA(cudaMemsetAsync(counter, 0, sizeof(uint32_t), st));
+            rc = ta_launch_search_filter(ctx, d_needle, (uint32_t)needle_len, d_hay, d_off, n, k,
+                                         costs.transpose != 0, (uint32_t *)ctx->d_work[0].p, counter, st);
+            if (rc == TA_OK) {
+                S_CUDA(cudaMemcpyAsync(ctx->h_flags + 2, counter, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+                S_CUDA(cudaStreamSynchronize(st));
+                work_n = ctx->h_flags[2];
+                d_idx = (const uint32_t *)ctx->d_work[0].p;
+            } else if (rc != TA_ERR_TOO_LARGE) {
+                return bail(rc);
+            }
+        }
+
+        if (work_n > 0) {
+            const bool trans = costs.transpose != 0;
+            const int threads = 64;
+            const size_t smem = exact_smem_bytes((uint32_t)needle_len, trans, threads);
+            if (smem > (size_t)ctx->smem_optin) return bail(TA_ERR_TOO_LARGE);
+            auto kern = trans ? search_exact_kernel<true> : search_exact_kernel<false>;
+            S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            unsigned long long cap = std::max<unsigned long long>(4096, work_n * 8);
+            for (int attempt = 0; attempt < 2; attempt++) {
+                if ((rc = ta_dev_reserve(ctx, ctx->d_work[1], cap * sizeof(Hit))) != TA_OK) return bail(rc);
+                unsigned long long *d_count = (unsigned long long *)(ctx->d_flags + 4);
+                S_CUDA(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st));
+                SearchArgs sa;
+                sa.needle = d_needle, sa.hay = d_hay, sa.hay_off = d_off, sa.idx = d_idx, sa.n = work_n;
+                sa.needle_len = (uint32_t)needle_len, sa.k = k;
+                sa.mism = costs.mismatch, sa.gap = costs.gap, sa.sgap = costs.start_gap, sa.tcost = costs.transpose;
+                sa.anchored = anchored, sa.hits = (Hit *)ctx->d_work[1].p, sa.hit_count = d_count, sa.hit_cap = cap;
+                const unsigned blocks = (unsigned)((work_n + threads - 1) / threads);
+                kern<<<blocks, threads, smem, st>>>(sa);
+                ctx->launches++;
+                S_CUDA(cudaGetLastError());
+                S_CUDA(cudaMemcpyAsync(ctx->h_flags + 4, d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+                S_CUDA(cudaStreamSynchronize(st));
+                unsigned long long got;
+                memcpy(&got, ctx->h_flags + 4, sizeof got);
+                if (got <= cap) {
+                    hits.resize((size_t)got);
+                    if (got)
+                        S_CUDA(cudaMemcpy(hits.data(), ctx->d_work[1].p, (size_t)got * sizeof(Hit), cudaMemcpyDeviceToHost));
+                    break;
+                }
+                if (attempt == 1) return bail(TA_ERR_TOO_LARGE);
+                cap = got;  // exact size known now: rerun once
+            }
+        }
+#undef S_CUDA
+        // the row-0 match Match{0, 0, needle_len*gap + start_gap} (src/levenshtein.rs:1686-1707) is emitted below
+        (void)row0_cost;
+    }
+
+    // ---- order the hits (haystack, end) and apply the reference's emission rules ------------------------------
+    std::sort(hits.begin(), hits.end(), [](const Hit &x, const Hit &y) {
+        return x.hay != y.hay ? x.hay < y.hay : x.end < y.end;
+    });
+    const uint32_t row0 = (uint32_t)needle_len * costs.gap + costs.start_gap;
+    size_t hp = 0;
+    std::vector<ta_match> cur;
+    for (size_t i = 0; i < n; i++) {
+        cur.clear();
+        uint32_t curr_k = k;
+        if (row0 <= curr_k) {  // :1693-1706
+            if (best) curr_k = row0;
+            cur.push_back(ta_match{0, 0, row0, 0});
+        }
+        for (; hp < hits.size() && hits[hp].hay == i; hp++) {
+            const Hit &h = hits[hp];
+            if (h.cost <= curr_k) {  // :1792-1806
+                if (best) curr_k = h.cost;
+                cur.push_back(ta_match{h.end - h.len, h.end, h.cost, 0});
+            }
+        }
+        if (best && !cur.empty()) {  // :1812-1835
+            size_t wpos = 0;
+            for (size_t r = 0; r < cur.size(); r++) {
+                if (wpos == 0)
+                    cur[wpos++] = cur[r];
+                else if (cur[r].start <= cur[wpos - 1].start)
+                    cur[wpos - 1] = cur[r];
+                else
+                    cur[wpos++] = cur[r];
+            }
+            size_t f = 0;
+            for (size_t r = 0; r < wpos; r++)
+                if (cur[r].k == curr_k) cur[f++] = cur[r];
+            cur.resize(f);
+        }
+        result.insert(result.end(), cur.begin(), cur.end());
+        moff[i + 1] = result.size();
+    }
+    return finish();
+}

@@ -1,0 +1,58 @@
+// ta_common.cuh -- shared declarations for the sm_100a kernels and the C-ABI host layer.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <mutex>
+#include <string>
+
+#include "../../include/triple_accel_b200.h"
+
+#define TA_INF 0x3FFFFFFFu  // "out of band" cell value; real costs stay below 2^30 (TA_MAX_STRING_LEN)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct ta_ctx {
+    int device = 0;
+    int sm_count = 148;
+    int smem_optin = 0;  // max opt-in dynamic shared memory per block
+    std::mutex mu;
+    cudaStream_t stream = nullptr;   // compute + D2H
+    cudaStream_t stream2 = nullptr;  // H2D of the next chunk
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
+    cudaEvent_t ev_done[2] = {nullptr, nullptr};
+    DevBuf d_a[2], d_b[2], d_aoff[2], d_boff[2], d_out[2], d_work[4];
+    DevBuf h_pin[4];         // pinned staging for pageable inputs / outputs
+    uint32_t *d_flags = nullptr;  // [0] = deferred error code of *_dev kernels, [1..] scratch counters
+    uint32_t *h_flags = nullptr;  // pinned mirror
+    uint64_t launches = 0;
+    std::string last_error;
+};
+
+// grow-only device / pinned-host buffers
+int ta_dev_reserve(ta_ctx *ctx, DevBuf &b, size_t bytes);
+int ta_pin_reserve(ta_ctx *ctx, DevBuf &b, size_t bytes);
+int ta_cuda_fail(ta_ctx *ctx, cudaError_t e, const char *what);
+
+#define TA_CUDA(ctx, call)                                        \
+    do {                                                          \
+        cudaError_t e__ = (call);                                 \
+        if (e__ != cudaSuccess) return ta_cuda_fail(ctx, e__, #call); \
+    } while (0)
+
+// ---- kernel launchers (device pointers; asynchronous on `st`) --------------------------------------------------
+int ta_launch_hamming(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b, const uint64_t *b_off,
+                      size_t n, uint32_t avg_len, uint32_t *out, uint32_t *err_flag, cudaStream_t st);
+
+// General banded anti-diagonal DP (all cost models, any k).  `idx` (may be null) is an indirection: work item w
+// processes pair idx[w] (used by the exponential-k driver to re-run only the pairs that are still TA_NONE).
+int ta_launch_lev_band(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b, const uint64_t *b_off,
+                       size_t n, const uint32_t *idx, uint32_t k, ta_costs costs, uint32_t max_len, uint32_t *out,
+                       cudaStream_t st);
+
+// band width (number of diagonals) the general kernel needs in the worst case for (k, costs, max_len)
+uint32_t ta_band_width_bound(uint32_t k, ta_costs c, uint32_t max_len);
