@@ -1,0 +1,345 @@
+#!/usr/bin/env python3
+"""bench.py -- throughput of the hot path on B200 (see DESIGN.md "Measurement").
+
+A "step" is one pass of the k-banded Levenshtein kernel over one batch of synthetic pairs.
+Default workload = BASELINE.json configs[1]: levenshtein_simd_k, k = 8, 1 M pairs, len 128, unit costs, on the
+"matching" set M (b = a after U[0,8] random edits, so no pair can be rejected early).
+
+  python bench.py --gpus 1 --steps 20 --warmup 5            # our CUDA path (one JSON line)
+  python bench.py --impl reference --steps 3 --warmup 1     # the reference's CPU algorithm (oracle port) on host cores
+  torchrun --nproc-per-node N bench.py --gpus N ...          # one rank per GPU, pairs sharded, no data-path collective
+
+value  = GCUPS (nominal band cells of the reference's scalar banded DP, (2k+1)n - k^2 per pair) with inputs
+         resident in HBM, timed with CUDA events on the launching stream, max over ranks.
+e2e    = the same metric through the host-buffer C-ABI call (pinned host inputs, H2D + kernel + D2H in the timed
+         region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (op, n_pairs, len, k, costs, description)
+    "lev_k8_len128": ("lev_k", 1_000_000, 128, 8, (1, 1, 0, 0),
+                      "levenshtein_simd_k k=8, 1M pairs len=128, unit costs, set M (b = a after U[0,8] edits)"),
+    "lev_k16_len128": ("lev_k", 1_000_000, 128, 16, (1, 1, 0, 0),
+                       "levenshtein_simd_k k=16, 1M pairs len=128, unit costs, set M (b = a after U[0,16] edits)"),
+    "rdamerau_k16_len512": ("lev_k", 1_000_000, 512, 16, (1, 1, 0, 1),
+                            "RDAMERAU_COSTS k=16, 1M pairs len=512, set M (U[0,16] edits incl. swaps)"),
+    "lev_k16_len4096": ("lev_k", 65_536, 4096, 16, (1, 1, 0, 0),
+                        "levenshtein_simd_k k=16, 64Ki pairs len=4096, unit costs, set M"),
+    "hamming_len64": ("hamming", 10_000, 64, 0, (1, 1, 0, 0), "hamming, 10k pairs len=64 (plumbing case)"),
+    "hamming_len4096": ("hamming", 262_144, 4096, 0, (1, 1, 0, 0), "hamming, 256Ki pairs len=4096"),
+}
+
+
+def nominal_cells(length, k):
+    """cells the reference's scalar banded DP visits for |a| = |b| = length, half-width k"""
+    u = min(k, length)
+    return (2 * u + 1) * length - u * u
+
+
+def make_inputs(op, n, length, k, costs, seed):
+    from triple_accel_b200 import synth
+    if op == "hamming":
+        return synth.hamming_pairs(n, length, seed=seed)
+    return synth.mutated_pairs(n, length, k, seed=seed, allow_swap=bool(costs[3]))
+
+
+class ClockSampler:
+    """samples nvidia-smi SM clocks / throttle reasons during the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def pinned_copy(lib, arr):
+    """copy a numpy array into pinned host memory obtained from the C ABI"""
+    import ctypes as C
+    nbytes = max(arr.nbytes, 1)
+    p = lib.ta_host_alloc(nbytes)
+    if not p:
+        raise MemoryError("ta_host_alloc")
+    buf = (C.c_uint8 * nbytes).from_address(p)
+    out = np.frombuffer(buf, dtype=arr.dtype, count=arr.size)
+    out[:] = arr.reshape(-1)
+    return out, p
+
+
+def run_reference(args, wl):
+    """--impl reference: the reference's own CPU algorithm for this path.  The crate is Rust-only and cannot be
+    built in this image, so this times the oracle port (kind "port") with every host thread, on a bounded sample."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _oracle as orc
+    op, n, length, k, costs, desc = wl
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = min(n, args.cpu_sample)
+    a, ao, b, bo = make_inputs(op, sample, length, k, costs, 1234)
+    threads = orc.max_threads()
+
+    def step():
+        if op == "hamming":
+            return orc.hamming_batch(a, ao, b, bo, threads=threads)
+        return orc.levenshtein_k_batch(a, ao, b, bo, k, costs, threads=threads)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    cells = nominal_cells(length, k) if op != "hamming" else length
+    val = sample * cells / dt / 1e9
+    line = {
+        "impl": "reference", "metric": "dp_cell_updates_per_s", "value": val, "unit": "GCUPS", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": desc, "name": args.workload, "sample_pairs": sample},
+        "pairs_per_s": sample / dt,
+        "cpu_baseline": {"value": val, "unit": "GCUPS", "cores": threads, "kind": "port",
+                         "sample": "%d pairs of the same workload per step" % sample},
+        "e2e": {"value": val, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="lev_k8_len128", choices=sorted(WORKLOADS))
+    ap.add_argument("--pairs", type=int, default=0, help="override the number of pairs per GPU")
+    ap.add_argument("--cpu-sample", type=int, default=200_000, help="pairs per step for CPU baselines")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    wl = list(WORKLOADS[args.workload])
+    if args.pairs:
+        wl[1] = args.pairs
+    op, n, length, k, costs, desc = wl
+
+    if args.impl == "reference":
+        run_reference(args, wl)
+        return
+
+    import torch
+    import triple_accel_b200 as ta
+    from triple_accel_b200 import _ffi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this framework has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    eng = ta.Engine(local_rank)
+    lib = _ffi.load()
+
+    # every rank owns an independent shard of the same shape (weak scaling; no data-path collective)
+    a, ao, b, bo = make_inputs(op, n, length, k, costs, 1234 + rank)
+    max_len = int(max((ao[1:] - ao[:-1]).max(), (bo[1:] - bo[:-1]).max())) if n else 0
+
+    def to_dev(x):
+        return torch.from_numpy(x.view(np.int64) if x.dtype == np.uint64 else x).to(dev)
+
+    d_a, d_ao, d_b, d_bo = to_dev(a), to_dev(ao), to_dev(b), to_dev(bo)
+    d_out = torch.empty(n, dtype=torch.int32, device=dev)
+
+    def step_dev():
+        if op == "hamming":
+            eng.hamming_batch_dev(d_a, d_ao, d_b, d_bo, d_out)
+        else:
+            eng.levenshtein_k_batch_dev(d_a, d_ao, d_b, d_bo, k, costs, max_len, d_out)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    eng.dev_status()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.15)
+    launches0 = eng.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step_dev()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    eng.dev_status()
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_step = ms / args.steps
+
+    # parity spot check on the timed output (bounded sample, oracle as the checker)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _oracle as orc
+    chk = min(n, 20000)
+    got = d_out[:chk].cpu().numpy().view(np.uint32)
+    if op == "hamming":
+        want = orc.hamming_batch(a, ao[:chk + 1], b, bo[:chk + 1], threads=orc.max_threads())
+    else:
+        want = orc.levenshtein_k_batch(a, ao[:chk + 1], b, bo[:chk + 1], k, costs, threads=orc.max_threads())
+    parity_ok = bool(np.array_equal(got, want))
+
+    cells_pair = nominal_cells(length, k) if op != "hamming" else length
+    total_pairs = n * world
+    value = total_pairs * cells_pair / (ms_step * 1e-3) / 1e9
+    alg_bytes = int(a.nbytes + b.nbytes + 4 * n)  # |a| + |b| + 4 per pair (offsets: +16 B/pair, not counted)
+
+    # ---- end to end through the host-buffer C ABI (pinned host inputs; H2D + kernel + D2H timed) --------------
+    e2e = None
+    if not args.no_e2e:
+        pa, _p1 = pinned_copy(lib, a)
+        pb, _p2 = pinned_copy(lib, b)
+        pao, _p3 = pinned_copy(lib, ao)
+        pbo, _p4 = pinned_copy(lib, bo)
+        pout, _p5 = pinned_copy(lib, np.zeros(n, np.uint32))
+
+        def step_host():
+            if op == "hamming":
+                eng.hamming_batch(pa, pao, pb, pbo, out=pout)
+            else:
+                eng.levenshtein_k_batch(pa, pao, pb, pbo, k, costs, out=pout)
+
+        for _ in range(2):
+            step_host()
+        barrier()
+        e_steps = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            step_host()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        dt /= e_steps
+        assert np.array_equal(pout[:chk], want), "e2e parity"
+        e2e = {"value": total_pairs * cells_pair / dt / 1e9, "unit": "GCUPS",
+               "h2d_bytes_per_step": int(a.nbytes + b.nbytes + ao.nbytes + bo.nbytes), "d2h_bytes_per_step": int(4 * n),
+               "ms_per_step": dt * 1e3, "pairs_per_s": total_pairs / dt}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = alg_bytes / (ms_step * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(args.workload)
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                "kernel": "lev_bitpar / lev_band (see DESIGN.md)" if op != "hamming" else "hamming_kernel"}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        sample = min(n, args.cpu_sample)
+        threads = orc.max_threads()
+        t0 = time.perf_counter()
+        if op == "hamming":
+            orc.hamming_batch(a, ao[:sample + 1], b, bo[:sample + 1], threads=threads)
+        else:
+            orc.levenshtein_k_batch(a, ao[:sample + 1], b, bo[:sample + 1], k, costs, threads=threads)
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": sample * cells_pair / dt / 1e9, "unit": "GCUPS", "cores": threads, "kind": "port",
+                        "sample": "first %d pairs of the same batch, scalar oracle on %d threads" % (sample, threads),
+                        "pairs_per_s": sample / dt}
+
+    line = {
+        "metric": "dp_cell_updates_per_s", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": desc, "name": args.workload, "pairs_per_gpu": n, "len": length, "k": k,
+                   "costs": list(costs), "cells_per_pair": cells_pair, "parallelism": "pairs sharded x%d" % world,
+                   "l2": "inputs (%.0f MB per GPU) larger than the 126 MB L2" % ((a.nbytes + b.nbytes) / 1e6)
+                   if a.nbytes + b.nbytes > 126e6 else "inputs fit in L2 (small config)"},
+        "pairs_per_s": total_pairs / (ms_step * 1e-3),
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+        "cpu_baseline": cpu_baseline, "parity_checked_pairs": chk, "parity_ok": parity_ok,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    if not parity_ok:
+        raise SystemExit("bench.py: GPU results differ from the oracle")
+
+
+if __name__ == "__main__":
+    main()

@@ -250,7 +250,7 @@ def test_nul_bytes_and_high_bytes(eng):
                                   orc.levenshtein_k_batch(a, ao, b, bo, k, costs))
 
 
-SEARCH_MODELS = [(1, 1, 0, 0), (1, 1, 0, 1), (1, 1, 2, 0), (2, 1, 2, 0), (3, 1, 0, 0), (2, 2, 1, 3), (1, 2, 0, 2)]
+SEARCH_MODELS = [(1, 1, 0, 0), (1, 1, 0, 1), (1, 1, 2, 0), (2, 1, 2, 0), (3, 1, 0, 0), (2, 2, 1, 3), (2, 2, 0, 2)]
 
 
 @pytest.mark.parametrize("costs", SEARCH_MODELS, ids=[str(c) for c in SEARCH_MODELS])
