@@ -1,0 +1,48 @@
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <random>
+#include "../triple_accel_b200/csrc/lev_bitpar_core.cuh"
+extern "C" {
+#include "../oracle/ta_oracle.h"
+}
+int main(int argc, char** argv) {
+    std::mt19937_64 rng(12345);
+    std::vector<uint8_t> arena(1 << 16);
+    uint8_t* base = (uint8_t*)(((uintptr_t)arena.data() + 4096) & ~(uintptr_t)15);
+    long bad = 0, tests = 0;
+    for (int it = 0; it < 400000; it++) {
+        int alpha = (int[]){2, 3, 4, 26, 256}[rng() % 5];
+        int la = rng() % (it % 7 == 0 ? 200 : 40), lb;
+        int mode = rng() % 3;
+        size_t offa = rng() % 64, offb = 1024 + rng() % 64;
+        uint8_t* a = base + offa; uint8_t* b = base + offb;
+        for (int i = 0; i < 2048; i++) base[i] = rng() & 0xff;  // junk around
+        for (int i = 0; i < la; i++) a[i] = rng() % alpha;
+        if (mode == 0) { lb = rng() % (it % 7 == 0 ? 200 : 40); for (int i = 0; i < lb; i++) b[i] = rng() % alpha; }
+        else { // mutate
+            std::vector<uint8_t> s(a, a + la);
+            int ne = rng() % 12;
+            for (int e = 0; e < ne; e++) {
+                int kind = rng() % 4;
+                if (kind == 0 && !s.empty()) s[rng() % s.size()] = rng() % alpha;
+                else if (kind == 1) s.insert(s.begin() + rng() % (s.size() + 1), rng() % alpha);
+                else if (kind == 2 && !s.empty()) s.erase(s.begin() + rng() % s.size());
+                else if (kind == 3 && s.size() > 1) { size_t p = rng() % (s.size() - 1); std::swap(s[p], s[p + 1]); }
+            }
+            lb = s.size(); memcpy(b, s.data(), lb);
+        }
+        for (int trans = 0; trans < 2; trans++) {
+            uint32_t kmax = trans ? 29 : 31;
+            uint32_t k = rng() % (kmax + 1);
+            orc_costs c = {1, 1, 0, (uint8_t)trans};
+            uint32_t want = orc_levenshtein_naive_k_with_opts(a, la, b, lb, k, c, NULL, NULL);
+            uint32_t got = trans ? bitpar::pair_unit_costs<true>(a, la, b, lb, k) : bitpar::pair_unit_costs<false>(a, la, b, lb, k);
+            tests++;
+            if (want != got) { if (bad++ < 10) printf("MISMATCH trans=%d k=%u la=%d lb=%d want=%u got=%u\n", trans, k, la, lb, want, got); }
+        }
+    }
+    printf("tests %ld bad %ld\n", tests, bad);
+    return bad != 0;
+}

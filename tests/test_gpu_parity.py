@@ -310,3 +310,16 @@ def test_device_resident_entry_points(eng):
     eng.hamming_batch_dev(t[0], t[1], tb, tbo, out2)
     with pytest.raises(AssertionError):
         eng.dev_status()
+
+
+def test_general_band_kernel_forced():
+    """The dispatcher sends unit-cost / narrow-band batches to the bit-parallel kernel; TA_FORCE_BAND=1 routes
+    them through the general anti-diagonal kernel instead.  Run the unit-cost differential tests again in a
+    subprocess with that switch so both kernels are pinned to the oracle on the same inputs."""
+    import subprocess
+    import sys
+    env = dict(os.environ, TA_FORCE_BAND="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", os.path.abspath(__file__), "-k",
+                        "test_lev_k_mutated or test_lev_k_random_short or test_nul_bytes or test_lev_exp"],
+                       env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

@@ -21,6 +21,15 @@ int ta_cuda_fail(ta_ctx *ctx, cudaError_t e, const char *what) {
     return TA_ERR_CUDA;
 }
 
+int ta_launch_lev(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b, const uint64_t *b_off,
+                  size_t n, const uint32_t *idx, uint32_t k, ta_costs costs, uint32_t max_len, uint32_t *out,
+                  cudaStream_t st) {
+    static const bool force_band = getenv("TA_FORCE_BAND") != nullptr;  // testing: exercise the general kernel
+    if (!force_band && ta_bitpar_can_handle(k, costs, max_len))
+        return ta_launch_lev_bitpar(ctx, a, a_off, b, b_off, n, idx, k, costs, out, st);
+    return ta_launch_lev_band(ctx, a, a_off, b, b_off, n, idx, k, costs, max_len, out, st);
+}
+
 int ta_dev_reserve(ta_ctx *ctx, DevBuf &b, size_t bytes) {
     bytes = (bytes + 255) & ~(size_t)255;
     if (bytes <= b.cap && b.p) return TA_OK;
@@ -226,7 +235,7 @@ int exp_rounds_dev(ta_ctx *ctx, const uint8_t *da, const uint64_t *da_off, const
                    size_t n, ta_costs costs, uint32_t max_len, uint32_t *d_out, cudaStream_t st) {
     int rc;
     uint32_t k = 30;
-    if ((rc = ta_launch_lev_band(ctx, da, da_off, db, db_off, n, nullptr, k, costs, max_len, d_out, st)) != TA_OK) return rc;
+    if ((rc = ta_launch_lev(ctx, da, da_off, db, db_off, n, nullptr, k, costs, max_len, d_out, st)) != TA_OK) return rc;
     if ((rc = ta_dev_reserve(ctx, ctx->d_work[0], n * sizeof(uint32_t))) != TA_OK) return rc;
     if ((rc = ta_dev_reserve(ctx, ctx->d_work[1], n * sizeof(uint32_t))) != TA_OK) return rc;
     uint32_t *idx[2] = {(uint32_t *)ctx->d_work[0].p, (uint32_t *)ctx->d_work[1].p};
@@ -249,7 +258,7 @@ int exp_rounds_dev(ta_ctx *ctx, const uint8_t *da, const uint64_t *da_off, const
         cur = idx[flip];
         cur_n = remaining;
         flip ^= 1;
-        if ((rc = ta_launch_lev_band(ctx, da, da_off, db, db_off, cur_n, cur, k, costs, max_len, d_out, st)) != TA_OK)
+        if ((rc = ta_launch_lev(ctx, da, da_off, db, db_off, cur_n, cur, k, costs, max_len, d_out, st)) != TA_OK)
             return rc;
     }
     return TA_OK;
@@ -284,7 +293,7 @@ int run_pairs(ta_ctx *ctx, Op op, const uint8_t *a, const uint64_t *a_off, const
             break;
         }
         case OP_LEV_K:
-            rc = ta_launch_lev_band(ctx, da, da_off, db, db_off, n, nullptr, k, costs, bs.max_len, d_out, st);
+            rc = ta_launch_lev(ctx, da, da_off, db, db_off, n, nullptr, k, costs, bs.max_len, d_out, st);
             break;
         case OP_LEV_EXP:
             rc = exp_rounds_dev(ctx, da, da_off, db, db_off, n, costs, bs.max_len, d_out, st);
@@ -345,7 +354,7 @@ int ta_levenshtein_k_batch_dev(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_
     if (max_len > TA_MAX_STRING_LEN) return TA_ERR_TOO_LARGE;
     std::lock_guard<std::mutex> lock(ctx->mu);
     TA_CUDA(ctx, cudaSetDevice(ctx->device));
-    return ta_launch_lev_band(ctx, a, a_off, b, b_off, n, nullptr, k, costs, max_len, out, (cudaStream_t)stream);
+    return ta_launch_lev(ctx, a, a_off, b, b_off, n, nullptr, k, costs, max_len, out, (cudaStream_t)stream);
 }
 
 int ta_dev_status(ta_ctx *ctx, void *stream) {

@@ -1,0 +1,215 @@
+// lev_bitpar_core.cuh -- per-pair core of the bit-parallel banded kernel (unit costs), host/device.
+//
+// One thread owns one pair.  The k-band (Ukkonen: W = diff + 2e + 1 <= 32 diagonals, e = (max_k - diff)/2) is a
+// 32-row window that slides one row down per text column; the vertical deltas of the window's cells live in two
+// 32-bit words (VP/VN) and a column is advanced with Myers' carry trick in Hyyro's diagonal-aligned form
+//     D0 = (((Eq & VP) + VP) ^ VP) | Eq | VN [| TR]        X  = D0 >> 1
+//     HP = VN | ~(D0 | VP),  HN = D0 & VP                  VP' = HN | ~(X | HP),  VN' = X & HP
+// (TR = ~D0prev & (Eq << 1) & (Eqprev >> 1) adds restricted-Damerau transpositions).  Rows above the matrix are
+// "virtual" cells with D = j - i (vertical delta -1), which makes the first row D[0][j] = j come out of the same
+// recurrence; rows below the pattern are garbage that can never flow upwards.  The distance is read off the
+// diagonal through (m, n):  d = diff + n - #columns whose D0 bit at that diagonal is set.
+//
+// Eq (which of the 32 window rows match the column's byte) is a SIMD-in-register compare: the window's pattern
+// bytes sit transposed in 8 registers (register q, byte t <-> row q + 8t), each is XORed with the broadcast text
+// byte and zero bytes are detected exactly with ((x & 0x7f..) + 0x7f..) | x; shifting register q's flags right by
+// 7 - q and OR-ing the eight results puts row r's flag at bit r.  Sliding the window is one PRMT (drop byte 0 of
+// the oldest register, append the next pattern byte); with the column loop unrolled by 16 every register role,
+// byte selector and shift is a compile-time constant.
+//
+// Both strings are streamed straight from global memory in aligned 16-byte vectors (one LDG.128 per string per 16
+// columns, prefetched one iteration ahead) and re-aligned in registers (a two-stage word select plus a funnel
+// shift), so arbitrary CSR offsets and string lengths need no staging buffer.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define TA_HD __host__ __device__ __forceinline__
+#else
+#define TA_HD inline
+#endif
+
+namespace bitpar {
+
+struct V4 {
+    uint32_t x, y, z, w;
+};
+
+TA_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) {  // low 32 bits of (hi:lo) >> s, s in [0, 31]
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, s);
+#else
+    return s ? (lo >> s) | (hi << (32 - s)) : lo;
+#endif
+}
+
+TA_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(a, b, sel);
+#else
+    uint64_t v = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) r |= (uint32_t)((v >> (8 * ((sel >> (4 * i)) & 7))) & 0xff) << (8 * i);
+    return r;
+#endif
+}
+
+TA_HD V4 ldvec(const uint8_t *p) {  // p is 16-byte aligned
+#if defined(__CUDA_ARCH__)
+    const uint4 v = __ldg((const uint4 *)p);
+    return V4{v.x, v.y, v.z, v.w};
+#else
+    V4 v;
+    const uint32_t *q = (const uint32_t *)p;
+    v.x = q[0], v.y = q[1], v.z = q[2], v.w = q[3];
+    return v;
+#endif
+}
+
+// A byte stream read through aligned 16-byte vectors.  Logical byte t of the stream is memory byte start + t;
+// vector addresses are clamped into [lo, hi] (the vectors holding the string's first / last byte), so nothing
+// outside the string's own 16-byte-aligned extent is ever touched; clamped positions deliver don't-care bytes.
+struct Stream {
+    uintptr_t next;    // address of the next vector to fetch (unclamped)
+    uintptr_t lo, hi;  // clamp range (aligned)
+    uint32_t wsel;     // word offset of the stream start inside its first vector (0..3)
+    uint32_t bsh;      // 8 * byte offset inside the word (0, 8, 16, 24)
+    V4 cur, nxt;       // vectors c and c+1 of the stream
+
+    TA_HD V4 fetch() {
+        uintptr_t p = next < lo ? lo : (next > hi ? hi : next);
+        next += 16;
+        return ldvec((const uint8_t *)p);
+    }
+    // start: address of logical byte 0 (may lie before first); first/last: first and last valid byte addresses
+    TA_HD void init(intptr_t start, uintptr_t first, uintptr_t last) {
+        lo = first & ~(uintptr_t)15;
+        hi = last & ~(uintptr_t)15;
+        const uintptr_t s = (uintptr_t)start;
+        next = s & ~(uintptr_t)15;
+        wsel = (uint32_t)(s >> 2) & 3u;
+        bsh = ((uint32_t)s & 3u) * 8u;
+        cur = fetch();
+        nxt = fetch();
+    }
+    // the next 16 logical bytes as four little-endian words; advances the stream
+    TA_HD void take(uint32_t out[4]) {
+        const uint32_t v[8] = {cur.x, cur.y, cur.z, cur.w, nxt.x, nxt.y, nxt.z, nxt.w};
+        uint32_t z[7], y[5];
+        const bool s1 = wsel & 1u, s2 = wsel & 2u;
+#pragma unroll
+        for (int i = 0; i < 7; i++) z[i] = s1 ? v[i + 1] : v[i];
+#pragma unroll
+        for (int i = 0; i < 5; i++) y[i] = s2 ? z[i + 2] : z[i];
+#pragma unroll
+        for (int i = 0; i < 4; i++) out[i] = funnel_r(y[i], y[i + 1], bsh);
+        cur = nxt;
+        nxt = fetch();
+    }
+};
+
+// flags (bit 7 of each byte) of the bytes of r that equal the corresponding byte of bb
+TA_HD uint32_t eq_flags(uint32_t r, uint32_t bb) {
+    const uint32_t x = r ^ bb;
+    const uint32_t t = (x & 0x7f7f7f7fu) + 0x7f7f7f7fu;
+    return ~(t | x) & 0x80808080u;
+}
+
+// Distance of one pair, `a` being the shorter string (m <= n), unit costs.  Requires m >= 1 and
+// diff + 2e + 1 <= 32 with e = (max_k - diff)/2 (+1 if TRANS).  Returns the exact distance whenever it is
+// <= max_k (and some value > max_k otherwise).
+template <bool TRANS>
+TA_HD uint32_t distance32(const uint8_t *a, int m, const uint8_t *b, int n, uint32_t max_k) {
+    const int diff = n - m;
+    const int e = (int)((max_k - (uint32_t)diff) >> 1) + (TRANS ? 1 : 0);
+    const int dhi = diff + e;  // window row p of column j is matrix row i = j - dhi + p
+
+    Stream sa, sb;
+    sa.init((intptr_t)a - dhi, (uintptr_t)a, (uintptr_t)a + m - 1);
+    sb.init((intptr_t)b, (uintptr_t)b, (uintptr_t)b + n - 1);
+
+    // initial window = pattern-stream bytes 0..31, transposed: register q, byte t <- stream byte q + 8t
+    uint32_t R[8];
+    {
+        uint32_t x[8];
+        sa.take(x);
+        sa.take(x + 4);
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const int w = q >> 2, bsel = q & 3;
+            const uint32_t lo2 = prmt(x[w], x[w + 2], (uint32_t)(bsel | ((4 + bsel) << 4)));      // bytes t = 0, 1
+            const uint32_t hi2 = prmt(x[w + 4], x[w + 6], (uint32_t)(bsel | ((4 + bsel) << 4)));  // bytes t = 2, 3
+            R[q] = prmt(lo2, hi2, 0x5410);
+        }
+    }
+
+    uint32_t VP = dhi >= 32 ? 0u : (0xffffffffu << dhi);  // rows i >= 1: vertical delta +1 in column 0
+    uint32_t VN = ~VP;                                    // rows i <= 0: virtual cells, delta -1
+    uint32_t D0prev = 0xffffffffu, Eqprev = 0;
+    uint32_t matches = 0;  // columns whose final-diagonal cell has diagonal delta 0
+
+    for (int j0 = 0; j0 < n; j0 += 16) {
+        uint32_t aw[4], bw[4];
+        sa.take(aw);
+        sb.take(bw);
+        uint32_t hist = 0;
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            const uint32_t bsel = (uint32_t)(u & 3);
+            const uint32_t bb = prmt(bw[u >> 2], 0, bsel * 0x1111u);  // text byte of this column, broadcast
+            uint32_t Eq = 0;
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                // role q is played by register (q + u) & 7 (the window slid u rows since the chunk began)
+                Eq |= eq_flags(R[(q + u) & 7], bb) >> (7 - q);
+            }
+            uint32_t D0 = (((Eq & VP) + VP) ^ VP) | Eq | VN;
+            if (TRANS) {
+                D0 |= ~D0prev & (Eq << 1) & (Eqprev >> 1);
+                D0prev = D0;
+                Eqprev = Eq;
+            }
+            const uint32_t HP = VN | ~(D0 | VP);
+            const uint32_t HN = D0 & VP;
+            const uint32_t X = D0 >> 1;
+            VN = X & HP;
+            VP = HN | ~(X | HP);
+            hist = funnel_r(hist, D0 >> e, 1);  // column u's flag ends up at bit 16 + u
+            // slide: the oldest register (role 0) drops its byte 0 and takes the next pattern byte as role 7
+            R[u & 7] = prmt(R[u & 7], aw[u >> 2], 0x0321u | ((4u + bsel) << 12));
+        }
+        const int cols = n - j0;  // columns of this chunk that exist
+        const uint32_t valid = cols >= 16 ? 0xffff0000u : (((1u << cols) - 1u) << 16);
+#if defined(__CUDA_ARCH__)
+        matches += __popc(hist & valid);
+#else
+        matches += (uint32_t)__builtin_popcount(hist & valid);
+#endif
+    }
+    return (uint32_t)diff + (uint32_t)n - matches;
+}
+
+// The whole per-pair contract of levenshtein_naive_k_with_opts for unit costs (reference
+// src/levenshtein.rs:386-430, 539-541): swap so a is shorter, clamp k, early None, then the banded distance.
+// can_handle(k, trans, max_len) on the host guarantees the band fits 32 rows.
+template <bool TRANS>
+TA_HD uint32_t pair_unit_costs(const uint8_t *a, uint64_t a_len, const uint8_t *b, uint64_t b_len, uint32_t k) {
+    if (a_len > b_len) {
+        const uint8_t *tp = a;
+        a = b;
+        b = tp;
+        const uint64_t tl = a_len;
+        a_len = b_len;
+        b_len = tl;
+    }
+    const int m = (int)a_len, n = (int)b_len;
+    const uint32_t diff = (uint32_t)(n - m);
+    // max_k = min(k, min(m*1, 2m*1) + diff*1) = min(k, n)   (src/levenshtein.rs:400-423 with unit costs)
+    const uint32_t max_k = k < (uint32_t)n ? k : (uint32_t)n;
+    if (diff > max_k) return 0xFFFFFFFFu;  // unit_k = max_k (src/levenshtein.rs:426-430)
+    if (m == 0) return (uint32_t)n;        // n <= max_k here
+    const uint32_t d = distance32<TRANS>(a, m, b, n, max_k);
+    return d <= max_k ? d : 0xFFFFFFFFu;
+}
+
+}  // namespace bitpar
