@@ -37,6 +37,10 @@ WORKLOADS = {
                             "RDAMERAU_COSTS k=16, 1M pairs len=512, set M (U[0,16] edits incl. swaps)"),
     "lev_k16_len4096": ("lev_k", 65_536, 4096, 16, (1, 1, 0, 0),
                         "levenshtein_simd_k k=16, 64Ki pairs len=4096, unit costs, set M"),
+    "exp_len1024": ("exp", 1_000_000, 1024, 30, (1, 1, 0, 0),
+                    "levenshtein_exp, 1M pairs len=1024, exactly 4 random edits (first round k=30 succeeds)"),
+    "search_n32_h4096": ("search", 100_000, 4096, 3, (1, 1, 0, 0),
+                         "levenshtein_search needle len=32 over 100k haystacks len=4096, k=3, Best, 1% planted hits"),
     "hamming_len64": ("hamming", 10_000, 64, 0, (1, 1, 0, 0), "hamming, 10k pairs len=64 (plumbing case)"),
     "hamming_len4096": ("hamming", 262_144, 4096, 0, (1, 1, 0, 0), "hamming, 256Ki pairs len=4096"),
 }
@@ -52,7 +56,32 @@ def make_inputs(op, n, length, k, costs, seed):
     from triple_accel_b200 import synth
     if op == "hamming":
         return synth.hamming_pairs(n, length, seed=seed)
+    if op == "exp":
+        return synth.mutated_pairs(n, length, 4, seed=seed, exact_edits=True)
+    if op == "search":  # (needle, needle offsets placeholder, haystack bytes, haystack offsets)
+        needle, hay, hoff = synth.needle_haystacks(n, length, 32, plant_frac=0.01, max_edits=3, seed=seed)
+        return needle, np.array([0, len(needle)], np.uint64), hay, hoff
     return synth.mutated_pairs(n, length, k, seed=seed, allow_swap=bool(costs[3]))
+
+
+def cells_per_unit(op, length, k):
+    if op == "hamming":
+        return length
+    if op == "search":
+        return 32 * length  # needle_len x haystack_len cells of the reference's scalar search DP
+    return nominal_cells(length, k)
+
+
+def oracle_run(orc, op, a, ao, b, bo, k, costs, cnt, threads):
+    """the oracle on the first cnt units; returns something comparable with gpu_result()"""
+    if op == "hamming":
+        return orc.hamming_batch(a, ao[:cnt + 1], b, bo[:cnt + 1], threads=threads)
+    if op == "exp":
+        return orc.levenshtein_exp_batch(a, ao[:cnt + 1], b, bo[:cnt + 1], costs, threads=threads)
+    if op == "search":
+        m, off = orc.levenshtein_search_batch(a, b, bo[:cnt + 1], k, 1, costs, False, threads=threads)
+        return np.concatenate([off.astype(np.uint64), m.reshape(-1)])
+    return orc.levenshtein_k_batch(a, ao[:cnt + 1], b, bo[:cnt + 1], k, costs, threads=threads)
 
 
 class ClockSampler:
@@ -123,14 +152,12 @@ def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = min(n, args.cpu_sample)
+    sample = min(n, args.cpu_sample if op != "search" else max(1, args.cpu_sample // 100))
     a, ao, b, bo = make_inputs(op, sample, length, k, costs, 1234)
     threads = orc.max_threads()
 
     def step():
-        if op == "hamming":
-            return orc.hamming_batch(a, ao, b, bo, threads=threads)
-        return orc.levenshtein_k_batch(a, ao, b, bo, k, costs, threads=threads)
+        return oracle_run(orc, op, a, ao, b, bo, k, costs, sample, threads)
 
     for _ in range(args.warmup):
         step()
@@ -138,7 +165,7 @@ def run_reference(args, wl):
     for _ in range(args.steps):
         step()
     dt = (time.perf_counter() - t0) / args.steps
-    cells = nominal_cells(length, k) if op != "hamming" else length
+    cells = cells_per_unit(op, length, k)
     val = sample * cells / dt / 1e9
     line = {
         "impl": "reference", "metric": "dp_cell_updates_per_s", "value": val, "unit": "GCUPS", "n_gpus": args.gpus,
@@ -202,11 +229,24 @@ def main():
     d_a, d_ao, d_b, d_bo = to_dev(a), to_dev(ao), to_dev(b), to_dev(bo)
     d_out = torch.empty(n, dtype=torch.int32, device=dev)
 
+    last = {}
+
     def step_dev():
         if op == "hamming":
             eng.hamming_batch_dev(d_a, d_ao, d_b, d_bo, d_out)
+        elif op == "exp":
+            eng.levenshtein_exp_batch_dev(d_a, d_ao, d_b, d_bo, costs, max_len, d_out)
+        elif op == "search":
+            last["m"] = eng.levenshtein_search_batch_dev(a, d_b, d_bo, max_len, k, 1, costs, False)
         else:
             eng.levenshtein_k_batch_dev(d_a, d_ao, d_b, d_bo, k, costs, max_len, d_out)
+
+    def gpu_result(cnt):
+        if op == "search":
+            m, off = last["m"]
+            tot = int(off[cnt])
+            return np.concatenate([off[:cnt + 1].astype(np.uint64), m[:tot].reshape(-1)])
+        return d_out[:cnt].cpu().numpy().view(np.uint32)
 
     def barrier():
         if dist is not None:
@@ -242,18 +282,16 @@ def main():
     # parity spot check on the timed output (bounded sample, oracle as the checker)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import _oracle as orc
-    chk = min(n, 20000)
-    got = d_out[:chk].cpu().numpy().view(np.uint32)
-    if op == "hamming":
-        want = orc.hamming_batch(a, ao[:chk + 1], b, bo[:chk + 1], threads=orc.max_threads())
-    else:
-        want = orc.levenshtein_k_batch(a, ao[:chk + 1], b, bo[:chk + 1], k, costs, threads=orc.max_threads())
+    chk = min(n, {"search": 2000, "exp": 5000}.get(op, 20000))
+    got = gpu_result(chk)
+    want = oracle_run(orc, op, a, ao, b, bo, k, costs, chk, orc.max_threads())
     parity_ok = bool(np.array_equal(got, want))
 
-    cells_pair = nominal_cells(length, k) if op != "hamming" else length
+    cells_pair = cells_per_unit(op, length, k)
     total_pairs = n * world
     value = total_pairs * cells_pair / (ms_step * 1e-3) / 1e9
-    alg_bytes = int(a.nbytes + b.nbytes + 4 * n)  # |a| + |b| + 4 per pair (offsets: +16 B/pair, not counted)
+    # algorithmic bytes: |a| + |b| + 4 per pair (CSR offsets, +16 B/pair, not counted); search: |haystack|
+    alg_bytes = int(b.nbytes) if op == "search" else int(a.nbytes + b.nbytes + 4 * n)
 
     # ---- end to end through the host-buffer C ABI (pinned host inputs; H2D + kernel + D2H timed) --------------
     e2e = None
@@ -267,6 +305,10 @@ def main():
         def step_host():
             if op == "hamming":
                 eng.hamming_batch(pa, pao, pb, pbo, out=pout)
+            elif op == "exp":
+                eng.levenshtein_exp_batch(pa, pao, pb, pbo, costs, out=pout)
+            elif op == "search":
+                last["m"] = eng.levenshtein_search_batch(pa, pb, pbo, k, 1, costs, False)
             else:
                 eng.levenshtein_k_batch(pa, pao, pb, pbo, k, costs, out=pout)
 
@@ -284,7 +326,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         dt /= e_steps
-        assert np.array_equal(pout[:chk], want), "e2e parity"
+        assert np.array_equal(gpu_result(chk) if op == "search" else pout[:chk], want), "e2e parity"
         e2e = {"value": total_pairs * cells_pair / dt / 1e9, "unit": "GCUPS",
                "h2d_bytes_per_step": int(a.nbytes + b.nbytes + ao.nbytes + bo.nbytes), "d2h_bytes_per_step": int(4 * n),
                "ms_per_step": dt * 1e3, "pairs_per_s": total_pairs / dt}
@@ -306,20 +348,20 @@ def main():
         traffic = json.load(open(tpath)).get(args.workload)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                "kernel": "lev_bitpar / lev_band (see DESIGN.md)" if op != "hamming" else "hamming_kernel"}
+                "kernel": {"hamming": "hamming_kernel", "search": "search_filter_kernel (+ search_exact_kernel on hits)"}
+                .get(op, "lev_bitpar32_kernel")}
 
     cpu_baseline = None
     if not args.no_cpu_baseline:
-        sample = min(n, args.cpu_sample)
+        sample = min(n, args.cpu_sample if op != "search" else max(1, args.cpu_sample // 100))
+        if op == "exp":
+            sample = min(sample, 20000)
         threads = orc.max_threads()
         t0 = time.perf_counter()
-        if op == "hamming":
-            orc.hamming_batch(a, ao[:sample + 1], b, bo[:sample + 1], threads=threads)
-        else:
-            orc.levenshtein_k_batch(a, ao[:sample + 1], b, bo[:sample + 1], k, costs, threads=threads)
+        oracle_run(orc, op, a, ao, b, bo, k, costs, sample, threads)
         dt = time.perf_counter() - t0
         cpu_baseline = {"value": sample * cells_pair / dt / 1e9, "unit": "GCUPS", "cores": threads, "kind": "port",
-                        "sample": "first %d pairs of the same batch, scalar oracle on %d threads" % (sample, threads),
+                        "sample": "first %d units of the same batch, scalar oracle on %d threads" % (sample, threads),
                         "pairs_per_s": sample / dt}
 
     line = {

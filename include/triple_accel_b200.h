@@ -128,6 +128,17 @@ int ta_hamming_batch_dev(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, c
 int ta_levenshtein_k_batch_dev(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b,
                                const uint64_t *b_off, size_t n, uint32_t k, ta_costs costs, uint32_t max_len,
                                uint32_t *out, void *stream);
+/* Exponential-k driver on device-resident pairs.  Synchronises `stream` between rounds (it has to read how many
+ * pairs are still TA_NONE); results are complete in `out` when it returns. */
+int ta_levenshtein_exp_batch_dev(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b,
+                                 const uint64_t *b_off, size_t n, ta_costs costs, uint32_t max_len, uint32_t *out,
+                                 void *stream);
+/* Search over device-resident haystacks (`needle` is a HOST pointer, needle_len >= 1; `max_hay_len` bounds the
+ * haystack lengths).  Match arrays are returned in host memory exactly as by ta_levenshtein_search_batch. */
+int ta_levenshtein_search_batch_dev(ta_ctx *ctx, const uint8_t *needle, size_t needle_len, const uint8_t *hay,
+                                    const uint64_t *hay_off, size_t n, uint64_t max_hay_len, uint32_t k,
+                                    int search_type, ta_costs costs, int anchored, ta_match **out_matches,
+                                    uint64_t **out_match_off, void *stream);
 /* Synchronises `stream` and reports a deferred contract violation seen by a *_dev kernel (e.g. a Hamming
  * length mismatch), clearing it. */
 int ta_dev_status(ta_ctx *ctx, void *stream);

@@ -312,14 +312,67 @@ def test_device_resident_entry_points(eng):
         eng.dev_status()
 
 
-def test_general_band_kernel_forced():
-    """The dispatcher sends unit-cost / narrow-band batches to the bit-parallel kernel; TA_FORCE_BAND=1 routes
-    them through the general anti-diagonal kernel instead.  Run the unit-cost differential tests again in a
-    subprocess with that switch so both kernels are pinned to the oracle on the same inputs."""
+def test_exp_and_search_device_entry_points(eng):
+    import torch
+    from triple_accel_b200 import synth
+    dev = torch.device("cuda", eng.device)
+
+    def to_dev(x):
+        return torch.from_numpy(x.view(np.int64) if x.dtype == np.uint64 else x).to(dev)
+
+    a, ao, b, bo = synth.mutated_pairs(3000, 300, 50, seed=11)
+    out = torch.empty(3000, dtype=torch.int32, device=dev)
+    eng.levenshtein_exp_batch_dev(to_dev(a), to_dev(ao), to_dev(b), to_dev(bo), (1, 1, 0, 0), 400, out)
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), orc.levenshtein_exp_batch(a, ao, b, bo, threads=8))
+    needle, hay, hoff = synth.needle_haystacks(400, 2048, 32, plant_frac=0.1, seed=12)
+    for st in (0, 1):
+        got, goff = eng.levenshtein_search_batch_dev(needle, to_dev(hay), to_dev(hoff), 2048, 3, st)
+        want, woff = orc.levenshtein_search_batch(needle, hay, hoff, 3, st, threads=8)
+        assert np.array_equal(goff, woff) and np.array_equal(got, want)
+
+
+def test_search_filter_long_needles_and_transpositions(eng):
+    """the bit-parallel pre-filter (needle <= 64, unit costs, with and without transpositions) must never drop a
+    haystack that has a match: compare the full match lists with the oracle"""
+    rng = random.Random(77)
+    for nlen in (7, 31, 32, 33, 48, 64, 65):
+        for costs in ((1, 1, 0, 0), (1, 1, 0, 1)):
+            alpha = 4
+            needle = bytes(rng.randrange(alpha) for _ in range(nlen))
+            hays = []
+            for _ in range(150):
+                h = bytearray(rng.randrange(alpha) for _ in range(rng.randrange(0, 1500)))
+                if rng.random() < 0.4 and len(h) > nlen + 2:
+                    p = rng.randrange(len(h) - nlen)
+                    h[p:p + nlen] = _mutate(rng, needle, rng.randrange(0, 5), alpha)[:nlen]
+                hays.append(bytes(h))
+            hay, hoff = _pack(hays)
+            for k in (0, 2, nlen // 4, nlen - 1):
+                got, goff = eng.levenshtein_search_batch(needle, hay, hoff, k, 0, costs)
+                want, woff = orc.levenshtein_search_batch(needle, hay, hoff, k, 0, costs, threads=8)
+                assert np.array_equal(goff, woff) and np.array_equal(got, want), (nlen, costs, k)
+
+
+LEV_TESTS = "test_lev_k_mutated or test_lev_k_random_short or test_nul_bytes or test_lev_exp"
+SEARCH_TESTS = ("test_search_random or test_search_planted or test_kat_search or "
+                "test_search_filter_long_needles_and_transpositions")
+
+
+@pytest.mark.parametrize("env,select", [
+    ({"TA_FORCE_BAND": "1"}, LEV_TESTS),
+    ({"TA_NO_SEARCH_FILTER": "1", "TA_SEARCH_KERNEL": "thread"}, SEARCH_TESTS),
+    ({"TA_NO_SEARCH_FILTER": "1", "TA_SEARCH_KERNEL": "wave"}, SEARCH_TESTS),
+    ({"TA_SEARCH_KERNEL": "thread"}, SEARCH_TESTS),
+], ids=["general-band-kernel", "search-thread-kernel-nofilter", "search-wave-kernel-nofilter",
+        "search-thread-kernel-filter"])
+def test_every_kernel_variant_forced(env, select):
+    """The dispatchers pick a kernel from the cost model, band width and batch size (bit-parallel vs general banded
+    kernel; pre-filter + warp-wavefront vs thread-per-haystack exact search).  These switches force the variants
+    the default run does not reach, and the differential tests run again in a subprocess, so that every kernel is
+    pinned to the oracle on the same inputs."""
     import subprocess
     import sys
-    env = dict(os.environ, TA_FORCE_BAND="1")
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", os.path.abspath(__file__), "-k",
-                        "test_lev_k_mutated or test_lev_k_random_short or test_nul_bytes or test_lev_exp"],
-                       env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+                        select], env=dict(os.environ, **env), capture_output=True, text=True,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

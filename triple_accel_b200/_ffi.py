@@ -52,6 +52,10 @@ SIGNATURES = {
     "ta_search_default_k": (_u32, [_sz]),
     "ta_hamming_batch_dev": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "ta_levenshtein_k_batch_dev": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, _u32, ta_costs, _u32, _vp, _vp]),
+    "ta_levenshtein_exp_batch_dev": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, ta_costs, _u32, _vp, _vp]),
+    "ta_levenshtein_search_batch_dev": (_int, [_vp, _vp, _sz, _vp, _vp, _sz, C.c_uint64, _u32, _int, ta_costs, _int,
+                                               C.POINTER(C.POINTER(ta_match)), C.POINTER(C.POINTER(C.c_uint64)),
+                                               _vp]),
     "ta_dev_status": (_int, [_vp, _vp]),
     "ta_hamming": (_int, [_vp, C.c_char_p, _sz, C.c_char_p, _sz, C.POINTER(_u32)]),
     "ta_levenshtein_simd_k_with_opts": (_int, [_vp, C.c_char_p, _sz, C.c_char_p, _sz, _u32, ta_costs,

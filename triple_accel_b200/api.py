@@ -177,6 +177,9 @@ class Engine:
                                                    int(k) & 0xFFFFFFFF, int(search_type), _as_costs(costs)._c(),
                                                    int(bool(anchored)), C.byref(mp), C.byref(op))
         self._check(rc)
+        return self._take_matches(mp, op, n)
+
+    def _take_matches(self, mp, op, n):
         try:
             moff = np.ctypeslib.as_array(op, shape=(n + 1,)).copy()
             total = int(moff[n])
@@ -210,6 +213,25 @@ class Engine:
                                                          _as_costs(costs)._c(), int(max_len), out.data_ptr(),
                                                          self._stream(stream)))
         return out
+
+    def levenshtein_exp_batch_dev(self, a, a_off, b, b_off, costs, max_len, out, stream=None):
+        n = a_off.numel() - 1
+        self._check(self._lib.ta_levenshtein_exp_batch_dev(self._h, a.data_ptr(), a_off.data_ptr(), b.data_ptr(),
+                                                           b_off.data_ptr(), n, _as_costs(costs)._c(), int(max_len),
+                                                           out.data_ptr(), self._stream(stream)))
+        return out
+
+    def levenshtein_search_batch_dev(self, needle, hay, hay_off, max_hay_len, k, search_type=SearchType.All,
+                                     costs=LEVENSHTEIN_COSTS, anchored=False, stream=None):
+        needle = _u8(needle)
+        n = hay_off.numel() - 1
+        mp, op = C.POINTER(ta_match)(), C.POINTER(C.c_uint64)()
+        rc = self._lib.ta_levenshtein_search_batch_dev(self._h, _ptr(needle), len(needle), hay.data_ptr(),
+                                                       hay_off.data_ptr(), n, int(max_hay_len), int(k) & 0xFFFFFFFF,
+                                                       int(search_type), _as_costs(costs)._c(), int(bool(anchored)),
+                                                       C.byref(mp), C.byref(op), self._stream(stream))
+        self._check(rc)
+        return self._take_matches(mp, op, n)
 
     def dev_status(self, stream=None):
         self._check(self._lib.ta_dev_status(self._h, self._stream(stream)))

@@ -357,6 +357,20 @@ int ta_levenshtein_k_batch_dev(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_
     return ta_launch_lev(ctx, a, a_off, b, b_off, n, nullptr, k, costs, max_len, out, (cudaStream_t)stream);
 }
 
+int ta_levenshtein_exp_batch_dev(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b,
+                                 const uint64_t *b_off, size_t n, ta_costs costs, uint32_t max_len, uint32_t *out,
+                                 void *stream) {
+    if (!ctx) return TA_ERR_BAD_ARG;
+    int rc = check_costs(costs);
+    if (rc != TA_OK) return rc;
+    if (n == 0) return TA_OK;
+    if (!a_off || !b_off || !out) return TA_ERR_BAD_ARG;
+    if (max_len > TA_MAX_STRING_LEN || n > 0xFFFFFFF0ull) return TA_ERR_TOO_LARGE;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    TA_CUDA(ctx, cudaSetDevice(ctx->device));
+    return exp_rounds_dev(ctx, a, a_off, b, b_off, n, costs, max_len, out, (cudaStream_t)stream);
+}
+
 int ta_dev_status(ta_ctx *ctx, void *stream) {
     if (!ctx) return TA_ERR_BAD_ARG;
     std::lock_guard<std::mutex> lock(ctx->mu);

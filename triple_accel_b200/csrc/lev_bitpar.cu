@@ -47,10 +47,104 @@ int ta_launch_lev_bitpar(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, c
     return TA_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Search pre-filter: Myers' bit-vector algorithm in its semi-global (search) form, one needle against many
+// haystacks.  Computes, for every end position, the unit-cost distance of the best alignment of the whole needle
+// ending there (the same cost the reference's scalar search DP produces, src/levenshtein.rs:1723-1806, without the
+// match-length bookkeeping) and flags the haystack as soon as one position is within k.  Flagged haystacks are
+// then re-run by the exact (cost, length) kernel in search.cu; unflagged ones provably have no match.
+//
+// Work split: thread (h, s) scans segment s (SEG bytes) of haystack h after a warm-up of 2*N bytes, which is
+// enough for the column state to be exact (an optimal alignment of a needle prefix of length i spans at most 2i
+// haystack bytes under unit costs).  The 256-entry match-mask table of the needle lives in shared memory.
+namespace {
+
+constexpr int FILTER_SEG = 512;
+
+template <typename W, bool TRANS>
+__global__ void __launch_bounds__(128) search_filter_kernel(const uint8_t *__restrict__ needle, uint32_t N,
+                                                            const uint8_t *__restrict__ hay,
+                                                            const uint64_t *__restrict__ hay_off, size_t n, uint32_t k,
+                                                            uint32_t *__restrict__ flags) {
+    __shared__ W peq[256];
+    for (int c = threadIdx.x; c < 256; c += blockDim.x) peq[c] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (uint32_t i = 0; i < N; i++) peq[needle[i]] |= (W)1 << i;
+    __syncthreads();
+
+    const size_t h = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= n) return;
+    const uint64_t h0 = hay_off[h], h1 = hay_off[h + 1];
+    const uint64_t H = h1 - h0;
+    const uint64_t seg_begin = (uint64_t)blockIdx.y * FILTER_SEG;
+    if (seg_begin >= H) return;
+    const uint64_t seg_end = seg_begin + FILTER_SEG < H ? seg_begin + FILTER_SEG : H;
+    const uint64_t warm = 2ull * N;
+    const uint64_t start = seg_begin > warm ? seg_begin - warm : 0;
+    const uint8_t *p = hay + h0;
+
+    W VP = ~(W)0, VN = 0, D0prev = ~(W)0, Eqprev = 0;
+    uint32_t score = N;
+    const W top = (W)1 << (N - 1);
+    for (uint64_t x = start; x < seg_end; x++) {
+        const W Eq = peq[__ldg(p + x)];
+        W D0 = (((Eq & VP) + VP) ^ VP) | Eq | VN;
+        if (TRANS) {
+            D0 |= ((~D0prev & Eq) << 1) & Eqprev;
+            D0prev = D0;
+            Eqprev = Eq;
+        }
+        W HP = VN | ~(D0 | VP);
+        W HN = D0 & VP;
+        score += (HP & top) ? 1u : 0u;
+        score -= (HN & top) ? 1u : 0u;
+        HP <<= 1;  // row 0 of a search has horizontal delta 0
+        HN <<= 1;
+        VP = HN | ~(D0 | HP);
+        VN = D0 & HP;
+        if (x >= seg_begin && score <= k) {
+            flags[h] = 1;
+            return;
+        }
+    }
+}
+
+__global__ void collect_flagged_kernel(const uint32_t *__restrict__ flags, size_t n, uint32_t *__restrict__ idx_out,
+                                       uint32_t *__restrict__ counter) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        if (flags[i]) idx_out[atomicAdd(counter, 1u)] = (uint32_t)i;
+}
+
+}  // namespace
+
+// flags haystacks with at least one end position of unit-cost distance <= k and writes their indices (unordered)
+// to idx_out, the count to *counter.  Needs needle_len in [1, 64]; max_hay = longest haystack.
 int ta_launch_search_filter(ta_ctx *ctx, const uint8_t *needle_dev, uint32_t needle_len, const uint8_t *hay,
-                            const uint64_t *hay_off, size_t n, uint32_t k, bool transpose, uint32_t *idx_out,
-                            uint32_t *counter, cudaStream_t st) {
-    (void)ctx, (void)needle_dev, (void)needle_len, (void)hay, (void)hay_off, (void)n, (void)k, (void)transpose;
-    (void)idx_out, (void)counter, (void)st;
-    return TA_ERR_TOO_LARGE;  // not available: caller runs the exact kernel on every haystack
+                            const uint64_t *hay_off, size_t n, uint64_t max_hay, uint32_t k, bool transpose,
+                            uint32_t *flags, uint32_t *idx_out, uint32_t *counter, cudaStream_t st) {
+    if (needle_len == 0 || needle_len > 64) return TA_ERR_TOO_LARGE;
+    if (n == 0 || max_hay == 0) return TA_OK;
+    const uint64_t segs = (max_hay + FILTER_SEG - 1) / FILTER_SEG;
+    if (segs > 65535) return TA_ERR_TOO_LARGE;
+    TA_CUDA(ctx, cudaMemsetAsync(flags, 0, n * sizeof(uint32_t), st));
+    const dim3 grid((unsigned)((n + 127) / 128), (unsigned)segs);
+    if (needle_len <= 32) {
+        if (transpose)
+            search_filter_kernel<uint32_t, true><<<grid, 128, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, k, flags);
+        else
+            search_filter_kernel<uint32_t, false><<<grid, 128, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, k, flags);
+    } else {
+        if (transpose)
+            search_filter_kernel<uint64_t, true><<<grid, 128, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, k, flags);
+        else
+            search_filter_kernel<uint64_t, false><<<grid, 128, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, k, flags);
+    }
+    ctx->launches++;
+    TA_CUDA(ctx, cudaGetLastError());
+    const unsigned cblocks = (unsigned)((n + 255) / 256 < (size_t)ctx->sm_count * 8 ? (n + 255) / 256 : (size_t)ctx->sm_count * 8);
+    collect_flagged_kernel<<<cblocks, 256, 0, st>>>(flags, n, idx_out, counter);
+    ctx->launches++;
+    TA_CUDA(ctx, cudaGetLastError());
+    return TA_OK;
 }

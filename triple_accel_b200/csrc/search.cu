@@ -22,8 +22,8 @@
 
 // implemented in lev_bitpar.cu: flags[i] = 1 iff haystack i has an end position with unit-cost distance <= k
 int ta_launch_search_filter(ta_ctx *ctx, const uint8_t *needle_dev, uint32_t needle_len, const uint8_t *hay,
-                            const uint64_t *hay_off, size_t n, uint32_t k, bool transpose, uint32_t *idx_out,
-                            uint32_t *counter, cudaStream_t st);
+                            const uint64_t *hay_off, size_t n, uint64_t max_hay, uint32_t k, bool transpose,
+                            uint32_t *flags, uint32_t *idx_out, uint32_t *counter, cudaStream_t st);
 
 namespace {
 
@@ -199,11 +199,343 @@ __global__ void __launch_bounds__(64) search_exact_kernel(const SearchArgs args)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// search_wave_kernel: the same exact (cost, length) recurrence, one WARP per haystack.  Lane t owns needle rows
+// t*C+1 .. t*C+C and is skewed t columns behind lane 0 (lane t handles haystack column x = s - t at step s), so the
+// (x, j-1) neighbour state it needs was produced by lane t-1 one step earlier and arrives by __shfl_up_sync; the
+// (x-1, j-1) and (x-2, j-2) values are the ones received one and two steps before.  Used when few haystacks survive
+// the pre-filter (a thread-per-haystack walk would leave the GPU idle) and for needles of up to 32*8 rows.
+template <int C, bool TRANS>
+__global__ void __launch_bounds__(128) search_wave_kernel(const SearchArgs args) {
+    const unsigned full = 0xffffffffu;
+    const int t = threadIdx.x & 31;
+    const size_t w = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= args.n) return;  // whole warp
+    const uint32_t hidx = args.idx ? args.idx[w] : (uint32_t)w;
+    const uint64_t h0 = args.hay_off[hidx], h1 = args.hay_off[hidx + 1];
+    const uint8_t *hay = args.hay + h0;
+    const uint64_t H = h1 - h0;
+    const uint32_t N = args.needle_len;
+    const uint32_t mism = args.mism, gap = args.gap, sgap = args.sgap, tcost = args.tcost, k = args.k;
+    const uint32_t open = sgap + gap;
+    const bool anchored = args.anchored != 0;
+    uint64_t iter_len = H;  // src/levenshtein.rs:1650-1661
+    if (anchored) {
+        const uint64_t lim = (uint64_t)N + (uint64_t)((k > sgap ? k - sgap : 0u) / gap);
+        iter_len = H < lim ? H : lim;
+    }
+
+    // rows owned by this lane: j = t*C + c + 1
+    uint32_t nc[C], dp1[C], len1[C], ng[C], ngl[C], dp2[C], len2[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        const uint32_t j = (uint32_t)(t * C + c + 1);
+        nc[c] = j <= N ? (uint32_t)args.needle[j - 1] : 0x100u;  // rows past the needle never match
+        dp1[c] = j * gap + sgap;                                   // column 0 (:1689-1691)
+        len1[c] = 0;
+        ng[c] = TA_INF;
+        ngl[c] = 0;
+        dp2[c] = 0;
+        len2[c] = 0;
+    }
+    const uint32_t nprev0 = (t * C >= 1 && (uint32_t)(t * C) <= N) ? (uint32_t)args.needle[t * C - 1] : 0x100u;
+
+    // state of the row just above this lane's rows (row t*C): received values for columns x, x-1, x-2
+    uint32_t Ldp1 = (uint32_t)(t * C) * gap + (t ? sgap : 0u), Llen1 = 0;  // column x-1 (starts as column 0)
+    uint32_t Ldp2 = 0, Llen2 = 0;                                            // column x-2
+    uint32_t T0dp1 = 0, T0len1 = 0;  // (x-2, row t*C-1) once shifted; pipeline of the value forwarded for TRANS
+    // what this lane offers to lane t+1: its last row at the column it just finished
+    uint32_t out_dp = dp1[C - 1], out_len = 0, out_hg = TA_INF, out_hgl = 0;
+    uint32_t out_tdp = 0, out_tlen = 0;  // (col-1 of the finished column, row (t+1)*C - 1) for lane t+1's TRANS
+    uint32_t hc_prev = 0x200u;
+
+    const int last_t = (int)((N - 1) / C), last_c = (int)((N - 1) % C);
+    const uint64_t steps = iter_len + 31;
+    for (uint64_t s = 1; s <= steps; s++) {
+        // neighbour state for column x = s - t, produced by lane t-1 at step s-1
+        uint32_t Ldp = __shfl_up_sync(full, out_dp, 1);
+        uint32_t Llen = __shfl_up_sync(full, out_len, 1);
+        uint32_t Lhg = __shfl_up_sync(full, out_hg, 1);
+        uint32_t Lhgl = __shfl_up_sync(full, out_hgl, 1);
+        uint32_t Tdp = 0, Tlen = 0;
+        if (TRANS) {
+            Tdp = __shfl_up_sync(full, out_tdp, 1);
+            Tlen = __shfl_up_sync(full, out_tlen, 1);
+        }
+        const int64_t x = (int64_t)s - t;
+        const bool active = x >= 1 && (uint64_t)x <= iter_len;
+        if (t == 0) {  // row 0 (:1710-1721)
+            Ldp = anchored ? (uint32_t)x * gap + sgap : 0u;
+            Llen = 0;
+            Lhg = TA_INF;
+            Lhgl = 0;
+        }
+        if (active) {
+            const uint32_t hc = __ldg(hay + (x - 1));
+            // running (x, j-1) values, (x-1, j-1) diagonal, (x-2, j-2) for transpositions
+            uint32_t left_dp = Ldp, left_len = Llen, hgap = Lhg, hgap_len = Lhgl;
+            uint32_t diag_dp = Ldp1, diag_len = Llen1;
+            uint32_t tr_dp = T0dp1, tr_len = T0len1;      // (x-2, row t*C - 1): for c == 0
+            uint32_t tr_dp_next = Ldp2, tr_len_next = Llen2;  // (x-2, row t*C): for c == 1
+            uint32_t nprev = nprev0;
+            uint32_t new_out_tdp = 0, new_out_tlen = 0;
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                const uint32_t up_dp = dp1[c], up_len = len1[c];
+                const uint32_t sub = diag_dp + (nc[c] != hc ? mism : 0u);
+                const uint32_t sub_len = diag_len + 1;
+                {  // needle gap (:1726-1737)
+                    const uint32_t new_gap = up_dp + open, cont_gap = ng[c] + gap;
+                    if (new_gap < cont_gap) {
+                        ng[c] = new_gap;
+                        ngl[c] = up_len + 1;
+                    } else if (new_gap > cont_gap) {
+                        ng[c] = cont_gap;
+                        ngl[c] = ngl[c] + 1;
+                    } else {
+                        ng[c] = cont_gap;
+                        ngl[c] = max(up_len, ngl[c]) + 1;
+                    }
+                    ng[c] = min(ng[c], TA_INF);
+                }
+                {  // haystack gap (:1739-1750)
+                    const uint32_t new_gap = left_dp + open, cont_gap = hgap + gap;
+                    if (new_gap < cont_gap) {
+                        hgap = new_gap;
+                        hgap_len = left_len;
+                    } else if (new_gap > cont_gap) {
+                        hgap = cont_gap;
+                    } else {
+                        hgap = cont_gap;
+                        hgap_len = max(left_len, hgap_len);
+                    }
+                    hgap = min(hgap, TA_INF);
+                }
+                uint32_t dp = ng[c], len = ngl[c];
+                if (hgap < dp || (hgap == dp && left_len > len)) {  // :1755-1760
+                    dp = hgap;
+                    len = hgap_len;
+                }
+                if (sub < dp || (sub == dp && sub_len > len)) {  // :1762-1765
+                    dp = sub;
+                    len = sub_len;
+                }
+                if (TRANS) {
+                    const uint32_t j = (uint32_t)(t * C + c + 1);
+                    if (x > 1 && j > 1 && nc[c] == hc_prev && nprev == hc) {  // :1767-1779
+                        const uint32_t tr = tr_dp + tcost;
+                        if (tr <= dp) {
+                            dp = tr;
+                            len = tr_len + 2;
+                        }
+                    }
+                    // next cell's (x-2, j-2) is this cell's row - 1 at column x-2
+                    tr_dp = tr_dp_next;
+                    tr_len = tr_len_next;
+                    tr_dp_next = dp2[c];
+                    tr_len_next = len2[c];
+                    if (c == C - 2) {  // row (t+1)*C - 1 at column x-1: what lane t+1's first cell will need
+                        new_out_tdp = up_dp;
+                        new_out_tlen = up_len;
+                    }
+                    dp2[c] = up_dp;
+                    len2[c] = up_len;
+                }
+                dp1[c] = dp;
+                len1[c] = len;
+                diag_dp = up_dp;
+                diag_len = up_len;
+                left_dp = dp;
+                left_len = len;
+                nprev = nc[c];
+                if (c == last_c && t == last_t && dp <= k) {  // :1792-1806 (All threshold; Best on the host)
+                    const unsigned long long slot = atomicAdd(args.hit_count, 1ull);
+                    if (slot < args.hit_cap) {
+                        Hit h;
+                        h.hay = hidx;
+                        h.cost = dp;
+                        h.end = (uint64_t)x;
+                        h.len = len;
+                        args.hits[slot] = h;
+                    }
+                }
+            }
+            if (TRANS) {
+                if (C == 1) {  // row t at column x-1 is the row above this lane's single row: forward L(x-1)
+                    new_out_tdp = Ldp1;
+                    new_out_tlen = Llen1;
+                }
+                out_tdp = new_out_tdp;
+                out_tlen = new_out_tlen;
+                // shift the received-history pipelines
+                T0dp1 = Tdp;  // received now: (x-1, row t*C-1); next step it is (x-2, ...) relative to column x+1
+                T0len1 = Tlen;
+                Ldp2 = Ldp1;
+                Llen2 = Llen1;
+                hc_prev = hc;
+            }
+            Ldp1 = Ldp;
+            Llen1 = Llen;
+            out_dp = left_dp;
+            out_len = left_len;
+            out_hg = hgap;
+            out_hgl = hgap_len;
+        }
+    }
+}
+
 size_t exact_smem_bytes(uint32_t needle_len, bool trans, int threads) {
     return (size_t)(trans ? 6 : 4) * (needle_len + 1) * threads * sizeof(uint32_t) + ((needle_len + 15) & ~15u);
 }
 
 }  // namespace
+
+// Device phase: optional bit-parallel pre-filter, then the exact kernel on the surviving haystacks; returns every
+// end position with cost <= k as a Hit (unordered).  Caller holds ctx->mu and has set the device.
+static int search_device(ta_ctx *ctx, cudaStream_t st, const uint8_t *d_needle, size_t needle_len,
+                         const uint8_t *d_hay, const uint64_t *d_off, size_t n, uint64_t max_hay, uint32_t k,
+                         ta_costs costs, int anchored, std::vector<Hit> &hits) {
+    int rc;
+    const bool unit = costs.mismatch == 1 && costs.gap == 1 && costs.start_gap == 0 && costs.transpose <= 1;
+    const uint32_t *d_idx = nullptr;
+    size_t work_n = n;
+    static const bool no_filter = getenv("TA_NO_SEARCH_FILTER") != nullptr;  // testing: exact kernel on everything
+    if (!no_filter && unit && needle_len <= 64 && !anchored && k < needle_len) {
+        if ((rc = ta_dev_reserve(ctx, ctx->d_work[0], n * sizeof(uint32_t))) != TA_OK) return rc;
+        if ((rc = ta_dev_reserve(ctx, ctx->d_work[2], n * sizeof(uint32_t))) != TA_OK) return rc;
+        uint32_t *counter = ctx->d_flags + 2;
+        TA_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(uint32_t), st));
+        rc = ta_launch_search_filter(ctx, d_needle, (uint32_t)needle_len, d_hay, d_off, n, max_hay, k,
+                                     costs.transpose != 0, (uint32_t *)ctx->d_work[2].p, (uint32_t *)ctx->d_work[0].p,
+                                     counter, st);
+        if (rc == TA_OK) {
+            TA_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags + 2, counter, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            TA_CUDA(ctx, cudaStreamSynchronize(st));
+            work_n = ctx->h_flags[2];
+            d_idx = (const uint32_t *)ctx->d_work[0].p;
+        } else if (rc != TA_ERR_TOO_LARGE) {
+            return rc;
+        }
+    }
+    if (work_n == 0) return TA_OK;
+
+    const bool trans = costs.transpose != 0;
+    // kernel choice: warp-per-haystack wavefront when the thread-per-haystack walk could not fill the GPU (or its
+    // shared-memory rows would not fit); TA_SEARCH_KERNEL=thread|wave forces one (testing)
+    static const char *force = getenv("TA_SEARCH_KERNEL");
+    int threads = 64;
+    size_t smem = exact_smem_bytes((uint32_t)needle_len, trans, threads);
+    if (smem > (size_t)ctx->smem_optin) {
+        threads = 32;
+        smem = exact_smem_bytes((uint32_t)needle_len, trans, threads);
+    }
+    const bool thread_ok = smem <= (size_t)ctx->smem_optin;
+    const bool wave_ok = needle_len <= 256;
+    bool use_wave = wave_ok && (!thread_ok || work_n < (size_t)ctx->sm_count * 256);
+    if (force && force[0] == 't' && thread_ok) use_wave = false;
+    if (force && force[0] == 'w' && wave_ok) use_wave = true;
+    if (!use_wave && !thread_ok) return TA_ERR_TOO_LARGE;
+    void (*kern)(const SearchArgs) = nullptr;
+    if (use_wave) {
+        const int C = needle_len <= 32 ? 1 : needle_len <= 64 ? 2 : needle_len <= 128 ? 4 : 8;
+        if (C == 1) kern = trans ? search_wave_kernel<1, true> : search_wave_kernel<1, false>;
+        if (C == 2) kern = trans ? search_wave_kernel<2, true> : search_wave_kernel<2, false>;
+        if (C == 4) kern = trans ? search_wave_kernel<4, true> : search_wave_kernel<4, false>;
+        if (C == 8) kern = trans ? search_wave_kernel<8, true> : search_wave_kernel<8, false>;
+        threads = 128;
+        smem = 0;
+    } else {
+        kern = trans ? search_exact_kernel<true> : search_exact_kernel<false>;
+        TA_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    unsigned long long cap = std::max<unsigned long long>(4096, work_n * 8);
+    for (int attempt = 0; attempt < 2; attempt++) {
+        if ((rc = ta_dev_reserve(ctx, ctx->d_work[1], cap * sizeof(Hit))) != TA_OK) return rc;
+        unsigned long long *d_count = (unsigned long long *)(ctx->d_flags + 4);
+        TA_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st));
+        SearchArgs sa;
+        sa.needle = d_needle, sa.hay = d_hay, sa.hay_off = d_off, sa.idx = d_idx, sa.n = work_n;
+        sa.needle_len = (uint32_t)needle_len, sa.k = k;
+        sa.mism = costs.mismatch, sa.gap = costs.gap, sa.sgap = costs.start_gap, sa.tcost = costs.transpose;
+        sa.anchored = anchored, sa.hits = (Hit *)ctx->d_work[1].p, sa.hit_count = d_count, sa.hit_cap = cap;
+        const size_t per_block = use_wave ? (size_t)threads / 32 : (size_t)threads;
+        const unsigned blocks = (unsigned)((work_n + per_block - 1) / per_block);
+        kern<<<blocks, threads, smem, st>>>(sa);
+        ctx->launches++;
+        TA_CUDA(ctx, cudaGetLastError());
+        TA_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags + 4, d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        TA_CUDA(ctx, cudaStreamSynchronize(st));
+        unsigned long long got;
+        memcpy(&got, ctx->h_flags + 4, sizeof got);
+        if (got <= cap) {
+            hits.resize((size_t)got);
+            if (got)
+                TA_CUDA(ctx, cudaMemcpyAsync(hits.data(), ctx->d_work[1].p, (size_t)got * sizeof(Hit),
+                                             cudaMemcpyDeviceToHost, st));
+            TA_CUDA(ctx, cudaStreamSynchronize(st));
+            return TA_OK;
+        }
+        cap = got;  // exact size known now: rerun once
+    }
+    return TA_ERR_TOO_LARGE;
+}
+
+// Host phase: order the hits by (haystack, end) and apply the reference's emission rules -- the row-0 match
+// (src/levenshtein.rs:1686-1707), the running Best threshold (:1792-1806) and the Best post-pass (:1812-1835).
+static void emit_matches(size_t n, size_t needle_len, uint32_t k, bool best, ta_costs costs, std::vector<Hit> &hits,
+                         uint64_t *moff, std::vector<ta_match> &result) {
+    std::sort(hits.begin(), hits.end(), [](const Hit &x, const Hit &y) {
+        return x.hay != y.hay ? x.hay < y.hay : x.end < y.end;
+    });
+    const uint32_t row0 = (uint32_t)needle_len * costs.gap + costs.start_gap;
+    size_t hp = 0;
+    std::vector<ta_match> cur;
+    for (size_t i = 0; i < n; i++) {
+        cur.clear();
+        uint32_t curr_k = k;
+        if (row0 <= curr_k) {
+            if (best) curr_k = row0;
+            cur.push_back(ta_match{0, 0, row0, 0});
+        }
+        for (; hp < hits.size() && hits[hp].hay == i; hp++) {
+            const Hit &h = hits[hp];
+            if (h.cost <= curr_k) {
+                if (best) curr_k = h.cost;
+                cur.push_back(ta_match{h.end - h.len, h.end, h.cost, 0});
+            }
+        }
+        if (best && !cur.empty()) {
+            size_t wpos = 0;
+            for (size_t r = 0; r < cur.size(); r++) {
+                if (wpos == 0)
+                    cur[wpos++] = cur[r];
+                else if (cur[r].start <= cur[wpos - 1].start)
+                    cur[wpos - 1] = cur[r];  // replace previous if fully overlapping
+                else
+                    cur[wpos++] = cur[r];
+            }
+            size_t f = 0;
+            for (size_t r = 0; r < wpos; r++)
+                if (cur[r].k == curr_k) cur[f++] = cur[r];
+            cur.resize(f);
+        }
+        result.insert(result.end(), cur.begin(), cur.end());
+        moff[i + 1] = result.size();
+    }
+}
+
+static int export_matches(const std::vector<ta_match> &result, uint64_t *moff, ta_match **out_matches,
+                          uint64_t **out_match_off) {
+    ta_match *m = (ta_match *)malloc((result.size() ? result.size() : 1) * sizeof(ta_match));
+    if (!m) {
+        free(moff);
+        return TA_ERR_NOMEM;
+    }
+    if (!result.empty()) memcpy(m, result.data(), result.size() * sizeof(ta_match));
+    *out_matches = m;
+    *out_match_off = moff;
+    return TA_OK;
+}
 
 extern "C" int ta_levenshtein_search_batch(ta_ctx *ctx, const uint8_t *needle, size_t needle_len, const uint8_t *hay,
                                            const uint64_t *hay_off, size_t n, uint32_t k, int search_type,
@@ -219,34 +551,17 @@ extern "C" int ta_levenshtein_search_batch(ta_ctx *ctx, const uint8_t *needle, s
     if (n > 0xFFFFFFF0ull || needle_len > TA_MAX_STRING_LEN) return TA_ERR_TOO_LARGE;
     const bool best = search_type == TA_SEARCH_BEST;
 
-    uint64_t *moff = (uint64_t *)calloc(n + 1, sizeof(uint64_t));
-    if (!moff) return TA_ERR_NOMEM;
-    std::vector<ta_match> result;
-    auto finish = [&]() {
-        ta_match *m = (ta_match *)malloc((result.size() ? result.size() : 1) * sizeof(ta_match));
-        if (!m) {
-            free(moff);
-            return (int)TA_ERR_NOMEM;
-        }
-        if (!result.empty()) memcpy(m, result.data(), result.size() * sizeof(ta_match));
-        *out_matches = m;
-        *out_match_off = moff;
-        return (int)TA_OK;
-    };
-
     uint64_t max_hay = 0, total_hay = 0;
     for (size_t i = 0; i < n; i++) {
-        if (hay_off[i + 1] < hay_off[i]) {
-            free(moff);
-            return TA_ERR_BAD_ARG;
-        }
+        if (hay_off[i + 1] < hay_off[i]) return TA_ERR_BAD_ARG;
         max_hay = std::max(max_hay, hay_off[i + 1] - hay_off[i]);
     }
     if (n) total_hay = hay_off[n] - hay_off[0];
-    if (total_hay && !hay) {
-        free(moff);
-        return TA_ERR_BAD_ARG;
-    }
+    if (total_hay && !hay) return TA_ERR_BAD_ARG;
+
+    uint64_t *moff = (uint64_t *)calloc(n + 1, sizeof(uint64_t));
+    if (!moff) return TA_ERR_NOMEM;
+    std::vector<ta_match> result;
 
     if (needle_len == 0) {  // reference src/levenshtein.rs:1600-1644 -- no DP involved, pure bookkeeping
         for (size_t i = 0; i < n; i++) {
@@ -266,140 +581,83 @@ extern "C" int ta_levenshtein_search_batch(ta_ctx *ctx, const uint8_t *needle, s
             }
             moff[i + 1] = result.size();
         }
-        return finish();
+        return export_matches(result, moff, out_matches, out_match_off);
     }
     if (!ta_costs_valid_search(costs)) {  // src/levenshtein.rs:1647
         free(moff);
         return TA_ERR_BAD_COSTS;
     }
-    if (n == 0) return finish();
+    if (n == 0) return export_matches(result, moff, out_matches, out_match_off);
 
-    // ---- device work ------------------------------------------------------------------------------------------
     std::vector<Hit> hits;
     {
         std::lock_guard<std::mutex> lock(ctx->mu);
-        auto bail = [&](int rc) {
+        auto run = [&]() -> int {
+            TA_CUDA(ctx, cudaSetDevice(ctx->device));
+            cudaStream_t st = ctx->stream;
+            int rc;
+            const uint64_t lo = hay_off[0];
+            const size_t skew = (size_t)(lo & 15);
+            if ((rc = ta_dev_reserve(ctx, ctx->d_a[0], skew + total_hay + 64)) != TA_OK) return rc;
+            if ((rc = ta_dev_reserve(ctx, ctx->d_aoff[0], (n + 1) * sizeof(uint64_t))) != TA_OK) return rc;
+            if ((rc = ta_dev_reserve(ctx, ctx->d_b[0], needle_len + 64)) != TA_OK) return rc;
+            if (total_hay)
+                TA_CUDA(ctx, cudaMemcpyAsync((uint8_t *)ctx->d_a[0].p + skew, hay + lo, total_hay,
+                                             cudaMemcpyHostToDevice, st));
+            TA_CUDA(ctx, cudaMemcpyAsync(ctx->d_aoff[0].p, hay_off, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+            TA_CUDA(ctx, cudaMemcpyAsync(ctx->d_b[0].p, needle, needle_len, cudaMemcpyHostToDevice, st));
+            return search_device(ctx, st, (const uint8_t *)ctx->d_b[0].p, needle_len,
+                                 (const uint8_t *)ctx->d_a[0].p + skew - lo, (const uint64_t *)ctx->d_aoff[0].p, n,
+                                 max_hay, k, costs, anchored, hits);
+        };
+        const int rc = run();
+        if (rc != TA_OK) {
+            cudaStreamSynchronize(ctx->stream);
             free(moff);
             return rc;
+        }
+    }
+    emit_matches(n, needle_len, k, best, costs, hits, moff, result);
+    return export_matches(result, moff, out_matches, out_match_off);
+}
+
+extern "C" int ta_levenshtein_search_batch_dev(ta_ctx *ctx, const uint8_t *needle, size_t needle_len,
+                                               const uint8_t *hay, const uint64_t *hay_off, size_t n,
+                                               uint64_t max_hay_len, uint32_t k, int search_type, ta_costs costs,
+                                               int anchored, ta_match **out_matches, uint64_t **out_match_off,
+                                               void *stream) {
+    if (!ctx || !out_matches || !out_match_off) return TA_ERR_BAD_ARG;
+    *out_matches = nullptr;
+    *out_match_off = nullptr;
+    if (search_type != TA_SEARCH_ALL && search_type != TA_SEARCH_BEST) return TA_ERR_BAD_ARG;
+    if (!ta_costs_valid(costs)) return TA_ERR_BAD_COSTS;
+    if (needle_len == 0 || !needle) return TA_ERR_BAD_ARG;  // the empty-needle bookkeeping needs host offsets
+    if (!ta_costs_valid_search(costs)) return TA_ERR_BAD_COSTS;
+    if (n && (!hay_off || !hay)) return TA_ERR_BAD_ARG;
+    if (n > 0xFFFFFFF0ull || needle_len > TA_MAX_STRING_LEN) return TA_ERR_TOO_LARGE;
+    uint64_t *moff = (uint64_t *)calloc(n + 1, sizeof(uint64_t));
+    if (!moff) return TA_ERR_NOMEM;
+    std::vector<ta_match> result;
+    if (n == 0) return export_matches(result, moff, out_matches, out_match_off);
+    std::vector<Hit> hits;
+    {
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        auto run = [&]() -> int {
+            TA_CUDA(ctx, cudaSetDevice(ctx->device));
+            cudaStream_t st = (cudaStream_t)stream;
+            int rc;
+            if ((rc = ta_dev_reserve(ctx, ctx->d_b[0], needle_len + 64)) != TA_OK) return rc;
+            TA_CUDA(ctx, cudaMemcpyAsync(ctx->d_b[0].p, needle, needle_len, cudaMemcpyHostToDevice, st));
+            return search_device(ctx, st, (const uint8_t *)ctx->d_b[0].p, needle_len, hay, hay_off, n, max_hay_len, k,
+                                 costs, anchored, hits);
         };
-        if (cudaSetDevice(ctx->device) != cudaSuccess) return bail(ta_cuda_fail(ctx, cudaGetLastError(), "cudaSetDevice"));
-        cudaStream_t st = ctx->stream;
-        int rc;
-        const uint64_t lo = hay_off[0];
-        const size_t skew = (size_t)(lo & 15);
-        if ((rc = ta_dev_reserve(ctx, ctx->d_a[0], skew + total_hay + 64)) != TA_OK) return bail(rc);
-        if ((rc = ta_dev_reserve(ctx, ctx->d_aoff[0], (n + 1) * sizeof(uint64_t))) != TA_OK) return bail(rc);
-        if ((rc = ta_dev_reserve(ctx, ctx->d_b[0], needle_len + 64)) != TA_OK) return bail(rc);
-        cudaError_t e;
-#define S_CUDA(call)                                                    \
-    if ((e = (call)) != cudaSuccess) return bail(ta_cuda_fail(ctx, e, #call))
-        if (total_hay)
-            S_CUDA(cudaMemcpyAsync((uint8_t *)ctx->d_a[0].p + skew, hay + lo, total_hay, cudaMemcpyHostToDevice, st));
-        S_CUDA(cudaMemcpyAsync(ctx->d_aoff[0].p, hay_off, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-        S_CUDA(cudaMemcpyAsync(ctx->d_b[0].p, needle, needle_len, cudaMemcpyHostToDevice, st));
-        const uint8_t *d_hay = (const uint8_t *)ctx->d_a[0].p + skew - lo;
-        const uint64_t *d_off = (const uint64_t *)ctx->d_aoff[0].p;
-        const uint8_t *d_needle = (const uint8_t *)ctx->d_b[0].p;
-
-        // optional bit-parallel pre-filter (unit costs, needle <= 64): only flagged haystacks get the exact DP
-        const bool unit = costs.mismatch == 1 && costs.gap == 1 && costs.start_gap == 0 && costs.transpose <= 1;
-        const uint32_t *d_idx = nullptr;
-        size_t work_n = n;
-        const uint32_t row0_cost = (uint32_t)needle_len * costs.gap + costs.start_gap;
-        if (unit && needle_len <= 64 && !anchored && k < needle_len) {
-            if ((rc = ta_dev_reserve(ctx, ctx->d_work[0], n * sizeof(uint32_t))) != TA_OK) return bail(rc);
-            uint32_t *counter = ctx->d_flags + 2;
-            S_CUDA(cudaMemsetAsync(counter, 0, sizeof(uint32_t), st));
-            rc = ta_launch_search_filter(ctx, d_needle, (uint32_t)needle_len, d_hay, d_off, n, k,
-                                         costs.transpose != 0, (uint32_t *)ctx->d_work[0].p, counter, st);
-            if (rc == TA_OK) {
-                S_CUDA(cudaMemcpyAsync(ctx->h_flags + 2, counter, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-                S_CUDA(cudaStreamSynchronize(st));
-                work_n = ctx->h_flags[2];
-                d_idx = (const uint32_t *)ctx->d_work[0].p;
-            } else if (rc != TA_ERR_TOO_LARGE) {
-                return bail(rc);
-            }
+        const int rc = run();
+        if (rc != TA_OK) {
+            cudaStreamSynchronize((cudaStream_t)stream);
+            free(moff);
+            return rc;
         }
-
-        if (work_n > 0) {
-            const bool trans = costs.transpose != 0;
-            const int threads = 64;
-            const size_t smem = exact_smem_bytes((uint32_t)needle_len, trans, threads);
-            if (smem > (size_t)ctx->smem_optin) return bail(TA_ERR_TOO_LARGE);
-            auto kern = trans ? search_exact_kernel<true> : search_exact_kernel<false>;
-            S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            unsigned long long cap = std::max<unsigned long long>(4096, work_n * 8);
-            for (int attempt = 0; attempt < 2; attempt++) {
-                if ((rc = ta_dev_reserve(ctx, ctx->d_work[1], cap * sizeof(Hit))) != TA_OK) return bail(rc);
-                unsigned long long *d_count = (unsigned long long *)(ctx->d_flags + 4);
-                S_CUDA(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st));
-                SearchArgs sa;
-                sa.needle = d_needle, sa.hay = d_hay, sa.hay_off = d_off, sa.idx = d_idx, sa.n = work_n;
-                sa.needle_len = (uint32_t)needle_len, sa.k = k;
-                sa.mism = costs.mismatch, sa.gap = costs.gap, sa.sgap = costs.start_gap, sa.tcost = costs.transpose;
-                sa.anchored = anchored, sa.hits = (Hit *)ctx->d_work[1].p, sa.hit_count = d_count, sa.hit_cap = cap;
-                const unsigned blocks = (unsigned)((work_n + threads - 1) / threads);
-                kern<<<blocks, threads, smem, st>>>(sa);
-                ctx->launches++;
-                S_CUDA(cudaGetLastError());
-                S_CUDA(cudaMemcpyAsync(ctx->h_flags + 4, d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-                S_CUDA(cudaStreamSynchronize(st));
-                unsigned long long got;
-                memcpy(&got, ctx->h_flags + 4, sizeof got);
-                if (got <= cap) {
-                    hits.resize((size_t)got);
-                    if (got)
-                        S_CUDA(cudaMemcpy(hits.data(), ctx->d_work[1].p, (size_t)got * sizeof(Hit), cudaMemcpyDeviceToHost));
-                    break;
-                }
-                if (attempt == 1) return bail(TA_ERR_TOO_LARGE);
-                cap = got;  // exact size known now: rerun once
-            }
-        }
-#undef S_CUDA
-        // the row-0 match Match{0, 0, needle_len*gap + start_gap} (src/levenshtein.rs:1686-1707) is emitted below
-        (void)row0_cost;
     }
-
-    // ---- order the hits (haystack, end) and apply the reference's emission rules ------------------------------
-    std::sort(hits.begin(), hits.end(), [](const Hit &x, const Hit &y) {
-        return x.hay != y.hay ? x.hay < y.hay : x.end < y.end;
-    });
-    const uint32_t row0 = (uint32_t)needle_len * costs.gap + costs.start_gap;
-    size_t hp = 0;
-    std::vector<ta_match> cur;
-    for (size_t i = 0; i < n; i++) {
-        cur.clear();
-        uint32_t curr_k = k;
-        if (row0 <= curr_k) {  // :1693-1706
-            if (best) curr_k = row0;
-            cur.push_back(ta_match{0, 0, row0, 0});
-        }
-        for (; hp < hits.size() && hits[hp].hay == i; hp++) {
-            const Hit &h = hits[hp];
-            if (h.cost <= curr_k) {  // :1792-1806
-                if (best) curr_k = h.cost;
-                cur.push_back(ta_match{h.end - h.len, h.end, h.cost, 0});
-            }
-        }
-        if (best && !cur.empty()) {  // :1812-1835
-            size_t wpos = 0;
-            for (size_t r = 0; r < cur.size(); r++) {
-                if (wpos == 0)
-                    cur[wpos++] = cur[r];
-                else if (cur[r].start <= cur[wpos - 1].start)
-                    cur[wpos - 1] = cur[r];
-                else
-                    cur[wpos++] = cur[r];
-            }
-            size_t f = 0;
-            for (size_t r = 0; r < wpos; r++)
-                if (cur[r].k == curr_k) cur[f++] = cur[r];
-            cur.resize(f);
-        }
-        result.insert(result.end(), cur.begin(), cur.end());
-        moff[i + 1] = result.size();
-    }
-    return finish();
+    emit_matches(n, needle_len, k, search_type == TA_SEARCH_BEST, costs, hits, moff, result);
+    return export_matches(result, moff, out_matches, out_match_off);
 }
