@@ -353,6 +353,36 @@ def test_search_filter_long_needles_and_transpositions(eng):
                 assert np.array_equal(goff, woff) and np.array_equal(got, want), (nlen, costs, k)
 
 
+@pytest.mark.parametrize("costs", [(1, 1, 0, 0), (1, 1, 0, 1), (2, 1, 3, 0), (2, 2, 1, 3)], ids=str)
+def test_lev_wide_band_block_kernel(eng, costs):
+    """bands wider than 1024 diagonals go to the block-per-pair kernel: levenshtein()/rdamerau() on long strings
+    (k = u32::MAX) and large explicit k"""
+    rng = random.Random(4242)
+    A = _rand_strs(rng, 12, 600, 1500, 4) + [b"", b"x" * 1200]
+    B = [(_mutate(rng, s, rng.randrange(0, 700), 4) if rng.random() < 0.6 else
+          bytes(rng.randrange(4) for _ in range(rng.randrange(500, 1500)))) for s in A[:12]] + [b"y" * 1300, b""]
+    a, ao = _pack(A)
+    b, bo = _pack(B)
+    for k in (0xFFFFFFFF, 1100):
+        got = eng.levenshtein_k_batch(a, ao, b, bo, k, costs)
+        want = orc.levenshtein_k_batch(a, ao, b, bo, k, costs, threads=8)
+        assert np.array_equal(got, want), (k, costs, got, want)
+    assert np.array_equal(eng.levenshtein_exp_batch(a, ao, b, bo, costs),
+                          orc.levenshtein_exp_batch(a, ao, b, bo, costs, threads=8))
+
+
+def test_lev_very_wide_band_global_workspace(eng):
+    """anti-diagonals that do not fit shared memory use the per-block global workspace"""
+    rng = random.Random(99)
+    A = [bytes(rng.randrange(3) for _ in range(6100)) for _ in range(2)]
+    B = [bytes(rng.randrange(3) for _ in range(6000)), _mutate(rng, A[1], 300, 3)]
+    a, ao = _pack(A)
+    b, bo = _pack(B)
+    got = eng.levenshtein_k_batch(a, ao, b, bo, 0xFFFFFFFF, (1, 1, 0, 1))
+    want = orc.levenshtein_k_batch(a, ao, b, bo, 0xFFFFFFFF, (1, 1, 0, 1), threads=2)
+    assert np.array_equal(got, want)
+
+
 LEV_TESTS = "test_lev_k_mutated or test_lev_k_random_short or test_nul_bytes or test_lev_exp"
 SEARCH_TESTS = ("test_search_random or test_search_planted or test_kat_search or "
                 "test_search_filter_long_needles_and_transpositions")

@@ -16,6 +16,8 @@
 // carried as the sender-side pre-minimised values outH = min(D + open, H + gap), outV likewise, so a step costs
 // one shuffle whatever the cost model; the transposition test needs the neighbours' match flags, which ride in
 // bit 0 of the shuffled word.  Strings are staged into shared memory with 16-byte cp.async (LDGSTS) vectors.
+#include <algorithm>
+
 #include "ta_common.cuh"
 
 namespace {
@@ -255,6 +257,143 @@ __global__ void __launch_bounds__(128) lev_band_kernel(const BandArgs args) {
     if (t == 0) args.out[pair] = val <= max_k ? val : TA_NONE;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// lev_wide_kernel: one BLOCK per pair for bands wider than 1024 diagonals (levenshtein()/rdamerau() on long
+// strings, late rounds of the exponential search).  Same anti-diagonal recurrence and band as above, but the
+// anti-diagonals live in shared memory (or, for very wide bands, in a per-block global workspace) and the block
+// advances one anti-diagonal per __syncthreads().
+struct WideArgs {
+    BandArgs b;
+    uint32_t wc;         // cells per anti-diagonal the buffers are sized for
+    uint32_t *workspace;  // null: use dynamic shared memory; else gridDim.x * 10 * wc words
+};
+
+__global__ void __launch_bounds__(256) lev_wide_kernel(const WideArgs wa) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const BandArgs &args = wa.b;
+    uint32_t *base = wa.workspace ? wa.workspace + (size_t)blockIdx.x * 10 * wa.wc : (uint32_t *)smem;
+    const uint32_t wc = wa.wc;
+    for (size_t w = blockIdx.x; w < args.n; w += gridDim.x) {
+        const size_t pair = args.idx ? (size_t)args.idx[w] : w;
+        const uint64_t a0 = args.a_off[pair], a1 = args.a_off[pair + 1];
+        const uint64_t b0 = args.b_off[pair], b1 = args.b_off[pair + 1];
+        const bool swap = (a1 - a0) > (b1 - b0);
+        const uint8_t *sa = swap ? args.b + b0 : args.a + a0;
+        const uint8_t *sb = swap ? args.a + a0 : args.b + b0;
+        const int m = (int)(swap ? (b1 - b0) : (a1 - a0));
+        const int n = (int)(swap ? (a1 - a0) : (b1 - b0));
+        const uint32_t mism = args.mism, gap = args.gap, sgap = args.sgap, tcost = args.tcost;
+        const uint32_t diff = (uint32_t)(n - m);
+        const bool trans = tcost != 0;
+        uint32_t max_k = min((uint32_t)m * mism, ((uint32_t)m << 1) * gap + (m == 0 ? 0u : sgap + (n == m ? sgap : 0u)));
+        max_k = min(args.k, max_k + diff * gap + (n == m ? 0u : sgap));
+        const uint32_t unit_k = (max_k > sgap ? max_k - sgap : 0u) / gap;
+        __syncthreads();  // previous pair's buffers are no longer read
+        if (diff > unit_k) {
+            if (threadIdx.x == 0) args.out[pair] = TA_NONE;
+            continue;
+        }
+        if (m == 0) {
+            if (threadIdx.x == 0) {
+                const uint32_t d = (uint32_t)n * gap + (n ? sgap : 0u);
+                args.out[pair] = d <= max_k ? d : TA_NONE;
+            }
+            continue;
+        }
+        const uint32_t spare = max_k >= 2 * sgap + diff * gap ? max_k - 2 * sgap - diff * gap : 0u;
+        const int e = (int)(spare / (2 * gap)) + (trans ? 1 : 0);
+        const int dlo = -e;
+        const int W = (int)diff + 2 * e + 1;
+        const int cells = (W + 1) / 2 + 1;  // <= wc (host)
+        uint32_t *D[4] = {base, base + wc, base + 2 * wc, base + 3 * wc};  // D[0] = s-1, D[1] = s-2, ...
+        uint32_t *oH[2] = {base + 4 * wc, base + 5 * wc}, *oV[2] = {base + 6 * wc, base + 7 * wc};
+        uint32_t *mt[2] = {base + 8 * wc, base + 9 * wc};
+        for (int ci = threadIdx.x; ci < cells; ci += blockDim.x) {
+            D[0][ci] = D[1][ci] = D[2][ci] = D[3][ci] = TA_INF;
+            oH[0][ci] = oV[0][ci] = TA_INF;
+            mt[0][ci] = 0;
+        }
+        __syncthreads();
+        const uint32_t open = sgap + gap;
+        const int s_end = m + n;
+        const int s0 = -((-dlo) & 1);
+        int cur = 0;  // oH/oV/mt[cur] hold step s-1
+        for (int s = s0; s <= s_end + 1; s++) {
+            const int p = (s - dlo) & 1;
+            uint32_t *Dn = trans ? D[3] : D[1];  // overwritten in place (each cell only reads its own old slot)
+            for (int ci = threadIdx.x; ci < cells; ci += blockDim.x) {
+                const int d = dlo + 2 * ci + p;
+                const int i = (s - d) >> 1, j = (s + d) >> 1;  // (s - d) is even
+                const int lh = p ? ci : ci - 1, lv = p ? ci + 1 : ci;
+                uint32_t h = (lh >= 0 && lh < cells) ? oH[cur][lh] : TA_INF;
+                uint32_t v = (lv >= 0 && lv < cells) ? oV[cur][lv] : TA_INF;
+                const uint32_t ca = sa[__vimin_s32_relu(i - 1, m - 1)], cb = sb[__vimin_s32_relu(j - 1, n - 1)];
+                const uint32_t eq = ca == cb;
+                uint32_t val = umin3(D[1][ci] + (eq ? 0u : mism), h, v);
+                if (trans) {
+                    const uint32_t mL = (lh >= 0 && lh < cells) ? mt[cur][lh] : 0u;
+                    const uint32_t mU = (lv >= 0 && lv < cells) ? mt[cur][lv] : 0u;
+                    if (mL & mU) val = min(val, D[3][ci] + tcost);
+                    mt[cur ^ 1][ci] = eq;
+                }
+                const bool bi = (i == 0) & (j >= 0), bj = (j == 0) & (i >= 0);
+                if (bi | bj) {
+                    const int q = bi ? j : i;
+                    val = (uint32_t)q * gap + (q > 0 ? sgap : 0u);
+                    h = v = TA_INF;
+                }
+                val = min(val, TA_INF);
+                Dn[ci] = val;
+                oH[cur ^ 1][ci] = min(min(val + open, h + gap), TA_INF);
+                oV[cur ^ 1][ci] = min(min(val + open, v + gap), TA_INF);
+            }
+            // rotate: new -> s-1
+            if (trans) {
+                uint32_t *t3 = D[3];
+                D[3] = D[2];
+                D[2] = D[1];
+                D[1] = D[0];
+                D[0] = t3;
+            } else {
+                uint32_t *t1 = D[1];
+                D[1] = D[0];
+                D[0] = t1;
+            }
+            cur ^= 1;
+            __syncthreads();
+            if (s == s_end) {
+                const int cif = ((int)diff - dlo - p) >> 1;
+                if (threadIdx.x == 0) {
+                    const uint32_t val = D[0][cif];
+                    args.out[pair] = val <= max_k ? val : TA_NONE;
+                }
+                break;
+            }
+        }
+    }
+}
+
+int launch_wide(ta_ctx *ctx, const BandArgs &args, uint32_t W, cudaStream_t st) {
+    WideArgs wa;
+    wa.b = args;
+    wa.wc = (W + 1) / 2 + 2;
+    const size_t bytes = (size_t)10 * wa.wc * sizeof(uint32_t);
+    unsigned blocks = (unsigned)std::min<size_t>(args.n, (size_t)ctx->sm_count * 2);
+    if (bytes <= (size_t)ctx->smem_optin - 1024) {
+        wa.workspace = nullptr;
+        TA_CUDA(ctx, cudaFuncSetAttribute(lev_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        lev_wide_kernel<<<blocks, 256, bytes, st>>>(wa);
+    } else {
+        int rc = ta_dev_reserve(ctx, ctx->d_work[3], bytes * blocks);
+        if (rc != TA_OK) return rc;
+        wa.workspace = (uint32_t *)ctx->d_work[3].p;
+        lev_wide_kernel<<<blocks, 256, 0, st>>>(wa);
+    }
+    ctx->launches++;
+    TA_CUDA(ctx, cudaGetLastError());
+    return TA_OK;
+}
+
 template <int G, int C, bool AFFINE, bool TRANS>
 int launch_gc(ta_ctx *ctx, const BandArgs &args0, uint32_t max_len, cudaStream_t st) {
     BandArgs args = args0;
@@ -286,7 +425,7 @@ int launch_w(ta_ctx *ctx, const BandArgs &args, uint32_t W, uint32_t max_len, cu
     if (W <= 256) return launch_gc<32, 4, AFFINE, TRANS>(ctx, args, max_len, st);
     if (W <= 512) return launch_gc<32, 8, AFFINE, TRANS>(ctx, args, max_len, st);
     if (W <= 1024) return launch_gc<32, 16, AFFINE, TRANS>(ctx, args, max_len, st);
-    return TA_ERR_TOO_LARGE;
+    return launch_wide(ctx, args, W, st);
 }
 
 }  // namespace

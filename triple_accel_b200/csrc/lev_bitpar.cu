@@ -87,23 +87,36 @@ __global__ void __launch_bounds__(128) search_filter_kernel(const uint8_t *__res
     W VP = ~(W)0, VN = 0, D0prev = ~(W)0, Eqprev = 0;
     uint32_t score = N;
     const W top = (W)1 << (N - 1);
-    for (uint64_t x = start; x < seg_end; x++) {
-        const W Eq = peq[__ldg(p + x)];
-        W D0 = (((Eq & VP) + VP) ^ VP) | Eq | VN;
-        if (TRANS) {
-            D0 |= ((~D0prev & Eq) << 1) & Eqprev;
-            D0prev = D0;
-            Eqprev = Eq;
+    // the haystack is streamed in aligned 16-byte vectors and re-aligned in registers (bitpar::Stream)
+    bitpar::Stream hs;
+    hs.init((intptr_t)(p + start), (uintptr_t)p, (uintptr_t)(p + H - 1));
+    for (uint64_t x0 = start; x0 < seg_end; x0 += 16) {
+        uint32_t wds[4];
+        hs.take(wds);
+        bool hit = false;
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            const uint64_t x = x0 + u;
+            const uint32_t ch = (wds[u >> 2] >> (8 * (u & 3))) & 0xffu;
+            const W Eq = peq[ch];
+            W D0 = (((Eq & VP) + VP) ^ VP) | Eq | VN;
+            if (TRANS) {
+                D0 |= ((~D0prev & Eq) << 1) & Eqprev;
+                D0prev = D0;
+                Eqprev = Eq;
+            }
+            W HP = VN | ~(D0 | VP);
+            W HN = D0 & VP;
+            score += (HP & top) ? 1u : 0u;
+            score -= (HN & top) ? 1u : 0u;
+            HP <<= 1;  // row 0 of a search has horizontal delta 0
+            HN <<= 1;
+            VP = HN | ~(D0 | HP);
+            VN = D0 & HP;
+            // positions past seg_end read don't-care bytes: they may only raise a flag inside the segment
+            hit |= (x >= seg_begin) & (x < seg_end) & (score <= k);
         }
-        W HP = VN | ~(D0 | VP);
-        W HN = D0 & VP;
-        score += (HP & top) ? 1u : 0u;
-        score -= (HN & top) ? 1u : 0u;
-        HP <<= 1;  // row 0 of a search has horizontal delta 0
-        HN <<= 1;
-        VP = HN | ~(D0 | HP);
-        VN = D0 & HP;
-        if (x >= seg_begin && score <= k) {
+        if (hit) {
             flags[h] = 1;
             return;
         }
