@@ -111,7 +111,7 @@ struct Stream {
 // flags (bit 7 of each byte) of the bytes of r that equal the corresponding byte of bb
 TA_HD uint32_t eq_flags(uint32_t r, uint32_t bb) {
     const uint32_t x = r ^ bb;
-    const uint32_t t = (x & 0x7f7f7f7fu) + 0x7f7f7f7fu;
+    const uint32_t t = (x & 0x7f7f7f7fu) + 0x7f7f7f7fu;  // bit 7 of each byte: low 7 bits non-zero
     return ~(t | x) & 0x80808080u;
 }
 
@@ -148,21 +148,20 @@ TA_HD uint32_t distance32(const uint8_t *a, int m, const uint8_t *b, int n, uint
     uint32_t D0prev = 0xffffffffu, Eqprev = 0;
     uint32_t matches = 0;  // columns whose final-diagonal cell has diagonal delta 0
 
+    const uint32_t emask = 1u << e;  // the diagonal through (m, n) is window row e
     for (int j0 = 0; j0 < n; j0 += 16) {
         uint32_t aw[4], bw[4];
         sa.take(aw);
         sb.take(bw);
-        uint32_t hist = 0;
+        uint32_t hist = 0;  // bit e + u <- column u's D0 bit on the final diagonal (e <= 16)
 #pragma unroll
         for (int u = 0; u < 16; u++) {
             const uint32_t bsel = (uint32_t)(u & 3);
             const uint32_t bb = prmt(bw[u >> 2], 0, bsel * 0x1111u);  // text byte of this column, broadcast
+            // role q is played by register (q + u) & 7 (the window slid u rows since the chunk began)
             uint32_t Eq = 0;
 #pragma unroll
-            for (int q = 0; q < 8; q++) {
-                // role q is played by register (q + u) & 7 (the window slid u rows since the chunk began)
-                Eq |= eq_flags(R[(q + u) & 7], bb) >> (7 - q);
-            }
+            for (int q = 0; q < 8; q++) Eq |= eq_flags(R[(q + u) & 7], bb) >> (7 - q);
             uint32_t D0 = (((Eq & VP) + VP) ^ VP) | Eq | VN;
             if (TRANS) {
                 D0 |= ~D0prev & (Eq << 1) & (Eqprev >> 1);
@@ -174,16 +173,16 @@ TA_HD uint32_t distance32(const uint8_t *a, int m, const uint8_t *b, int n, uint
             const uint32_t X = D0 >> 1;
             VN = X & HP;
             VP = HN | ~(X | HP);
-            hist = funnel_r(hist, D0 >> e, 1);  // column u's flag ends up at bit 16 + u
+            hist += (D0 & emask) << u;
             // slide: the oldest register (role 0) drops its byte 0 and takes the next pattern byte as role 7
             R[u & 7] = prmt(R[u & 7], aw[u >> 2], 0x0321u | ((4u + bsel) << 12));
         }
         const int cols = n - j0;  // columns of this chunk that exist
-        const uint32_t valid = cols >= 16 ? 0xffff0000u : (((1u << cols) - 1u) << 16);
+        const uint32_t valid = cols >= 16 ? 0xffffu : ((1u << cols) - 1u);
 #if defined(__CUDA_ARCH__)
-        matches += __popc(hist & valid);
+        matches += __popc((hist >> e) & valid);
 #else
-        matches += (uint32_t)__builtin_popcount(hist & valid);
+        matches += (uint32_t)__builtin_popcount((hist >> e) & valid);
 #endif
     }
     return (uint32_t)diff + (uint32_t)n - matches;
