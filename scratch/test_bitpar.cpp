@@ -38,6 +38,10 @@ int main(int argc, char** argv) {
             uint32_t k = rng() % (kmax + 1);
             orc_costs c = {1, 1, 0, (uint8_t)trans};
             uint32_t want = orc_levenshtein_naive_k_with_opts(a, la, b, lb, k, c, NULL, NULL);
+            static uint32_t tab[128];
+            uint32_t got2 = (it & 1) ? (trans ? bitpar::pair_unit_costs_tab<true,1>(a, la, b, lb, k, (uint8_t*)tab, 2) : bitpar::pair_unit_costs_tab<false,1>(a, la, b, lb, k, (uint8_t*)tab, 2)) : (trans ? bitpar::pair_unit_costs_tab<true,2>(a, la, b, lb, k, (uint8_t*)tab, 2) : bitpar::pair_unit_costs_tab<false,2>(a, la, b, lb, k, (uint8_t*)tab, 2));
+            for (int q = 0; q < 128; q++) if (tab[q]) { printf("table not clean\n"); bad++; tab[q] = 0; }
+            if (got2 != want) { if (bad++ < 10) printf("TAB MISMATCH trans=%d k=%u la=%d lb=%d want=%u got=%u\n", trans, k, la, lb, want, got2); }
             uint32_t got = trans ? bitpar::pair_unit_costs<true>(a, la, b, lb, k) : bitpar::pair_unit_costs<false>(a, la, b, lb, k);
             tests++;
             if (want != got) { if (bad++ < 10) printf("MISMATCH trans=%d k=%u la=%d lb=%d want=%u got=%u\n", trans, k, la, lb, want, got); }

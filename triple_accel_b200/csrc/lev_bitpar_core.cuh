@@ -70,23 +70,27 @@ TA_HD V4 ldvec(const uint8_t *p) {  // p is 16-byte aligned
 // vector addresses are clamped into [lo, hi] (the vectors holding the string's first / last byte), so nothing
 // outside the string's own 16-byte-aligned extent is ever touched; clamped positions deliver don't-care bytes.
 struct Stream {
-    uintptr_t next;    // address of the next vector to fetch (unclamped)
-    uintptr_t lo, hi;  // clamp range (aligned)
-    uint32_t wsel;     // word offset of the stream start inside its first vector (0..3)
-    uint32_t bsh;      // 8 * byte offset inside the word (0, 8, 16, 24)
-    V4 cur, nxt;       // vectors c and c+1 of the stream
+    const uint8_t *base;  // 16-byte aligned address of vector 0
+    int next;             // index of the next vector to fetch (unclamped)
+    int lo, hi;           // clamp range of vector indices
+    uint32_t wsel;        // word offset of the stream start inside its first vector (0..3)
+    uint32_t bsh;         // 8 * byte offset inside the word (0, 8, 16, 24)
+    V4 cur, nxt;          // vectors c and c+1 of the stream
 
     TA_HD V4 fetch() {
-        uintptr_t p = next < lo ? lo : (next > hi ? hi : next);
-        next += 16;
-        return ldvec((const uint8_t *)p);
+        int i = next < hi ? next : hi;
+        i = i > lo ? i : lo;
+        next += 1;
+        return ldvec(base + (intptr_t)i * 16);
     }
     // start: address of logical byte 0 (may lie before first); first/last: first and last valid byte addresses
     TA_HD void init(intptr_t start, uintptr_t first, uintptr_t last) {
-        lo = first & ~(uintptr_t)15;
-        hi = last & ~(uintptr_t)15;
         const uintptr_t s = (uintptr_t)start;
-        next = s & ~(uintptr_t)15;
+        const uintptr_t b0 = s & ~(uintptr_t)15;
+        base = (const uint8_t *)b0;
+        lo = (int)(((intptr_t)(first & ~(uintptr_t)15) - (intptr_t)b0) >> 4);
+        hi = (int)(((intptr_t)(last & ~(uintptr_t)15) - (intptr_t)b0) >> 4);
+        next = 0;
         wsel = (uint32_t)(s >> 2) & 3u;
         bsh = ((uint32_t)s & 3u) * 8u;
         cur = fetch();
@@ -186,6 +190,154 @@ TA_HD uint32_t distance32(const uint8_t *a, int m, const uint8_t *b, int n, uint
 #endif
     }
     return (uint32_t)diff + (uint32_t)n - matches;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// distance32_tab: same recurrence, but Eq comes from a per-thread match table instead of SIMD compares.
+//
+// tab[c * stride] (c = low 7 bits of a byte, 128 entries, 32 bits each, thread-private column of a shared-memory
+// array) has bit (t mod 32) set iff pattern-stream byte t is inside the current 32-row window and its low 7 bits
+// are c; the bytes' top bits live in a 32-bit plane A7 with the same circular bit numbering.  Sliding the window
+// clears the bit of the byte that leaves and sets the same bit position for the byte that enters (two read-modify-
+// writes), so a column costs  Eq = rotr(tab[b & 0x7f] & ~(A7 ^ topmask(b)), u mod 32)  -- one LDS, one LOP3, one
+// funnel shift -- instead of 8 SWAR compares.  The table must be all-zero on entry and is left all-zero on exit.
+// `tab` points at this thread's entry 0; entry c lives `c << pitch_log2` BYTES further (pitch = 4 * threads).
+TA_HD uint32_t &tab_at(uint8_t *tab, uint32_t c, uint32_t pitch_log2) {
+    return *(uint32_t *)(tab + ((size_t)c << pitch_log2));
+}
+TA_HD uint32_t byte_of(uint32_t w, int t) {  // byte t of w, zero-extended (one PRMT)
+    return prmt(w, 0u, 0x4440u | (uint32_t)t);
+}
+
+// gathers bit `bitpos` of each of the 16 bytes of w[0..3] into a 16-bit word (byte t of w[i] -> bit 4i + t)
+TA_HD uint32_t gather_bits16(const uint32_t w[4], int bitpos) {
+    uint32_t r = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint32_t f = (w[i] >> bitpos) & 0x01010101u;        // bits 0, 8, 16, 24
+        r |= (((f * 0x00204081u) >> 21) & 0xfu) << (4 * i);       // gathered to 4 adjacent bits
+    }
+    return r;
+}
+// all-ones iff bit `bitpos` of byte t of w is set
+TA_HD uint32_t bit_mask_of(uint32_t w, int t, int bitpos) {
+    return (uint32_t)((int32_t)(w << (31 - 8 * t - bitpos)) >> 31);
+}
+
+// PLANES = 1: 128 table entries (7-bit classes) + the A7 plane; PLANES = 2: 64 entries (6-bit classes) + A6, A7
+// planes -- half the shared memory per thread, twice the resident warps, two more ALU ops per column.
+template <bool TRANS, int PLANES>
+TA_HD uint32_t distance32_tab(const uint8_t *a, int m, const uint8_t *b, int n, uint32_t max_k, uint8_t *tab,
+                              const uint32_t pitch_log2) {
+    constexpr uint32_t CMASK = PLANES == 1 ? 0x7f7f7f7fu : 0x3f3f3f3fu;
+    const int diff = n - m;
+    const int e = (int)((max_k - (uint32_t)diff) >> 1) + (TRANS ? 1 : 0);
+    const int dhi = diff + e;  // window row p of column j is matrix row i = j - dhi + p
+
+    Stream sa, sb;
+    sa.init((intptr_t)a - dhi, (uintptr_t)a, (uintptr_t)a + m - 1);
+    sb.init((intptr_t)b, (uintptr_t)b, (uintptr_t)b + n - 1);
+
+    // ring of the pattern-stream bytes currently inside the window (class bits only): chunks c and c+1
+    uint32_t ring[8];
+    uint32_t A7 = 0, A6 = 0;
+    {
+        uint32_t x[8];
+        sa.take(x);
+        sa.take(x + 4);
+        A7 = gather_bits16(x, 7) | (gather_bits16(x + 4, 7) << 16);
+        if (PLANES == 2) A6 = gather_bits16(x, 6) | (gather_bits16(x + 4, 6) << 16);
+#pragma unroll
+        for (int w = 0; w < 8; w++) ring[w] = x[w] & CMASK;
+#pragma unroll
+        for (int t = 0; t < 32; t++) tab_at(tab, byte_of(ring[t >> 2], t & 3), pitch_log2) |= 1u << t;
+    }
+
+    uint32_t VP = dhi >= 32 ? 0u : (0xffffffffu << dhi);
+    uint32_t VN = ~VP;
+    uint32_t D0prev = 0xffffffffu, Eqprev = 0;
+    uint32_t matches = 0;
+    const uint32_t emask = 1u << e;
+    uint32_t half = 0;   // 0 or 16: circular bit position of this chunk's first column, (16 * chunk) mod 32
+    uint32_t bit0 = 1u;  // 1 << half
+
+    for (int j0 = 0; j0 < n; j0 += 16) {
+        uint32_t aw[4], bw[4], bc[4];
+        sa.take(aw);  // stream chunk c+2: the bytes that enter during this chunk
+        sb.take(bw);
+        // plane bits of the entering bytes, placed at the circular positions they will occupy
+        const uint32_t tops7 = gather_bits16(aw, 7) * bit0;
+        const uint32_t tops6 = PLANES == 2 ? gather_bits16(aw, 6) * bit0 : 0u;
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            aw[w] &= CMASK;
+            bc[w] = bw[w] & CMASK;
+        }
+        uint32_t hist = 0;
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            uint32_t miss = A7 ^ bit_mask_of(bw[u >> 2], u & 3, 7);  // rows whose plane bits differ from the text byte's
+            if (PLANES == 2) miss |= A6 ^ bit_mask_of(bw[u >> 2], u & 3, 6);
+            const uint32_t raw = tab_at(tab, byte_of(bc[u >> 2], u & 3), pitch_log2) & ~miss;
+            const uint32_t Eq = funnel_r(raw, raw, half + (uint32_t)u);  // rotate: window row 0 to bit 0
+            uint32_t D0 = (((Eq & VP) + VP) ^ VP) | Eq | VN;
+            if (TRANS) {
+                D0 |= ~D0prev & (Eq << 1) & (Eqprev >> 1);
+                D0prev = D0;
+                Eqprev = Eq;
+            }
+            const uint32_t HP = VN | ~(D0 | VP);
+            const uint32_t HN = D0 & VP;
+            const uint32_t X = D0 >> 1;
+            VN = X & HP;
+            VP = HN | ~(X | HP);
+            hist += (D0 & emask) << u;
+            // slide: stream byte 16c + u leaves, byte 16c + 32 + u enters at the same circular bit position
+            const uint32_t bit = bit0 << u;
+            tab_at(tab, byte_of(ring[u >> 2], u & 3), pitch_log2) &= ~bit;
+            tab_at(tab, byte_of(aw[u >> 2], u & 3), pitch_log2) |= bit;
+            A7 = (A7 & ~bit) | (tops7 & bit);
+            if (PLANES == 2) A6 = (A6 & ~bit) | (tops6 & bit);
+        }
+        const int cols = n - j0;
+        const uint32_t valid = cols >= 16 ? 0xffffu : ((1u << cols) - 1u);
+#if defined(__CUDA_ARCH__)
+        matches += __popc((hist >> e) & valid);
+#else
+        matches += (uint32_t)__builtin_popcount((hist >> e) & valid);
+#endif
+#pragma unroll
+        for (int w = 0; w < 4; w++) {  // ring <- chunks c+1, c+2
+            ring[w] = ring[w + 4];
+            ring[w + 4] = aw[w];
+        }
+        half ^= 16u;
+        bit0 ^= 0x10001u;
+    }
+    // leave the table clean: every set bit belongs to one of the 32 bytes still in the window
+#pragma unroll
+    for (int t = 0; t < 32; t++) tab_at(tab, byte_of(ring[t >> 2], t & 3), pitch_log2) = 0;
+    return (uint32_t)diff + (uint32_t)n - matches;
+}
+
+template <bool TRANS, int PLANES>
+TA_HD uint32_t pair_unit_costs_tab(const uint8_t *a, uint64_t a_len, const uint8_t *b, uint64_t b_len, uint32_t k,
+                                   uint8_t *tab, const uint32_t pitch_log2) {
+    if (a_len > b_len) {
+        const uint8_t *tp = a;
+        a = b;
+        b = tp;
+        const uint64_t tl = a_len;
+        a_len = b_len;
+        b_len = tl;
+    }
+    const int m = (int)a_len, n = (int)b_len;
+    const uint32_t diff = (uint32_t)(n - m);
+    const uint32_t max_k = k < (uint32_t)n ? k : (uint32_t)n;
+    if (diff > max_k) return 0xFFFFFFFFu;
+    if (m == 0) return (uint32_t)n;
+    const uint32_t d = distance32_tab<TRANS, PLANES>(a, m, b, n, max_k, tab, pitch_log2);
+    return d <= max_k ? d : 0xFFFFFFFFu;
 }
 
 // The whole per-pair contract of levenshtein_naive_k_with_opts for unit costs (reference
