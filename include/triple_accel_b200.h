@@ -41,7 +41,8 @@ enum {
     TA_ERR_BAD_COSTS = -3,    /* EditCosts::new / check_search asserts (src/levenshtein.rs:44-52, 69) */
     TA_ERR_BAD_ARG = -4,      /* null pointer, non-monotone offsets, bad enum value */
     TA_ERR_TOO_LARGE = -5,    /* a string exceeds TA_MAX_STRING_LEN, or cost arithmetic would overflow u32 */
-    TA_ERR_NOMEM = -6         /* host allocation failed */
+    TA_ERR_NOMEM = -6,        /* host allocation failed */
+    TA_ERR_NUL_BYTE = -7      /* hamming_search: NUL byte in a haystack (check_no_null_bytes, src/lib.rs:237-243) */
 };
 
 /* (len_a + len_b) * max(cost) must stay below 2^30 so that u32 cells never wrap */
@@ -119,6 +120,14 @@ int ta_levenshtein_search_batch(ta_ctx *ctx, const uint8_t *needle, size_t needl
                                 const uint64_t *hay_off, size_t n, uint32_t k, int search_type, ta_costs costs,
                                 int anchored, ta_match **out_matches, uint64_t **out_match_off);
 uint32_t ta_search_default_k(size_t needle_len); /* src/levenshtein.rs:1873 */
+
+/* hamming_search_simd_with_opts(needle, haystack_i, k, search_type) (src/hamming.rs:454-475), bit-exact with the
+ * scalar hamming_search_naive_with_opts (src/hamming.rs:96-146) for every haystack of the batch; output layout as
+ * ta_levenshtein_search_batch.  A NUL byte in a searched haystack is TA_ERR_NUL_BYTE (the reference panics).
+ * hamming_search(needle, haystack) (src/hamming.rs:588-590) is k = ta_search_default_k(needle_len), TA_SEARCH_BEST. */
+int ta_hamming_search_batch(ta_ctx *ctx, const uint8_t *needle, size_t needle_len, const uint8_t *hay,
+                            const uint64_t *hay_off, size_t n, uint32_t k, int search_type, ta_match **out_matches,
+                            uint64_t **out_match_off);
 
 /* ---- device-resident entry points (kernel-only; all pointers are device pointers on ctx's device) ---------- */
 /* `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  Calls are asynchronous.

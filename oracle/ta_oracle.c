@@ -488,6 +488,50 @@ int64_t orc_levenshtein_search_naive_with_opts(const uint8_t *needle, size_t nee
     return (int64_t)mv.n;
 }
 
+int64_t orc_hamming_search_naive_with_opts(const uint8_t *needle, size_t needle_len, const uint8_t *haystack,
+                                           size_t haystack_len, uint32_t k, int search_type, orc_match **out) {
+    /* src/hamming.rs:96-146 */
+    match_vec mv = {NULL, 0, 0};
+    *out = NULL;
+    if (needle_len > haystack_len) return 0; /* :100-102 */
+    size_t len = haystack_len + 1 - needle_len;
+    uint32_t curr_k = k;
+    int best = search_type == 1;
+    for (size_t i = 0; i < len; i++) { /* :108-131 */
+        uint32_t final_res = 0;
+        int skip = 0;
+        for (size_t j = 0; j < needle_len; j++) {
+            final_res += (needle[j] != haystack[i + j]);
+            if (final_res > curr_k) { /* early stop */
+                skip = 1;
+                break;
+            }
+        }
+        if (skip) continue;
+        if (best) curr_k = final_res;
+        mv_push(&mv, i, i + needle_len, final_res);
+    }
+    if (best) { /* :136-143 */
+        size_t f = 0;
+        for (size_t r = 0; r < mv.n; r++)
+            if (mv.v[r].k == curr_k) mv.v[f++] = mv.v[r];
+        mv.n = f;
+    }
+    *out = mv.v;
+    return (int64_t)mv.n;
+}
+
+int64_t orc_hamming_search_with_opts(const uint8_t *needle, size_t needle_len, const uint8_t *haystack,
+                                     size_t haystack_len, uint32_t k, int search_type, orc_match **out) {
+    /* src/hamming.rs:454-475 */
+    *out = NULL;
+    if (needle_len > haystack_len) return 0;
+    if (needle_len == 0) return 0;
+    for (size_t i = 0; i < haystack_len; i++) /* check_no_null_bytes, src/lib.rs:237-243 */
+        if (haystack[i] == 0) return -2;
+    return orc_hamming_search_naive_with_opts(needle, needle_len, haystack, haystack_len, k, search_type, out);
+}
+
 /* ------------------------------------------------------------------------------------------------ */
 /* batch drivers for the CPU baseline: a pthread parallel-for with dynamic chunking (libgomp is not   */
 /* in this image).  The reference has no batch API or threads; this is "a user's loop over pairs".   */
@@ -566,6 +610,12 @@ static void lev_exp_range(void *p, size_t lo, size_t hi) {
         x->out[i] = orc_levenshtein_exp_with_opts(x->a + x->a_off[i], x->a_off[i + 1] - x->a_off[i],
                                                   x->b + x->b_off[i], x->b_off[i + 1] - x->b_off[i], x->c);
 }
+static void hsearch_range(void *p, size_t lo, size_t hi) {
+    batch_ctx *x = (batch_ctx *)p;
+    for (size_t i = lo; i < hi; i++)
+        x->cnt[i] = orc_hamming_search_with_opts(x->needle, x->needle_len, x->a + x->a_off[i],
+                                                 x->a_off[i + 1] - x->a_off[i], x->k, x->search_type, &x->per[i]);
+}
 static void search_range(void *p, size_t lo, size_t hi) {
     batch_ctx *x = (batch_ctx *)p;
     for (size_t i = lo; i < hi; i++)
@@ -620,6 +670,37 @@ int64_t orc_levenshtein_search_batch(const uint8_t *needle, size_t needle_len, c
     } else {
         *out = NULL;
         total = -1;
+    }
+    for (size_t i = 0; i < n; i++) free(x.per[i]);
+    free(x.per);
+    free(x.cnt);
+    return total;
+}
+
+int64_t orc_hamming_search_batch(const uint8_t *needle, size_t needle_len, const uint8_t *hay,
+                                 const uint64_t *hay_off, size_t n, uint32_t k, int search_type, orc_match **out,
+                                 uint64_t *match_off, int n_threads) {
+    batch_ctx x = {0};
+    x.a = hay, x.a_off = hay_off, x.k = k, x.needle = needle, x.needle_len = needle_len;
+    x.search_type = search_type;
+    x.per = (orc_match **)calloc(n ? n : 1, sizeof(orc_match *));
+    x.cnt = (int64_t *)calloc(n ? n : 1, sizeof(int64_t));
+    parallel_for(n, 16, n_threads, hsearch_range, &x);
+    int64_t bad = 0, total = 0;
+    for (size_t i = 0; i < n; i++)
+        if (x.cnt[i] < 0) bad = x.cnt[i];
+    if (!bad) {
+        match_off[0] = 0;
+        for (size_t i = 0; i < n; i++) {
+            total += x.cnt[i];
+            match_off[i + 1] = (uint64_t)total;
+        }
+        *out = (orc_match *)malloc((size_t)(total ? total : 1) * sizeof(orc_match));
+        for (size_t i = 0; i < n; i++)
+            if (x.cnt[i] > 0) memcpy(*out + match_off[i], x.per[i], (size_t)x.cnt[i] * sizeof(orc_match));
+    } else {
+        *out = NULL;
+        total = bad;
     }
     for (size_t i = 0; i < n; i++) free(x.per[i]);
     free(x.per);

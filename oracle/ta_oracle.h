@@ -68,6 +68,17 @@ int64_t orc_levenshtein_search_naive_with_opts(const uint8_t *needle, size_t nee
                                                size_t haystack_len, uint32_t k, int search_type, orc_costs c,
                                                int anchored, orc_match **out);
 
+/* hamming_search_naive_with_opts, src/hamming.rs:96-146.  Returns the number of matches (malloc'd array). */
+int64_t orc_hamming_search_naive_with_opts(const uint8_t *needle, size_t needle_len, const uint8_t *haystack,
+                                           size_t haystack_len, uint32_t k, int search_type, orc_match **out);
+/* the public entry hamming_search_simd_with_opts, src/hamming.rs:454-475: empty needle -> no matches, NUL byte in
+ * the haystack -> -2 (the reference panics, src/lib.rs:237-243), otherwise the scalar routine. */
+int64_t orc_hamming_search_with_opts(const uint8_t *needle, size_t needle_len, const uint8_t *haystack,
+                                     size_t haystack_len, uint32_t k, int search_type, orc_match **out);
+int64_t orc_hamming_search_batch(const uint8_t *needle, size_t needle_len, const uint8_t *hay,
+                                 const uint64_t *hay_off, size_t n, uint32_t k, int search_type, orc_match **out,
+                                 uint64_t *match_off, int n_threads);
+
 /* default k of levenshtein_search / levenshtein_search_naive, src/levenshtein.rs:1556, 1873 */
 uint32_t orc_search_default_k(size_t needle_len);
 

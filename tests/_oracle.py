@@ -58,6 +58,14 @@ def lib():
         L.orc_levenshtein_search_naive_with_opts.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t,
                                                              C.c_uint32, C.c_int, Costs, C.c_int,
                                                              C.POINTER(C.POINTER(Match))]
+        for nm in ("orc_hamming_search_naive_with_opts", "orc_hamming_search_with_opts"):
+            f = getattr(L, nm)
+            f.restype = C.c_int64
+            f.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_uint32, C.c_int,
+                          C.POINTER(C.POINTER(Match))]
+        L.orc_hamming_search_batch.restype = C.c_int64
+        L.orc_hamming_search_batch.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32,
+                                               C.c_int, C.POINTER(C.POINTER(Match)), C.c_void_p, C.c_int]
         L.orc_search_default_k.restype = C.c_uint32
         L.orc_search_default_k.argtypes = [C.c_size_t]
         L.orc_costs_valid.argtypes = [Costs]
@@ -132,6 +140,37 @@ def levenshtein_search_naive_with_opts(needle, haystack, k, search_type=0, costs
     if mp:
         lib().orc_free(mp)
     return out
+
+
+def hamming_search_naive_with_opts(needle, haystack, k, search_type=0, public_entry=False):
+    """scalar routine (src/hamming.rs:96-146); public_entry=True adds the checks of hamming_search_simd_with_opts"""
+    mp = C.POINTER(Match)()
+    fn = lib().orc_hamming_search_with_opts if public_entry else lib().orc_hamming_search_naive_with_opts
+    n = fn(needle, len(needle), haystack, len(haystack), k, search_type, C.byref(mp))
+    if n == -2:
+        raise AssertionError("No zero/null bytes allowed in the string! (src/lib.rs:240)")
+    out = [(mp[i].start, mp[i].end, mp[i].k) for i in range(n)]
+    if mp:
+        lib().orc_free(mp)
+    return out
+
+
+def hamming_search_batch(needle, hay, hay_off, k, search_type=0, threads=1):
+    n = len(hay_off) - 1
+    mp = C.POINTER(Match)()
+    moff = np.zeros(n + 1, np.uint64)
+    total = lib().orc_hamming_search_batch(bytes(needle), len(needle), _p(hay), _p(hay_off), n, k, search_type,
+                                           C.byref(mp), _p(moff), threads)
+    if total == -2:
+        raise AssertionError("No zero/null bytes allowed in the string! (src/lib.rs:240)")
+    arr = np.zeros((total, 3), np.uint64)
+    if total:
+        raw = np.ctypeslib.as_array(C.cast(mp, C.POINTER(C.c_uint64)), shape=(total, 3)).copy()
+        arr[:, 0], arr[:, 1] = raw[:, 0], raw[:, 1]
+        arr[:, 2] = raw[:, 2] & 0xFFFFFFFF
+    if mp:
+        lib().orc_free(mp)
+    return arr, moff
 
 
 # ---- batch (CSR numpy arrays) --------------------------------------------------------------------

@@ -85,6 +85,65 @@ def test_kat_search(eng, r):
     assert got == [(m["start"], m["end"], m["k"]) for m in r["expect"]["matches"]]
 
 
+def test_levenshtein_simd_k_str(eng):
+    """src/levenshtein.rs:641-651 (doc-test :637-639) -- chars, not bytes, for non-ASCII strings"""
+    assert eng.levenshtein_simd_k_str("abc", "ab", 1) == 1
+    assert eng.levenshtein_simd_k_str("abc", "xyz", 2) is None
+    assert eng.levenshtein_simd_k_str("nai\u0308ve caf\u00e9", "naive cafe", 5) == 2  # 1 deleted char + 1 substituted
+    assert eng.levenshtein_simd_k_str("\u4f60\u597d\u4e16\u754c", "\u4f60\u597d\u4e16", 3) == 1
+    many = "".join(chr(0x4e00 + i) for i in range(300))
+    assert eng.levenshtein_simd_k_str(many, "x", 400) is None  # > 256 distinct chars (translate_str returns None)
+    rng = random.Random(8)
+    for _ in range(50):
+        alpha = [chr(c) for c in (0x61, 0x62, 0xe9, 0x4f60, 0x1f600)]
+        a = "".join(rng.choice(alpha) for _ in range(rng.randrange(0, 12)))
+        b = "".join(rng.choice(alpha) for _ in range(rng.randrange(0, 12)))
+        code = {ch: i for i, ch in enumerate(alpha)}
+        want = orc.levenshtein_naive_k_with_opts(bytes(code[c] for c in a), bytes(code[c] for c in b), 6)
+        assert eng.levenshtein_simd_k_str(a, b, 6) == (None if want is None else want[0])
+
+
+HSEARCH = [r for r in KAT if r["fn"].startswith("hamming_search")]
+
+
+@pytest.mark.parametrize("r", HSEARCH, ids=_ids(HSEARCH))
+def test_kat_hamming_search(eng, r):
+    needle, hay = bytes.fromhex(r["a"]), bytes.fromhex(r["b"])
+    if "k" in r:
+        got = eng.hamming_search_simd_with_opts(needle, hay, r["k"], r["search_type"])
+    else:
+        got = eng.hamming_search(needle, hay)
+    assert [tuple(m) for m in got] == [(m["start"], m["end"], m["k"]) for m in r["expect"]["matches"]]
+
+
+def test_hamming_search_random(eng):
+    rng = random.Random(31)
+    for trial in range(12):
+        alpha = rng.choice([2, 3, 20])
+        nlen = rng.choice([1, 2, 5, 16, 33, 70])
+        needle = bytes(1 + rng.randrange(alpha) for _ in range(nlen))
+        hays = []
+        for _ in range(100):
+            h = bytearray(1 + rng.randrange(alpha) for _ in range(rng.randrange(0, 400)))
+            if rng.random() < 0.5 and len(h) > nlen:
+                p = rng.randrange(len(h) - nlen)
+                h[p:p + nlen] = bytes((c if rng.random() < 0.9 else 1 + rng.randrange(alpha)) for c in needle)
+            hays.append(bytes(h))
+        hay, hoff = _pack(hays)
+        for k in (0, 1, nlen // 2, nlen, nlen + 5):
+            for st in (0, 1):
+                got, goff = eng.hamming_search_batch(needle, hay, hoff, k, st)
+                want, woff = orc.hamming_search_batch(needle, hay, hoff, k, st, threads=8)
+                assert np.array_equal(goff, woff) and np.array_equal(got, want), (nlen, k, st)
+    # empty needle -> no matches (src/hamming.rs:459-461); NUL byte in a haystack -> panic (src/lib.rs:237-243)
+    hay, hoff = _pack([b"abc", b"defg"])
+    got, goff = eng.hamming_search_batch(b"", hay, hoff, 1, 0)
+    assert len(got) == 0 and list(goff) == [0, 0, 0]
+    hay, hoff = _pack([b"abc", b"de\0g"])
+    with pytest.raises(AssertionError):
+        eng.hamming_search_batch(b"de", hay, hoff, 1, 0)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # error behaviour of the boundary
 def test_hamming_length_mismatch_panics(eng):

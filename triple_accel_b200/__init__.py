@@ -4,9 +4,10 @@ The product is libtriple_accel_b200.so (C ABI in include/triple_accel_b200.h, CU
 package is the Python host mirror of the crate's public names used by the tests and the bench.
 """
 from .api import (EditCosts, EditType, Engine, LEVENSHTEIN_COSTS, Match, RDAMERAU_COSTS, SearchType, TA_NONE,
-                  TripleAccelError, default_engine, hamming, hamming_batch, levenshtein, levenshtein_exp,
+                  TripleAccelError, default_engine, hamming, hamming_batch, hamming_search, hamming_search_batch,
+                  hamming_search_simd, hamming_search_simd_with_opts, levenshtein, levenshtein_exp,
                   levenshtein_exp_batch, levenshtein_exp_with_opts, levenshtein_k_batch, levenshtein_search,
                   levenshtein_search_batch, levenshtein_search_simd, levenshtein_search_simd_with_opts,
-                  levenshtein_simd_k, levenshtein_simd_k_with_opts, pack, rdamerau, rdamerau_exp)
+                  levenshtein_simd_k, levenshtein_simd_k_str, levenshtein_simd_k_with_opts, pack, rdamerau, rdamerau_exp)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

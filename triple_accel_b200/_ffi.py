@@ -17,6 +17,7 @@ TA_ERR_BAD_COSTS = -3
 TA_ERR_BAD_ARG = -4
 TA_ERR_TOO_LARGE = -5
 TA_ERR_NOMEM = -6
+TA_ERR_NUL_BYTE = -7
 TA_SEARCH_ALL = 0
 TA_SEARCH_BEST = 1
 
@@ -50,6 +51,8 @@ SIGNATURES = {
     "ta_levenshtein_search_batch": (_int, [_vp, _vp, _sz, _vp, _vp, _sz, _u32, _int, ta_costs, _int,
                                            C.POINTER(C.POINTER(ta_match)), C.POINTER(C.POINTER(C.c_uint64))]),
     "ta_search_default_k": (_u32, [_sz]),
+    "ta_hamming_search_batch": (_int, [_vp, _vp, _sz, _vp, _vp, _sz, _u32, _int,
+                                       C.POINTER(C.POINTER(ta_match)), C.POINTER(C.POINTER(C.c_uint64))]),
     "ta_hamming_batch_dev": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "ta_levenshtein_k_batch_dev": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, _u32, ta_costs, _u32, _vp, _vp]),
     "ta_levenshtein_exp_batch_dev": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, ta_costs, _u32, _vp, _vp]),

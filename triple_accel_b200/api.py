@@ -134,6 +134,8 @@ class Engine:
             return
         if rc == _ffi.TA_ERR_LEN_MISMATCH:  # the crate panics (src/hamming.rs:38, 318)
             raise AssertionError("hamming: a.len() != b.len()")
+        if rc == _ffi.TA_ERR_NUL_BYTE:  # src/lib.rs:237-243
+            raise AssertionError("No zero/null bytes allowed in the string!")
         if rc == _ffi.TA_ERR_BAD_COSTS:  # src/levenshtein.rs:44-52, 69
             raise AssertionError("invalid EditCosts")
         raise TripleAccelError(rc, self._lib.ta_last_error(self._h).decode() if rc == _ffi.TA_ERR_CUDA else "")
@@ -178,6 +180,29 @@ class Engine:
                                                    int(bool(anchored)), C.byref(mp), C.byref(op))
         self._check(rc)
         return self._take_matches(mp, op, n)
+
+    def hamming_search_batch(self, needle, hay, hay_off, k, search_type=SearchType.All):
+        """Returns (matches[total, 3] uint64 = start,end,k ; match_off[n+1])."""
+        needle, hay, hay_off = _u8(needle), _u8(hay), _u64(hay_off)
+        n = len(hay_off) - 1
+        mp, op = C.POINTER(ta_match)(), C.POINTER(C.c_uint64)()
+        rc = self._lib.ta_hamming_search_batch(self._h, _ptr(needle), len(needle), _ptr(hay), _ptr(hay_off), n,
+                                               int(k) & 0xFFFFFFFF, int(search_type), C.byref(mp), C.byref(op))
+        self._check(rc)
+        return self._take_matches(mp, op, n)
+
+    def hamming_search_simd_with_opts(self, needle, haystack, k, search_type=SearchType.All):
+        """src/hamming.rs:454-475.  Returns a list of Match."""
+        haystack = _u8(haystack)
+        off = np.array([0, len(haystack)], np.uint64)
+        arr, _ = self.hamming_search_batch(needle, haystack, off, k, search_type)
+        return [Match(int(s), int(e), int(c)) for s, e, c in arr]
+
+    def hamming_search_simd(self, needle, haystack):  # src/hamming.rs:422-424
+        k = self._lib.ta_search_default_k(len(bytes(needle)))
+        return self.hamming_search_simd_with_opts(needle, haystack, k, SearchType.Best)
+
+    hamming_search = hamming_search_simd  # src/hamming.rs:588-590
 
     def _take_matches(self, mp, op, n):
         try:
@@ -257,6 +282,26 @@ class Engine:
         r = self.levenshtein_simd_k_with_opts(a, b, k, False, LEVENSHTEIN_COSTS)
         return None if r is None else r[0]
 
+    def levenshtein_simd_k_str(self, a: str, b: str, k):
+        """src/levenshtein.rs:641-651: distance between two `str`s counted in chars.  ASCII strings are compared as
+        bytes; otherwise every distinct char (in order of first appearance in a, then b) is mapped to a u8 code
+        (translate_str, :609-624) and None is returned if there are more than 256 distinct chars."""
+        if a.isascii() and b.isascii():
+            return self.levenshtein_simd_k(a.encode(), b.encode(), k)
+        codes = {}
+        out = []
+        for s in (a, b):
+            buf = bytearray()
+            for ch in s:
+                c = codes.get(ch)
+                if c is None:
+                    if len(codes) >= 256:
+                        return None
+                    c = codes[ch] = len(codes)
+                buf.append(c)
+            out.append(bytes(buf))
+        return self.levenshtein_simd_k(out[0], out[1], k)
+
     def levenshtein(self, a, b):  # src/levenshtein.rs:1397-1399
         return self.levenshtein_simd_k(a, b, 0xFFFFFFFF)
 
@@ -318,10 +363,15 @@ levenshtein_exp = _forward("levenshtein_exp")
 levenshtein_exp_with_opts = _forward("levenshtein_exp_with_opts")
 rdamerau_exp = _forward("rdamerau_exp")
 levenshtein_simd_k = _forward("levenshtein_simd_k")
+levenshtein_simd_k_str = _forward("levenshtein_simd_k_str")
 levenshtein_simd_k_with_opts = _forward("levenshtein_simd_k_with_opts")
 levenshtein_search = _forward("levenshtein_search")
 levenshtein_search_simd = _forward("levenshtein_search_simd")
 levenshtein_search_simd_with_opts = _forward("levenshtein_search_simd_with_opts")
+hamming_search = _forward("hamming_search")
+hamming_search_simd = _forward("hamming_search_simd")
+hamming_search_simd_with_opts = _forward("hamming_search_simd_with_opts")
+hamming_search_batch = _forward("hamming_search_batch")
 hamming_batch = _forward("hamming_batch")
 levenshtein_k_batch = _forward("levenshtein_k_batch")
 levenshtein_exp_batch = _forward("levenshtein_exp_batch")

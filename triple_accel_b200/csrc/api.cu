@@ -70,6 +70,7 @@ const char *ta_strerror(int code) {
         case TA_ERR_BAD_ARG: return "bad argument";
         case TA_ERR_TOO_LARGE: return "input too large for this build";
         case TA_ERR_NOMEM: return "out of host memory";
+        case TA_ERR_NUL_BYTE: return "hamming_search: zero/null bytes are not allowed in the haystack";
         default: return "unknown error";
     }
 }
