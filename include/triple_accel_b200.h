@@ -64,6 +64,12 @@ typedef struct {
     uint32_t k, _pad;
 } ta_match;
 
+/* Edit (src/lib.rs:159-165): a run of `count` edits of one EditType (src/lib.rs:147-154) */
+enum { TA_EDIT_MATCH = 0, TA_EDIT_MISMATCH = 1, TA_EDIT_AGAP = 2, TA_EDIT_BGAP = 3, TA_EDIT_TRANSPOSE = 4 };
+typedef struct {
+    uint32_t edit, count;
+} ta_edit;
+
 /* SearchType (src/lib.rs:170-174) */
 enum { TA_SEARCH_ALL = 0, TA_SEARCH_BEST = 1 };
 
@@ -102,6 +108,18 @@ int ta_hamming_batch(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const
  * k = 0xFFFFFFFF gives levenshtein() / rdamerau() (src/levenshtein.rs:1397-1399, 1419-1423). */
 int ta_levenshtein_k_batch(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b,
                            const uint64_t *b_off, size_t n, uint32_t k, ta_costs costs, uint32_t *out);
+
+/* levenshtein_simd_k_with_opts(a, b, k, true, costs): distances as above plus the edit traceback of every pair
+ * within k, bit-exact with the scalar levenshtein_naive_k_with_opts(.., trace_on = true)
+ * (src/levenshtein.rs:493-606).  Runs of pair i are (*out_edits)[(*out_edit_off)[i] .. (*out_edit_off)[i+1])
+ * (none for TA_NONE pairs); release both arrays with ta_free.  Bands up to 1024 diagonals. */
+int ta_levenshtein_k_trace_batch(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b,
+                                 const uint64_t *b_off, size_t n, uint32_t k, ta_costs costs, uint32_t *out_dist,
+                                 ta_edit **out_edits, uint64_t **out_edit_off);
+/* levenshtein_exp_with_opts(a, b, true, costs) (src/levenshtein.rs:1480-1494): exact distance and traceback. */
+int ta_levenshtein_exp_trace_batch(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b,
+                                   const uint64_t *b_off, size_t n, ta_costs costs, uint32_t *out_dist,
+                                   ta_edit **out_edits, uint64_t **out_edit_off);
 
 /* levenshtein_exp / levenshtein_exp_with_opts / rdamerau_exp (src/levenshtein.rs:1445-1454, 1480-1494,
  * 1516-1526): exact distance by running the k-bounded routine with k = 30, 60, 120, ... on the pairs that are

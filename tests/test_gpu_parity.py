@@ -60,6 +60,9 @@ def test_kat_distance(eng, r):
     costs = ta.EditCosts(c[0], c[1], c[2], c[3] or None)
     if fn in ("levenshtein_exp", "levenshtein_exp_with_opts", "rdamerau_exp"):
         assert eng.levenshtein_exp_with_opts(a, b, False, costs)[0] == r["expect"]["dist"]
+        if r.get("trace"):
+            d, edits = eng.levenshtein_exp_with_opts(a, b, True, costs)
+            assert d == r["expect"]["dist"] and [list(e) for e in edits] == r["expect"]["edits"]
         return
     k = r.get("k", 0xFFFFFFFF)  # levenshtein()/rdamerau()/naive: k = u32::MAX
     res = eng.levenshtein_simd_k_with_opts(a, b, k, False, costs)
@@ -67,6 +70,11 @@ def test_kat_distance(eng, r):
         assert res is None
     else:
         assert res is not None and res[0] == r["expect"]["dist"]
+    # trace_on = true KATs of the k-bounded routines (tests/basic_tests.rs:395-427, 545-577 and doc-tests); the
+    # unbounded levenshtein_naive_with_opts has its own tie rules and is not on the offloaded path
+    if r.get("trace") and fn in ("levenshtein_naive_k_with_opts", "levenshtein_simd_k_with_opts"):
+        d, edits = eng.levenshtein_simd_k_with_opts(a, b, k, True, costs)
+        assert d == r["expect"]["dist"] and [list(e) for e in edits] == r["expect"]["edits"]
 
 
 @pytest.mark.parametrize("r", SEARCH, ids=_ids(SEARCH))
@@ -440,6 +448,56 @@ def test_lev_very_wide_band_global_workspace(eng):
     got = eng.levenshtein_k_batch(a, ao, b, bo, 0xFFFFFFFF, (1, 1, 0, 1))
     want = orc.levenshtein_k_batch(a, ao, b, bo, 0xFFFFFFFF, (1, 1, 0, 1), threads=2)
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("costs", COST_MODELS, ids=[str(c) for c in COST_MODELS])
+def test_traceback_random(eng, costs):
+    """trace_on = true: the run-length encoded edits must equal the scalar routine's, tie-breaks included
+    (src/levenshtein.rs:493-606); small alphabets make ties the common case"""
+    rng = random.Random(1000 + sum(costs))
+    A, B = [], []
+    for _ in range(1500):
+        alpha = rng.choice([2, 3, 4, 26])
+        s = bytes(rng.randrange(alpha) for _ in range(rng.randrange(0, 40)))
+        A.append(s)
+        B.append(_mutate(rng, s, rng.randrange(0, 8), alpha) if rng.random() < 0.7 else
+                 bytes(rng.randrange(alpha) for _ in range(rng.randrange(0, 40))))
+    a, ao = _pack(A)
+    b, bo = _pack(B)
+    for k in (0, 3, 9, 40, 0xFFFFFFFF):
+        dist, edits, eoff = eng.levenshtein_k_trace_batch(a, ao, b, bo, k, costs)
+        assert np.array_equal(dist, orc.levenshtein_k_batch(a, ao, b, bo, k, costs))
+        for i in range(0, len(A), 3):
+            want = orc.levenshtein_naive_k_with_opts(A[i], B[i], k, True, costs)
+            got = [tuple(int(x) for x in e) for e in edits[int(eoff[i]):int(eoff[i + 1])]]
+            if want is None:
+                assert dist[i] == NONE and got == []
+            else:
+                assert got == [tuple(e) for e in want[1]], (A[i], B[i], k, costs, got, want)
+    # exponential search with traceback (src/levenshtein.rs:1480-1494)
+    dist, edits, eoff = eng.levenshtein_exp_trace_batch(a, ao, b, bo, costs)
+    assert np.array_equal(dist, orc.levenshtein_exp_batch(a, ao, b, bo, costs))
+    for i in range(0, len(A), 7):
+        want = orc.levenshtein_naive_k_with_opts(A[i], B[i], 0xFFFFFFFF, True, costs)
+        got = [tuple(int(x) for x in e) for e in edits[int(eoff[i]):int(eoff[i + 1])]]
+        assert got == [tuple(e) for e in want[1]], (A[i], B[i], costs)
+
+
+def test_traceback_longer_strings(eng):
+    rng = random.Random(5150)
+    A = _rand_strs(rng, 120, 100, 400, 4)
+    B = [_mutate(rng, s, rng.randrange(0, 60), 4) for s in A]
+    a, ao = _pack(A)
+    b, bo = _pack(B)
+    for costs, k in (((1, 1, 0, 0), 30), ((1, 1, 0, 1), 70), ((2, 1, 3, 0), 200), ((1, 1, 0, 0), 0xFFFFFFFF)):
+        dist, edits, eoff = eng.levenshtein_k_trace_batch(a, ao, b, bo, k, costs)
+        for i in range(len(A)):
+            want = orc.levenshtein_naive_k_with_opts(A[i], B[i], k, True, costs)
+            got = [tuple(int(x) for x in e) for e in edits[int(eoff[i]):int(eoff[i + 1])]]
+            if want is None:
+                assert dist[i] == NONE and got == []
+            else:
+                assert dist[i] == want[0] and got == [tuple(e) for e in want[1]], (i, costs, k)
 
 
 LEV_TESTS = "test_lev_k_mutated or test_lev_k_random_short or test_nul_bytes or test_lev_exp"

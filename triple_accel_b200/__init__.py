@@ -3,7 +3,7 @@
 The product is libtriple_accel_b200.so (C ABI in include/triple_accel_b200.h, CUDA sources in csrc/).  This
 package is the Python host mirror of the crate's public names used by the tests and the bench.
 """
-from .api import (EditCosts, EditType, Engine, LEVENSHTEIN_COSTS, Match, RDAMERAU_COSTS, SearchType, TA_NONE,
+from .api import (Edit, EditCosts, EditType, Engine, LEVENSHTEIN_COSTS, Match, RDAMERAU_COSTS, SearchType, TA_NONE,
                   TripleAccelError, default_engine, hamming, hamming_batch, hamming_search, hamming_search_batch,
                   hamming_search_simd, hamming_search_simd_with_opts, levenshtein, levenshtein_exp,
                   levenshtein_exp_batch, levenshtein_exp_with_opts, levenshtein_k_batch, levenshtein_search,

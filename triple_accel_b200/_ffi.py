@@ -26,6 +26,10 @@ class ta_costs(C.Structure):
     _fields_ = [("mismatch", C.c_uint8), ("gap", C.c_uint8), ("start_gap", C.c_uint8), ("transpose", C.c_uint8)]
 
 
+class ta_edit(C.Structure):
+    _fields_ = [("edit", C.c_uint32), ("count", C.c_uint32)]
+
+
 class ta_match(C.Structure):
     _fields_ = [("start", C.c_uint64), ("end", C.c_uint64), ("k", C.c_uint32), ("_pad", C.c_uint32)]
 
@@ -48,6 +52,10 @@ SIGNATURES = {
     "ta_hamming_batch": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ta_levenshtein_k_batch": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, _u32, ta_costs, _vp]),
     "ta_levenshtein_exp_batch": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, ta_costs, _vp]),
+    "ta_levenshtein_k_trace_batch": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, _u32, ta_costs, _vp,
+                                            C.POINTER(C.POINTER(ta_edit)), C.POINTER(C.POINTER(C.c_uint64))]),
+    "ta_levenshtein_exp_trace_batch": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, ta_costs, _vp,
+                                              C.POINTER(C.POINTER(ta_edit)), C.POINTER(C.POINTER(C.c_uint64))]),
     "ta_levenshtein_search_batch": (_int, [_vp, _vp, _sz, _vp, _vp, _sz, _u32, _int, ta_costs, _int,
                                            C.POINTER(C.POINTER(ta_match)), C.POINTER(C.POINTER(C.c_uint64))]),
     "ta_search_default_k": (_u32, [_sz]),

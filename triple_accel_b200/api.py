@@ -12,10 +12,12 @@ from collections import namedtuple
 import numpy as np
 
 from . import _ffi
-from ._ffi import TA_NONE, ta_costs, ta_match
+from ._ffi import TA_NONE, ta_costs, ta_edit, ta_match
 
 # src/lib.rs:134-142 -- start inclusive, end exclusive
 Match = namedtuple("Match", ["start", "end", "k"])
+# src/lib.rs:159-165 -- a run of `count` edits of type `edit` (EditType)
+Edit = namedtuple("Edit", ["edit", "count"])
 
 
 class SearchType:  # src/lib.rs:170-174
@@ -169,6 +171,30 @@ class Engine:
                                                        _as_costs(costs)._c(), _ptr(out)))
         return out
 
+    def _trace(self, fn, a, a_off, b, b_off, *mid):
+        a, b, a_off, b_off = _u8(a), _u8(b), _u64(a_off), _u64(b_off)
+        n = len(a_off) - 1
+        out = np.empty(n, np.uint32)
+        ep, op = C.POINTER(ta_edit)(), C.POINTER(C.c_uint64)()
+        self._check(fn(self._h, _ptr(a), _ptr(a_off), _ptr(b), _ptr(b_off), n, *mid, _ptr(out), C.byref(ep), C.byref(op)))
+        try:
+            eoff = np.ctypeslib.as_array(op, shape=(n + 1,)).copy()
+            total = int(eoff[n])
+            edits = (np.ctypeslib.as_array(C.cast(ep, C.POINTER(C.c_uint32)), shape=(total, 2)).copy()
+                     if total else np.zeros((0, 2), np.uint32))
+        finally:
+            self._lib.ta_free(ep)
+            self._lib.ta_free(op)
+        return out, edits, eoff
+
+    def levenshtein_k_trace_batch(self, a, a_off, b, b_off, k, costs=LEVENSHTEIN_COSTS):
+        """trace_on = true for a batch: (dist[n], edits[total, 2] = (EditType, count), edit_off[n+1])."""
+        return self._trace(self._lib.ta_levenshtein_k_trace_batch, a, a_off, b, b_off, int(k) & 0xFFFFFFFF,
+                           _as_costs(costs)._c())
+
+    def levenshtein_exp_trace_batch(self, a, a_off, b, b_off, costs=LEVENSHTEIN_COSTS):
+        return self._trace(self._lib.ta_levenshtein_exp_trace_batch, a, a_off, b, b_off, _as_costs(costs)._c())
+
     def levenshtein_search_batch(self, needle, hay, hay_off, k, search_type=SearchType.All,
                                  costs=LEVENSHTEIN_COSTS, anchored=False):
         """Returns (matches[total, 3] uint64 = start,end,k ; match_off[n+1])."""
@@ -269,10 +295,13 @@ class Engine:
         return out.value
 
     def levenshtein_simd_k_with_opts(self, a, b, k, trace_on=False, costs=LEVENSHTEIN_COSTS):
-        """src/levenshtein.rs:714-720: None, or (distance, None).  trace_on=True is not built yet (SURVEY 8f #1)."""
-        if trace_on:
-            raise NotImplementedError("traceback (trace_on=true) is a 'next' row of the scope table")
+        """src/levenshtein.rs:714-720: None, or (distance, None | [Edit, ...])."""
         a, b = bytes(a), bytes(b)
+        if trace_on:
+            ab, ao = pack([a])
+            bb, bo = pack([b])
+            d, ed, _ = self.levenshtein_k_trace_batch(ab, ao, bb, bo, k, costs)
+            return None if d[0] == TA_NONE else (int(d[0]), [Edit(int(e), int(c)) for e, c in ed])
         out = C.c_uint32()
         self._check(self._lib.ta_levenshtein_simd_k_with_opts(self._h, a, len(a), b, len(b), int(k) & 0xFFFFFFFF,
                                                               _as_costs(costs)._c(), C.byref(out)))
@@ -309,9 +338,12 @@ class Engine:
         return self.levenshtein_simd_k_with_opts(a, b, 0xFFFFFFFF, False, RDAMERAU_COSTS)[0]
 
     def levenshtein_exp_with_opts(self, a, b, trace_on=False, costs=LEVENSHTEIN_COSTS):  # :1480-1494
-        if trace_on:
-            raise NotImplementedError("traceback (trace_on=true) is a 'next' row of the scope table")
         a, b = bytes(a), bytes(b)
+        if trace_on:
+            ab, ao = pack([a])
+            bb, bo = pack([b])
+            d, ed, _ = self.levenshtein_exp_trace_batch(ab, ao, bb, bo, costs)
+            return int(d[0]), [Edit(int(e), int(c)) for e, c in ed]
         out = C.c_uint32()
         self._check(self._lib.ta_levenshtein_exp_with_opts(self._h, a, len(a), b, len(b), _as_costs(costs)._c(),
                                                            C.byref(out)))

@@ -333,6 +333,169 @@ int ta_levenshtein_exp_batch(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_of
     return run_pairs(ctx, OP_LEV_EXP, a, a_off, b, b_off, n, 0, costs, out);
 }
 
+}  // extern "C"
+
+namespace {
+
+// Runs the TRACE kernel + the two walk passes over `cnt` work items (pairs pair_base + w, or h_idx[w] when an index
+// list is given; d_idx is its device copy) in chunks bounded by the trace workspace, appending every pair's runs
+// to `pool` and recording where they start (pos) and how many there are (num).
+int run_trace_group(ta_ctx *ctx, cudaStream_t st, const uint8_t *da, const uint64_t *da_off, const uint8_t *db,
+                    const uint64_t *db_off, const uint32_t *d_idx, const uint32_t *h_idx, size_t pair_base, size_t cnt,
+                    uint32_t k, ta_costs costs, uint32_t max_len, uint32_t *d_out, std::vector<ta_edit> &pool,
+                    std::vector<uint64_t> &pos, std::vector<uint32_t> &num) {
+    if (cnt == 0) return TA_OK;
+    const uint32_t W = ta_band_width_bound(k, costs, max_len);
+    const uint32_t wc = ta_trace_cells(W);
+    if (wc == 0) return TA_ERR_TOO_LARGE;  // traceback supports bands of up to 1024 diagonals
+    const size_t stride = (((size_t)2 * max_len + 3) * wc + 15) & ~(size_t)15;
+    const size_t budget = (size_t)2 << 30;
+    const size_t chunk_n = std::max<size_t>(1, std::min(cnt, budget / stride));
+    int rc;
+    if ((rc = ta_dev_reserve(ctx, ctx->d_work[3], chunk_n * stride)) != TA_OK) return rc;
+    if ((rc = ta_dev_reserve(ctx, ctx->d_work[2], chunk_n * sizeof(uint32_t))) != TA_OK) return rc;
+    if ((rc = ta_dev_reserve(ctx, ctx->d_work[1], chunk_n * sizeof(uint64_t))) != TA_OK) return rc;
+    std::vector<uint32_t> h_counts(chunk_n);
+    std::vector<uint64_t> h_off(chunk_n + 1);
+    for (size_t c0 = 0; c0 < cnt; c0 += chunk_n) {
+        const size_t cn = std::min(chunk_n, cnt - c0);
+        const uint32_t *ci = d_idx ? d_idx + c0 : nullptr;
+        uint8_t *trace = (uint8_t *)ctx->d_work[3].p;
+        uint32_t *d_counts = (uint32_t *)ctx->d_work[2].p;
+        uint64_t *d_off = (uint64_t *)ctx->d_work[1].p;
+        if ((rc = ta_launch_lev_band_trace(ctx, da, da_off, db, db_off, cn, ci, pair_base + c0, k, costs, max_len, d_out,
+                                           trace, stride, st)) != TA_OK)
+            return rc;
+        if ((rc = ta_launch_trace_walk(ctx, da, da_off, db, db_off, cn, ci, pair_base + c0, k, costs, max_len, d_out,
+                                       trace, stride, d_counts, nullptr, nullptr, st)) != TA_OK)
+            return rc;
+        TA_CUDA(ctx, cudaMemcpyAsync(h_counts.data(), d_counts, cn * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        TA_CUDA(ctx, cudaStreamSynchronize(st));
+        h_off[0] = 0;
+        for (size_t q = 0; q < cn; q++) h_off[q + 1] = h_off[q] + h_counts[q];
+        const uint64_t total = h_off[cn];
+        if (total) {
+            if ((rc = ta_dev_reserve(ctx, ctx->d_work[0], total * sizeof(ta_edit))) != TA_OK) return rc;
+            TA_CUDA(ctx, cudaMemcpyAsync(d_off, h_off.data(), cn * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+            if ((rc = ta_launch_trace_walk(ctx, da, da_off, db, db_off, cn, ci, pair_base + c0, k, costs, max_len,
+                                           d_out, trace, stride, d_counts, d_off, (ta_edit *)ctx->d_work[0].p, st)) != TA_OK)
+                return rc;
+            const size_t base = pool.size();
+            pool.resize(base + total);
+            TA_CUDA(ctx, cudaMemcpyAsync(pool.data() + base, ctx->d_work[0].p, total * sizeof(ta_edit),
+                                         cudaMemcpyDeviceToHost, st));
+            TA_CUDA(ctx, cudaStreamSynchronize(st));
+            for (size_t q = 0; q < cn; q++) {
+                const size_t pair = h_idx ? h_idx[c0 + q] : pair_base + c0 + q;
+                pos[pair] = base + h_off[q];
+                num[pair] = h_counts[q];
+            }
+        }
+    }
+    return TA_OK;
+}
+
+int trace_batch(ta_ctx *ctx, bool exp_mode, const uint8_t *a, const uint64_t *a_off, const uint8_t *b,
+                const uint64_t *b_off, size_t n, uint32_t k, ta_costs costs, uint32_t *out_dist, ta_edit **out_edits,
+                uint64_t **out_edit_off) {
+    if (!ctx || !out_edits || !out_edit_off) return TA_ERR_BAD_ARG;
+    *out_edits = nullptr;
+    *out_edit_off = nullptr;
+    int rc = check_costs(costs);
+    if (rc != TA_OK) return rc;
+    if (n && (!a_off || !b_off || !out_dist)) return TA_ERR_BAD_ARG;
+    if (n > 0xFFFFFFF0ull) return TA_ERR_TOO_LARGE;
+    uint64_t *eoff = (uint64_t *)calloc(n + 1, sizeof(uint64_t));
+    if (!eoff) return TA_ERR_NOMEM;
+    std::vector<ta_edit> pool;
+    std::vector<uint64_t> pos(n, 0);
+    std::vector<uint32_t> num(n, 0);
+    if (n) {
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        auto run = [&]() -> int {
+            TA_CUDA(ctx, cudaSetDevice(ctx->device));
+            BatchStats bs;
+            int r = scan_offsets(a_off, b_off, n, false, bs);
+            if (r != TA_OK) return r;
+            if ((bs.a_bytes && !a) || (bs.b_bytes && !b)) return TA_ERR_BAD_ARG;
+            cudaStream_t st = ctx->stream;
+            const uint8_t *da, *db;
+            const uint64_t *da_off, *db_off;
+            if ((r = upload_side(ctx, 0, true, a, a_off, n, &da, &da_off, st)) != TA_OK) return r;
+            if ((r = upload_side(ctx, 0, false, b, b_off, n, &db, &db_off, st)) != TA_OK) return r;
+            if ((r = ta_dev_reserve(ctx, ctx->d_out[0], n * sizeof(uint32_t))) != TA_OK) return r;
+            uint32_t *d_out = (uint32_t *)ctx->d_out[0].p;
+            if (!exp_mode) {
+                r = run_trace_group(ctx, st, da, da_off, db, db_off, nullptr, nullptr, 0, n, k, costs, bs.max_len, d_out,
+                                    pool, pos, num);
+                if (r != TA_OK) return r;
+            } else {
+                // exact distances first (src/levenshtein.rs:1486-1493), then the traceback of each pair with the k of
+                // the round that accepted it (the decisions along an optimal path do not depend on the band width)
+                if ((r = exp_rounds_dev(ctx, da, da_off, db, db_off, n, costs, bs.max_len, d_out, st)) != TA_OK) return r;
+                TA_CUDA(ctx, cudaMemcpyAsync(out_dist, d_out, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+                TA_CUDA(ctx, cudaStreamSynchronize(st));
+                std::vector<std::vector<uint32_t>> rounds;
+                for (size_t i = 0; i < n; i++) {
+                    size_t rr = 0;
+                    uint64_t kk = 30;
+                    while (kk < out_dist[i]) kk *= 2, rr++;
+                    if (rounds.size() <= rr) rounds.resize(rr + 1);
+                    rounds[rr].push_back((uint32_t)i);
+                }
+                if ((r = ta_dev_reserve(ctx, ctx->d_aoff[1], n * sizeof(uint32_t))) != TA_OK) return r;
+                uint32_t *d_idx = (uint32_t *)ctx->d_aoff[1].p;
+                uint64_t kk = 30;
+                for (size_t rr = 0; rr < rounds.size(); rr++, kk *= 2) {
+                    if (rounds[rr].empty()) continue;
+                    TA_CUDA(ctx, cudaMemcpyAsync(d_idx, rounds[rr].data(), rounds[rr].size() * sizeof(uint32_t),
+                                                 cudaMemcpyHostToDevice, st));
+                    r = run_trace_group(ctx, st, da, da_off, db, db_off, d_idx, rounds[rr].data(), 0, rounds[rr].size(),
+                                        (uint32_t)std::min<uint64_t>(kk, 0xFFFFFFFFull), costs, bs.max_len, d_out, pool,
+                                        pos, num);
+                    if (r != TA_OK) return r;
+                }
+            }
+            TA_CUDA(ctx, cudaMemcpyAsync(out_dist, d_out, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            TA_CUDA(ctx, cudaStreamSynchronize(st));
+            return TA_OK;
+        };
+        rc = run();
+        if (rc != TA_OK) {
+            cudaStreamSynchronize(ctx->stream);
+            free(eoff);
+            return rc;
+        }
+    }
+    for (size_t i = 0; i < n; i++) eoff[i + 1] = eoff[i] + num[i];
+    ta_edit *ed = (ta_edit *)malloc((eoff[n] ? eoff[n] : 1) * sizeof(ta_edit));
+    if (!ed) {
+        free(eoff);
+        return TA_ERR_NOMEM;
+    }
+    for (size_t i = 0; i < n; i++)
+        if (num[i]) memcpy(ed + eoff[i], pool.data() + pos[i], (size_t)num[i] * sizeof(ta_edit));
+    *out_edits = ed;
+    *out_edit_off = eoff;
+    return TA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ta_levenshtein_k_trace_batch(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b,
+                                 const uint64_t *b_off, size_t n, uint32_t k, ta_costs costs, uint32_t *out_dist,
+                                 ta_edit **out_edits, uint64_t **out_edit_off) {
+    return trace_batch(ctx, false, a, a_off, b, b_off, n, k, costs, out_dist, out_edits, out_edit_off);
+}
+
+int ta_levenshtein_exp_trace_batch(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b,
+                                   const uint64_t *b_off, size_t n, ta_costs costs, uint32_t *out_dist,
+                                   ta_edit **out_edits, uint64_t **out_edit_off) {
+    return trace_batch(ctx, true, a, a_off, b, b_off, n, 0, costs, out_dist, out_edits, out_edit_off);
+}
+
 int ta_hamming_batch_dev(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b,
                          const uint64_t *b_off, size_t n, uint32_t *out, void *stream) {
     if (!ctx) return TA_ERR_BAD_ARG;

@@ -27,12 +27,17 @@ struct BandArgs {
     const uint64_t *a_off;
     const uint8_t *b;
     const uint64_t *b_off;
-    const uint32_t *idx;  // optional indirection
+    const uint32_t *idx;  // optional indirection: work item w -> pair idx[w]
+    size_t pair_base;     // without idx: work item w -> pair pair_base + w
     size_t n;
     uint32_t k;
     uint32_t mism, gap, sgap, tcost;
     uint32_t slot;  // shared-memory bytes reserved per string (SMEM variants)
     uint32_t *out;
+    // traceback (TRACE variants): one byte per band cell, work item w owns trace[w * trace_stride ..), laid out
+    // [anti-diagonal s - s0][cell]; 0 = substitution/match, 1 = a-gap, 2 = b-gap, 3 = transposition
+    uint8_t *trace;
+    size_t trace_stride;
 };
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
@@ -43,7 +48,31 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 __device__ __forceinline__ uint32_t umin3(uint32_t x, uint32_t y, uint32_t z) { return min(min(x, y), z); }
 
-template <int G, int C, bool AFFINE, bool TRANS, bool SMEM>
+// Per-pair band: the reference's max_k / unit_k clamps (src/levenshtein.rs:400-430) and the Ukkonen band
+// [dlo, dlo + W - 1] = [-e, diff + e]; one extra diagonal each side when transpositions need the neighbours' match
+// flags.  Shared by every kernel of this file and by the traceback walker so that they agree cell by cell.
+struct BandInfo {
+    uint32_t max_k;
+    int dlo, W;
+    bool none;  // the length difference alone exceeds the band: Option::None
+};
+__device__ __forceinline__ BandInfo band_info(int m, int n, uint32_t k, uint32_t mism, uint32_t gap, uint32_t sgap,
+                                              bool trans) {
+    BandInfo bi;
+    const uint32_t diff = (uint32_t)(n - m);
+    uint32_t max_k = min((uint32_t)m * mism, ((uint32_t)m << 1) * gap + (m == 0 ? 0u : sgap + (n == m ? sgap : 0u)));
+    max_k = min(k, max_k + diff * gap + (n == m ? 0u : sgap));
+    const uint32_t unit_k = (max_k > sgap ? max_k - sgap : 0u) / gap;
+    bi.max_k = max_k;
+    bi.none = diff > unit_k;
+    const uint32_t spare = max_k >= 2 * sgap + diff * gap ? max_k - 2 * sgap - diff * gap : 0u;
+    const int e = (int)(spare / (2 * gap)) + (trans ? 1 : 0);
+    bi.dlo = -e;
+    bi.W = (int)diff + 2 * e + 1;
+    return bi;
+}
+
+template <int G, int C, bool AFFINE, bool TRANS, bool SMEM, bool TRACE>
 __global__ void __launch_bounds__(128) lev_band_kernel(const BandArgs args) {
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr int GROUPS = 128 / G;
@@ -53,7 +82,7 @@ __global__ void __launch_bounds__(128) lev_band_kernel(const BandArgs args) {
 
     const size_t w = (size_t)blockIdx.x * GROUPS + grp;
     if (w >= args.n) return;  // whole group leaves together (shuffles below use the group mask)
-    const size_t pair = args.idx ? (size_t)args.idx[w] : w;
+    const size_t pair = args.idx ? (size_t)args.idx[w] : args.pair_base + w;
 
     // ---- per-pair setup (every lane computes the same scalars) --------------------------------------------------
     const uint64_t a0 = args.a_off[pair], a1 = args.a_off[pair + 1];
@@ -66,11 +95,9 @@ __global__ void __launch_bounds__(128) lev_band_kernel(const BandArgs args) {
     const uint32_t mism = args.mism, gap = args.gap, sgap = args.sgap, tcost = args.tcost;
     const uint32_t diff = (uint32_t)(n - m);
 
-    // src/levenshtein.rs:400-426
-    uint32_t max_k = min((uint32_t)m * mism, ((uint32_t)m << 1) * gap + (m == 0 ? 0u : sgap + (n == m ? sgap : 0u)));
-    max_k = min(args.k, max_k + diff * gap + (n == m ? 0u : sgap));
-    const uint32_t unit_k = (max_k > sgap ? max_k - sgap : 0u) / gap;
-    if (diff > unit_k) {  // src/levenshtein.rs:428-430
+    const BandInfo bi = band_info(m, n, args.k, mism, gap, sgap, TRANS);
+    const uint32_t max_k = bi.max_k;
+    if (bi.none) {  // src/levenshtein.rs:428-430
         if (t == 0) args.out[pair] = TA_NONE;
         return;
     }
@@ -81,11 +108,7 @@ __global__ void __launch_bounds__(128) lev_band_kernel(const BandArgs args) {
         }
         return;
     }
-    // Ukkonen band; one extra diagonal each side when transpositions need the neighbours' match flags
-    const uint32_t spare = max_k >= 2 * sgap + diff * gap ? max_k - 2 * sgap - diff * gap : 0u;
-    const int e = (int)(spare / (2 * gap)) + (TRANS ? 1 : 0);
-    const int dlo = -e;
-    // host guarantees diff + 2e + 1 <= 2*G*C
+    const int dlo = bi.dlo;  // host guarantees bi.W <= 2*G*C
 
     // ---- stage both strings into shared memory (16-byte cp.async vectors on the aligned-down addresses) --------
     const uint8_t *sa, *sb;
@@ -137,6 +160,7 @@ __global__ void __launch_bounds__(128) lev_band_kernel(const BandArgs args) {
     // steps with s <= s_bnd may touch the first row / column and need the boundary override
     const int s_bnd = max(-dlo, dlo + 2 * G * C);
 
+    uint8_t *trow = TRACE ? args.trace + w * args.trace_stride + (size_t)t * C : nullptr;  // advances G*C per step
     auto step = [&](const int p, const bool boundary) {
         // p == 0: i advanced by one since the previous step; p == 1: j advanced by one
         uint32_t rH, rV;
@@ -189,10 +213,32 @@ __global__ void __launch_bounds__(128) lev_band_kernel(const BandArgs args) {
                 }
             }
             const uint32_t eq = ca[c] == cb[c];
-            uint32_t d = umin3(D2[c] + (eq ? 0u : mism), h, v);
-            if (TRANS) {
-                const uint32_t tr = D4[c] + tcost;
-                if (mL & mU) d = min(d, tr);
+            uint32_t d, arg = 0;
+            if (TRACE) {
+                // the scalar routine's decision order (src/levenshtein.rs:493-532): substitution, a-gap if <,
+                // b-gap if <, transposition if <=
+                d = D2[c] + (eq ? 0u : mism);
+                if (h < d) {
+                    d = h;
+                    arg = 1;
+                }
+                if (v < d) {
+                    d = v;
+                    arg = 2;
+                }
+                if (TRANS && (mL & mU)) {
+                    const uint32_t tr = D4[c] + tcost;
+                    if (tr <= d) {
+                        d = tr;
+                        arg = 3;
+                    }
+                }
+            } else {
+                d = umin3(D2[c] + (eq ? 0u : mism), h, v);
+                if (TRANS) {
+                    const uint32_t tr = D4[c] + tcost;
+                    if (mL & mU) d = min(d, tr);
+                }
             }
             uint32_t hh = h, vv = v;
             if (boundary) {
@@ -202,8 +248,10 @@ __global__ void __launch_bounds__(128) lev_band_kernel(const BandArgs args) {
                     const int q = bi ? j : i;
                     d = (uint32_t)q * gap + (q > 0 ? sgap : 0u);
                     hh = vv = TA_INF;
+                    arg = bi ? 1u : 2u;  // first row: a-gaps (:450-456); first column: b-gaps
                 }
             }
+            if (TRACE) trow[c] = (uint8_t)arg;
             nD[c] = d;
             if (AFFINE) {
                 nH[c] = min(d + open, hh + gap);
@@ -225,6 +273,7 @@ __global__ void __launch_bounds__(128) lev_band_kernel(const BandArgs args) {
             if (AFFINE) oH[c] = nH[c];
             oV[c] = nV[c];
         }
+        if (TRACE) trow += G * C;
     };
 
     // phase 1: anti-diagonals that can contain first-row / first-column cells
@@ -274,7 +323,7 @@ __global__ void __launch_bounds__(256) lev_wide_kernel(const WideArgs wa) {
     uint32_t *base = wa.workspace ? wa.workspace + (size_t)blockIdx.x * 10 * wa.wc : (uint32_t *)smem;
     const uint32_t wc = wa.wc;
     for (size_t w = blockIdx.x; w < args.n; w += gridDim.x) {
-        const size_t pair = args.idx ? (size_t)args.idx[w] : w;
+        const size_t pair = args.idx ? (size_t)args.idx[w] : args.pair_base + w;
         const uint64_t a0 = args.a_off[pair], a1 = args.a_off[pair + 1];
         const uint64_t b0 = args.b_off[pair], b1 = args.b_off[pair + 1];
         const bool swap = (a1 - a0) > (b1 - b0);
@@ -285,11 +334,10 @@ __global__ void __launch_bounds__(256) lev_wide_kernel(const WideArgs wa) {
         const uint32_t mism = args.mism, gap = args.gap, sgap = args.sgap, tcost = args.tcost;
         const uint32_t diff = (uint32_t)(n - m);
         const bool trans = tcost != 0;
-        uint32_t max_k = min((uint32_t)m * mism, ((uint32_t)m << 1) * gap + (m == 0 ? 0u : sgap + (n == m ? sgap : 0u)));
-        max_k = min(args.k, max_k + diff * gap + (n == m ? 0u : sgap));
-        const uint32_t unit_k = (max_k > sgap ? max_k - sgap : 0u) / gap;
+        const BandInfo bi = band_info(m, n, args.k, mism, gap, sgap, trans);
+        const uint32_t max_k = bi.max_k;
         __syncthreads();  // previous pair's buffers are no longer read
-        if (diff > unit_k) {
+        if (bi.none) {
             if (threadIdx.x == 0) args.out[pair] = TA_NONE;
             continue;
         }
@@ -300,10 +348,8 @@ __global__ void __launch_bounds__(256) lev_wide_kernel(const WideArgs wa) {
             }
             continue;
         }
-        const uint32_t spare = max_k >= 2 * sgap + diff * gap ? max_k - 2 * sgap - diff * gap : 0u;
-        const int e = (int)(spare / (2 * gap)) + (trans ? 1 : 0);
-        const int dlo = -e;
-        const int W = (int)diff + 2 * e + 1;
+        const int dlo = bi.dlo;
+        const int W = bi.W;
         const int cells = (W + 1) / 2 + 1;  // <= wc (host)
         uint32_t *D[4] = {base, base + wc, base + 2 * wc, base + 3 * wc};  // D[0] = s-1, D[1] = s-2, ...
         uint32_t *oH[2] = {base + 4 * wc, base + 5 * wc}, *oV[2] = {base + 6 * wc, base + 7 * wc};
@@ -394,7 +440,7 @@ int launch_wide(ta_ctx *ctx, const BandArgs &args, uint32_t W, cudaStream_t st) 
     return TA_OK;
 }
 
-template <int G, int C, bool AFFINE, bool TRANS>
+template <int G, int C, bool AFFINE, bool TRANS, bool TRACE = false>
 int launch_gc(ta_ctx *ctx, const BandArgs &args0, uint32_t max_len, cudaStream_t st) {
     BandArgs args = args0;
     constexpr int GROUPS = 128 / G;
@@ -403,13 +449,13 @@ int launch_gc(ta_ctx *ctx, const BandArgs &args0, uint32_t max_len, cudaStream_t
     const size_t smem = (size_t)GROUPS * 2 * slot;
     if (smem <= 96 * 1024) {
         args.slot = slot;
-        auto kern = lev_band_kernel<G, C, AFFINE, TRANS, true>;
+        auto kern = lev_band_kernel<G, C, AFFINE, TRANS, true, TRACE>;
         if (smem > 48 * 1024)
             TA_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<(unsigned)blocks, 128, smem, st>>>(args);
     } else {
         args.slot = 0;
-        lev_band_kernel<G, C, AFFINE, TRANS, false><<<(unsigned)blocks, 128, 0, st>>>(args);
+        lev_band_kernel<G, C, AFFINE, TRANS, false, TRACE><<<(unsigned)blocks, 128, 0, st>>>(args);
     }
     ctx->launches++;
     TA_CUDA(ctx, cudaGetLastError());
@@ -426,6 +472,99 @@ int launch_w(ta_ctx *ctx, const BandArgs &args, uint32_t W, uint32_t max_len, cu
     if (W <= 512) return launch_gc<32, 8, AFFINE, TRANS>(ctx, args, max_len, st);
     if (W <= 1024) return launch_gc<32, 16, AFFINE, TRANS>(ctx, args, max_len, st);
     return launch_wide(ctx, args, W, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Traceback walk (reference src/levenshtein.rs:547-606): one thread per pair follows the per-cell decisions stored
+// by the TRACE variant of lev_band_kernel from (m, n) back to (0, 0) and run-length encodes the edits.  Pass 1
+// (edits == nullptr) counts the runs, pass 2 writes them in forward order at edit_off[w].
+struct WalkArgs {
+    BandArgs b;
+    uint32_t wc;               // cells per anti-diagonal in the trace (G * C of the kernel that wrote it)
+    uint32_t *counts;          // [n] runs per work item
+    const uint64_t *edit_off;  // [n] first output slot per work item (pass 2)
+    ta_edit *edits;            // pass 2 output, or nullptr for pass 1
+};
+
+__global__ void __launch_bounds__(128) trace_walk_kernel(const WalkArgs wa) {
+    const BandArgs &args = wa.b;
+    const size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= args.n) return;
+    const size_t pair = args.idx ? (size_t)args.idx[w] : args.pair_base + w;
+    const uint64_t a0 = args.a_off[pair], a1 = args.a_off[pair + 1];
+    const uint64_t b0 = args.b_off[pair], b1 = args.b_off[pair + 1];
+    const bool swap = (a1 - a0) > (b1 - b0);
+    const uint8_t *sa = swap ? args.b + b0 : args.a + a0;
+    const uint8_t *sb = swap ? args.a + a0 : args.b + b0;
+    const int m = (int)(swap ? (b1 - b0) : (a1 - a0));
+    const int n = (int)(swap ? (a1 - a0) : (b1 - b0));
+    const bool writing = wa.edits != nullptr;
+    uint32_t runs = 0;
+    if (args.out[pair] != TA_NONE && (m > 0 || n > 0)) {
+        const uint32_t total = writing ? wa.counts[w] : 0u;
+        ta_edit *dst = writing ? wa.edits + wa.edit_off[w] : nullptr;
+        uint32_t cur = 0xffffffffu, cnt = 0;
+        auto push = [&](uint32_t e) {  // src/levenshtein.rs:598-602 (reversed order: the walk goes backwards)
+            if (e == cur) {
+                cnt++;
+                return;
+            }
+            if (cnt) {
+                if (writing) dst[total - 1 - runs] = ta_edit{cur, cnt};
+                runs++;
+            }
+            cur = e;
+            cnt = 1;
+        };
+        const uint32_t e_agap = swap ? 3u : 2u, e_bgap = swap ? 2u : 3u;  // AGap = 2, BGap = 3 (src/lib.rs:147-154)
+        if (m == 0) {
+            for (int j = n; j > 0; j--) push(e_agap);  // first row: every step is an a-gap (:450-456, 574-581)
+        } else {
+            const BandInfo bi = band_info(m, n, args.k, args.mism, args.gap, args.sgap, args.tcost != 0);
+            const int dlo = bi.dlo, s0 = -((-dlo) & 1);
+            const uint8_t *tr = args.trace + w * args.trace_stride;
+            int i = m, j = n;
+            while (i > 0 || j > 0) {
+                const int s = i + j, d = j - i;
+                const int p = (s - dlo) & 1;
+                const int ci = (d - dlo - p) >> 1;
+                const uint32_t arg = tr[(size_t)(s - s0) * wa.wc + ci];
+                if (arg == 0) {
+                    i--;
+                    j--;
+                    push(sa[i] == sb[j] ? 0u : 1u);  // Match / Mismatch
+                } else if (arg == 1) {
+                    j--;
+                    push(e_agap);
+                } else if (arg == 2) {
+                    i--;
+                    push(e_bgap);
+                } else {
+                    i -= 2;
+                    j -= 2;
+                    push(4u);  // Transpose
+                }
+            }
+        }
+        if (cnt) {
+            if (writing) dst[total - 1 - runs] = ta_edit{cur, cnt};
+            runs++;
+        }
+    }
+    if (!writing) wa.counts[w] = runs;
+}
+
+template <bool TRANS>
+int launch_trace_w(ta_ctx *ctx, const BandArgs &args, uint32_t W, uint32_t max_len, cudaStream_t st, uint32_t *wc) {
+    // affine formulas are valid for start_gap == 0 too: the TRACE variants are only instantiated with AFFINE = true
+    if (W <= 16) return *wc = 8, launch_gc<8, 1, true, TRANS, true>(ctx, args, max_len, st);
+    if (W <= 32) return *wc = 16, launch_gc<16, 1, true, TRANS, true>(ctx, args, max_len, st);
+    if (W <= 64) return *wc = 32, launch_gc<32, 1, true, TRANS, true>(ctx, args, max_len, st);
+    if (W <= 128) return *wc = 64, launch_gc<32, 2, true, TRANS, true>(ctx, args, max_len, st);
+    if (W <= 256) return *wc = 128, launch_gc<32, 4, true, TRANS, true>(ctx, args, max_len, st);
+    if (W <= 512) return *wc = 256, launch_gc<32, 8, true, TRANS, true>(ctx, args, max_len, st);
+    if (W <= 1024) return *wc = 512, launch_gc<32, 16, true, TRANS, true>(ctx, args, max_len, st);
+    return TA_ERR_TOO_LARGE;
 }
 
 }  // namespace
@@ -449,11 +588,61 @@ int ta_launch_lev_band(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, con
     BandArgs args;
     args.a = a, args.a_off = a_off, args.b = b, args.b_off = b_off, args.idx = idx, args.n = n, args.k = k;
     args.mism = costs.mismatch, args.gap = costs.gap, args.sgap = costs.start_gap, args.tcost = costs.transpose;
-    args.slot = 0, args.out = out;
+    args.slot = 0, args.out = out, args.trace = nullptr, args.trace_stride = 0, args.pair_base = 0;
     const uint32_t W = ta_band_width_bound(k, costs, max_len);
     const bool affine = costs.start_gap != 0, trans = costs.transpose != 0;
     if (affine && trans) return launch_w<true, true>(ctx, args, W, max_len, st);
     if (affine) return launch_w<true, false>(ctx, args, W, max_len, st);
     if (trans) return launch_w<false, true>(ctx, args, W, max_len, st);
     return launch_w<false, false>(ctx, args, W, max_len, st);
+}
+
+// cells per anti-diagonal (G * C) the trace kernel will use for band width W; 0 if the band is too wide
+uint32_t ta_trace_cells(uint32_t W) {
+    if (W <= 16) return 8;
+    if (W <= 32) return 16;
+    if (W <= 64) return 32;
+    if (W <= 128) return 64;
+    if (W <= 256) return 128;
+    if (W <= 512) return 256;
+    if (W <= 1024) return 512;
+    return 0;
+}
+
+// Distances + per-cell decisions for work items [0, n) (pairs pair_base + w, or idx[w]); trace needs
+// n * trace_stride bytes with trace_stride >= (2 * max_len + 3) * ta_trace_cells(W).
+int ta_launch_lev_band_trace(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b,
+                             const uint64_t *b_off, size_t n, const uint32_t *idx, size_t pair_base, uint32_t k,
+                             ta_costs costs, uint32_t max_len, uint32_t *out, uint8_t *trace, size_t trace_stride,
+                             cudaStream_t st) {
+    if (n == 0) return TA_OK;
+    BandArgs args;
+    args.a = a, args.a_off = a_off, args.b = b, args.b_off = b_off, args.idx = idx, args.pair_base = pair_base;
+    args.n = n, args.k = k;
+    args.mism = costs.mismatch, args.gap = costs.gap, args.sgap = costs.start_gap, args.tcost = costs.transpose;
+    args.slot = 0, args.out = out, args.trace = trace, args.trace_stride = trace_stride;
+    const uint32_t W = ta_band_width_bound(k, costs, max_len);
+    uint32_t wc = 0;
+    return costs.transpose ? launch_trace_w<true>(ctx, args, W, max_len, st, &wc)
+                           : launch_trace_w<false>(ctx, args, W, max_len, st, &wc);
+}
+
+// pass 1 (edits == nullptr): counts[w] = number of runs; pass 2: writes them at edits[edit_off[w] ..)
+int ta_launch_trace_walk(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b, const uint64_t *b_off,
+                         size_t n, const uint32_t *idx, size_t pair_base, uint32_t k, ta_costs costs, uint32_t max_len,
+                         const uint32_t *out, const uint8_t *trace, size_t trace_stride, uint32_t *counts,
+                         const uint64_t *edit_off, ta_edit *edits, cudaStream_t st) {
+    if (n == 0) return TA_OK;
+    WalkArgs wa;
+    wa.b.a = a, wa.b.a_off = a_off, wa.b.b = b, wa.b.b_off = b_off, wa.b.idx = idx, wa.b.pair_base = pair_base;
+    wa.b.n = n, wa.b.k = k;
+    wa.b.mism = costs.mismatch, wa.b.gap = costs.gap, wa.b.sgap = costs.start_gap, wa.b.tcost = costs.transpose;
+    wa.b.slot = 0, wa.b.out = const_cast<uint32_t *>(out), wa.b.trace = const_cast<uint8_t *>(trace);
+    wa.b.trace_stride = trace_stride;
+    wa.wc = ta_trace_cells(ta_band_width_bound(k, costs, max_len));
+    wa.counts = counts, wa.edit_off = edit_off, wa.edits = edits;
+    trace_walk_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(wa);
+    ctx->launches++;
+    TA_CUDA(ctx, cudaGetLastError());
+    return TA_OK;
 }

@@ -64,5 +64,16 @@ int ta_launch_lev(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const ui
                   size_t n, const uint32_t *idx, uint32_t k, ta_costs costs, uint32_t max_len, uint32_t *out,
                   cudaStream_t st);
 
+// Traceback (trace_on = true): TRACE variant of the banded kernel + walk kernels, lev_band.cu
+uint32_t ta_trace_cells(uint32_t W);
+int ta_launch_lev_band_trace(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b,
+                             const uint64_t *b_off, size_t n, const uint32_t *idx, size_t pair_base, uint32_t k,
+                             ta_costs costs, uint32_t max_len, uint32_t *out, uint8_t *trace, size_t trace_stride,
+                             cudaStream_t st);
+int ta_launch_trace_walk(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b, const uint64_t *b_off,
+                         size_t n, const uint32_t *idx, size_t pair_base, uint32_t k, ta_costs costs, uint32_t max_len,
+                         const uint32_t *out, const uint8_t *trace, size_t trace_stride, uint32_t *counts,
+                         const uint64_t *edit_off, ta_edit *edits, cudaStream_t st);
+
 // band width (number of diagonals) the general kernel needs in the worst case for (k, costs, max_len)
 uint32_t ta_band_width_bound(uint32_t k, ta_costs c, uint32_t max_len);
