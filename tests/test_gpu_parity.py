@@ -500,6 +500,59 @@ def test_traceback_longer_strings(eng):
                 assert dist[i] == want[0] and got == [tuple(e) for e in want[1]], (i, costs, k)
 
 
+def test_full_size_properties(eng):
+    """BASELINE.json sizes (1 M pairs, len 128, k = 8 and 16; 1 M x len 512 Damerau is covered by the bench's parity
+    check) through size-independent properties: symmetry, identity, the edit budget as an upper bound, monotonicity
+    in k, agreement between the two bit-parallel kernels' dispatch and the exponential search, plus an oracle check
+    of a 30 k sample."""
+    from triple_accel_b200 import synth
+    n = 1_000_000
+    a, ao, b, bo = synth.mutated_pairs(n, 128, 8, seed=77)
+    d8 = eng.levenshtein_k_batch(a, ao, b, bo, 8)
+    assert not (d8 == NONE).any() and d8.max() <= 8          # b = a after <= 8 edits
+    assert np.array_equal(d8, eng.levenshtein_k_batch(b, bo, a, ao, 8))  # symmetry
+    assert not eng.levenshtein_k_batch(a, ao, a, ao, 0).any()             # identity at k = 0
+    d16 = eng.levenshtein_k_batch(a, ao, b, bo, 16)
+    assert np.array_equal(d16, d8)                                        # monotone in k: same value once within k
+    d3 = eng.levenshtein_k_batch(a, ao, b, bo, 3)
+    assert np.array_equal(d3, np.where(d8 <= 3, d8, NONE).astype(np.uint32))
+    assert np.array_equal(eng.levenshtein_exp_batch(a, ao, b, bo), d8)
+    dd = eng.levenshtein_k_batch(a, ao, b, bo, 8, (1, 1, 0, 1))
+    assert (dd <= d8).all()                                               # transpositions can only help
+    sel = slice(123_000, 153_000)
+    sa, sao = a[int(ao[sel.start]):int(ao[sel.stop])], ao[sel.start:sel.stop + 1] - ao[sel.start]
+    sb, sbo = b[int(bo[sel.start]):int(bo[sel.stop])], bo[sel.start:sel.stop + 1] - bo[sel.start]
+    assert np.array_equal(d8[sel], orc.levenshtein_k_batch(sa, sao, sb, sbo, 8, threads=8))
+    assert np.array_equal(dd[sel], orc.levenshtein_k_batch(sa, sao, sb, sbo, 8, (1, 1, 0, 1), threads=8))
+    # Hamming at full size: equal-length pairs, hamming >= levenshtein, hamming(a, a) = 0
+    ha, hao, hb, hbo = synth.hamming_pairs(n, 128, seed=78)
+    h = eng.hamming_batch(ha, hao, hb, hbo)
+    assert h.max() <= 6 and not eng.hamming_batch(ha, hao, ha, hao).any()
+    assert (eng.levenshtein_k_batch(ha, hao, hb, hbo, 8) <= h).all()
+
+
+def test_full_size_search_properties(eng):
+    """cfg 4 at full size (100 k haystacks x 4096 B): All vs Best consistency and an oracle check on the haystacks
+    that report matches plus a random sample of silent ones."""
+    from triple_accel_b200 import synth
+    needle, hay, hoff = synth.needle_haystacks(100_000, 4096, 32, plant_frac=0.01, max_edits=3, seed=79)
+    m_all, o_all = eng.levenshtein_search_batch(needle, hay, hoff, 3, 0)
+    m_best, o_best = eng.levenshtein_search_batch(needle, hay, hoff, 3, 1)
+    cnt_all, cnt_best = np.diff(o_all.astype(np.int64)), np.diff(o_best.astype(np.int64))
+    assert ((cnt_all > 0) == (cnt_best > 0)).all() and (cnt_best <= cnt_all).all()
+    assert 900 <= (cnt_all > 0).sum() <= 1100   # ~1 % planted
+    assert (m_all[:, 2] <= 3).all() and (m_all[:, 0] <= m_all[:, 1]).all()
+    hit = np.nonzero(cnt_all > 0)[0]
+    rng = np.random.default_rng(1)
+    chk = np.concatenate([hit, rng.choice(100_000, 300, replace=False)])
+    for h in chk[:1500]:
+        hs = bytes(hay[int(hoff[h]):int(hoff[h + 1])])
+        for st, (mm, oo) in ((0, (m_all, o_all)), (1, (m_best, o_best))):
+            want = orc.levenshtein_search_naive_with_opts(bytes(needle), hs, 3, st)
+            got = [tuple(int(x) for x in r) for r in mm[int(oo[h]):int(oo[h + 1])]]
+            assert got == want, (h, st)
+
+
 LEV_TESTS = "test_lev_k_mutated or test_lev_k_random_short or test_nul_bytes or test_lev_exp"
 SEARCH_TESTS = ("test_search_random or test_search_planted or test_kat_search or "
                 "test_search_filter_long_needles_and_transpositions")
