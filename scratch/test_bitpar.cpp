@@ -34,7 +34,7 @@ int main(int argc, char** argv) {
             lb = s.size(); memcpy(b, s.data(), lb);
         }
         for (int trans = 0; trans < 2; trans++) {
-            uint32_t kmax = trans ? 29 : 31;
+            uint32_t kmax = trans ? 30 : 31;
             uint32_t k = rng() % (kmax + 1);
             orc_costs c = {1, 1, 0, (uint8_t)trans};
             uint32_t want = orc_levenshtein_naive_k_with_opts(a, la, b, lb, k, c, NULL, NULL);

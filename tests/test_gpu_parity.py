@@ -553,6 +553,22 @@ def test_full_size_search_properties(eng):
             assert got == want, (h, st)
 
 
+def test_cpp_header_mirror(tmp_path):
+    """include/triple_accel.hpp (the C++ host mirror of the crate's names) compiled against the shared library"""
+    import shutil
+    import subprocess
+    if not shutil.which("g++"):
+        pytest.skip("no g++ on this box")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "hpp_kat")
+    libdir = os.path.join(root, "triple_accel_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "tests", "cpp", "hpp_kat.cpp"), "-L", libdir, "-ltriple_accel_b200",
+                           "-Wl,-rpath," + libdir, "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "hpp ok" in r.stdout, r.stdout + r.stderr
+
+
 LEV_TESTS = "test_lev_k_mutated or test_lev_k_random_short or test_nul_bytes or test_lev_exp"
 SEARCH_TESTS = ("test_search_random or test_search_planted or test_kat_search or "
                 "test_search_filter_long_needles_and_transpositions")

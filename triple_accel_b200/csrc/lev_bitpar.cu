@@ -1,7 +1,7 @@
 // lev_bitpar.cu -- bit-parallel fast paths for unit costs (LEVENSHTEIN_COSTS / RDAMERAU_COSTS) on sm_100a.
 //
 //  * lev_bitpar32_tab_kernel / lev_bitpar32_kernel: k-bounded distance, one thread per pair, band of <= 32
-//    diagonals (k <= 31, or <= 29 with transpositions).  Algorithm and data movement are described in
+//    diagonals (k <= 31, or <= 30 with transpositions).  Algorithm and data movement are described in
 //    lev_bitpar_core.cuh (match-table variant = default; SWAR-compare variant = register-only alternative).  Same
 //    contract as the general kernel in lev_band.cu (reference src/levenshtein.rs:376-545); the dispatcher in api.cu
 //    picks these whenever the cost model is unit and the band fits.
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(128) lev_bitpar32_tab_kernel(const uint8_t *__
 bool ta_bitpar_can_handle(uint32_t k, ta_costs c, uint32_t max_len) {
     if (!(c.mismatch == 1 && c.gap == 1 && c.start_gap == 0 && c.transpose <= 1)) return false;
     const uint32_t kk = k < max_len ? k : max_len;  // max_k = min(k, n) for unit costs
-    return kk <= (c.transpose ? 29u : 31u);
+    return kk <= (c.transpose ? 30u : 31u);  // band (+ transposition margin) <= 32 rows, see lev_bitpar_core.cuh
 }
 
 int ta_launch_lev_bitpar(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b,

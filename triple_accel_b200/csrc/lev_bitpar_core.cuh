@@ -120,12 +120,15 @@ TA_HD uint32_t eq_flags(uint32_t r, uint32_t bb) {
 }
 
 // Distance of one pair, `a` being the shorter string (m <= n), unit costs.  Requires m >= 1 and
-// diff + 2e + 1 <= 32 with e = (max_k - diff)/2 (+1 if TRANS).  Returns the exact distance whenever it is
+// diff + 2e + 1 <= 32 with e = (max_k - diff)/2 (+1 if TRANS and max_k - diff is odd).  Returns the exact distance whenever it is
 // <= max_k (and some value > max_k otherwise).
 template <bool TRANS>
 TA_HD uint32_t distance32(const uint8_t *a, int m, const uint8_t *b, int n, uint32_t max_k) {
     const int diff = n - m;
-    const int e = (int)((max_k - (uint32_t)diff) >> 1) + (TRANS ? 1 : 0);
+    // one margin diagonal each side so that the transposition test can see its neighbours' match flags -- only needed
+    // when max_k - diff is odd: with an even budget the gaps needed to reach an extreme diagonal and come back use
+    // all of max_k, so no transposition can lie on it
+    const int e = (int)((max_k - (uint32_t)diff) >> 1) + ((TRANS && ((max_k - (uint32_t)diff) & 1u)) ? 1 : 0);
     const int dhi = diff + e;  // window row p of column j is matrix row i = j - dhi + p
 
     Stream sa, sb;
@@ -231,7 +234,10 @@ TA_HD uint32_t distance32_tab(const uint8_t *a, int m, const uint8_t *b, int n, 
                               const uint32_t pitch_log2) {
     constexpr uint32_t CMASK = PLANES == 1 ? 0x7f7f7f7fu : 0x3f3f3f3fu;
     const int diff = n - m;
-    const int e = (int)((max_k - (uint32_t)diff) >> 1) + (TRANS ? 1 : 0);
+    // one margin diagonal each side so that the transposition test can see its neighbours' match flags -- only needed
+    // when max_k - diff is odd: with an even budget the gaps needed to reach an extreme diagonal and come back use
+    // all of max_k, so no transposition can lie on it
+    const int e = (int)((max_k - (uint32_t)diff) >> 1) + ((TRANS && ((max_k - (uint32_t)diff) & 1u)) ? 1 : 0);
     const int dhi = diff + e;  // window row p of column j is matrix row i = j - dhi + p
 
     Stream sa, sb;
