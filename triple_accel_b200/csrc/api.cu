@@ -98,10 +98,8 @@ int ta_init(int device, ta_ctx **out) {
     ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "stream");
     if ((e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "stream");
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < ta_ctx::MAX_CHUNKS; i++)
         if ((e = cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming)) != cudaSuccess) return fail(e, "event");
-        if ((e = cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming)) != cudaSuccess) return fail(e, "event");
-    }
     if ((e = cudaMalloc((void **)&ctx->d_flags, 64 * sizeof(uint32_t))) != cudaSuccess) return fail(e, "cudaMalloc");
     if ((e = cudaMemset(ctx->d_flags, 0, 64 * sizeof(uint32_t))) != cudaSuccess) return fail(e, "cudaMemset");
     if ((e = cudaMallocHost((void **)&ctx->h_flags, 64 * sizeof(uint32_t))) != cudaSuccess) return fail(e, "cudaMallocHost");
@@ -123,10 +121,8 @@ void ta_shutdown(ta_ctx *ctx) {
         if (b.p) cudaFreeHost(b.p);
     if (ctx->d_flags) cudaFree(ctx->d_flags);
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < ta_ctx::MAX_CHUNKS; i++)
         if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
-        if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
-    }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     delete ctx;
@@ -184,19 +180,19 @@ struct BatchStats {
 
 // validates monotone offsets, computes totals; returns TA_OK or an error
 int scan_offsets(const uint64_t *a_off, const uint64_t *b_off, size_t n, bool need_equal, BatchStats &st) {
-    uint64_t max_len = 0;
-    bool mismatch = false;
-    for (size_t i = 0; i < n; i++) {
-        if (a_off[i + 1] < a_off[i] || b_off[i + 1] < b_off[i]) return TA_ERR_BAD_ARG;
+    uint64_t max_len = 0, bad = 0, mismatch = 0;
+    for (size_t i = 0; i < n; i++) {  // branch-free so that it vectorises
         const uint64_t la = a_off[i + 1] - a_off[i], lb = b_off[i + 1] - b_off[i];
+        bad |= (uint64_t)(a_off[i + 1] < a_off[i]) | (uint64_t)(b_off[i + 1] < b_off[i]);
         max_len = std::max(max_len, std::max(la, lb));
-        mismatch |= la != lb;
+        mismatch |= la ^ lb;
     }
+    if (bad) return TA_ERR_BAD_ARG;
     if (max_len > TA_MAX_STRING_LEN) return TA_ERR_TOO_LARGE;
     st.a_bytes = a_off[n] - a_off[0];
     st.b_bytes = b_off[n] - b_off[0];
     st.max_len = (uint32_t)max_len;
-    if (need_equal && mismatch) return TA_ERR_LEN_MISMATCH;
+    if (need_equal && mismatch != 0) return TA_ERR_LEN_MISMATCH;
     return TA_OK;
 }
 
@@ -275,36 +271,83 @@ int run_pairs(ta_ctx *ctx, Op op, const uint8_t *a, const uint64_t *a_off, const
     if (n > 0xFFFFFFF0ull) return TA_ERR_TOO_LARGE;
     std::lock_guard<std::mutex> lock(ctx->mu);
     TA_CUDA(ctx, cudaSetDevice(ctx->device));
-    BatchStats bs;
-    int rc = scan_offsets(a_off, b_off, n, op == OP_HAMMING, bs);
-    if (rc != TA_OK) return rc;
-    if ((bs.a_bytes && !a) || (bs.b_bytes && !b)) return TA_ERR_BAD_ARG;
-    cudaStream_t st = ctx->stream;
-    const uint8_t *da, *db;
-    const uint64_t *da_off, *db_off;
-    if ((rc = upload_side(ctx, 0, true, a, a_off, n, &da, &da_off, st)) != TA_OK) return rc;
-    if ((rc = upload_side(ctx, 0, false, b, b_off, n, &db, &db_off, st)) != TA_OK) return rc;
+    // Pipeline: the batch is cut into up to MAX_CHUNKS ranges of pairs.  All H2D copies are queued on the copy stream
+    // first (a range only needs its first and last offsets), the offsets are validated on the host while the DMA
+    // engine is busy, then each range's kernel + D2H is queued on the compute stream behind that range's copy event,
+    // so kernels overlap the copies of later ranges.  A contract violation found by the validation drains the
+    // streams and returns the error.
+    if (a_off[n] < a_off[0] || b_off[n] < b_off[0]) return TA_ERR_BAD_ARG;
+    if ((a_off[n] > a_off[0] && !a) || (b_off[n] > b_off[0] && !b)) return TA_ERR_BAD_ARG;
+    int rc;
+    cudaStream_t st = ctx->stream, cp = ctx->stream2;
+    const uint64_t a_lo = a_off[0], b_lo = b_off[0];
+    const uint64_t a_bytes = a_off[n] - a_lo, b_bytes = b_off[n] - b_lo;
+    const size_t a_skew = (size_t)(a_lo & 15), b_skew = (size_t)(b_lo & 15);  // keep 16-byte alignment classes
+    if ((rc = ta_dev_reserve(ctx, ctx->d_a[0], a_skew + a_bytes + 64)) != TA_OK) return rc;
+    if ((rc = ta_dev_reserve(ctx, ctx->d_b[0], b_skew + b_bytes + 64)) != TA_OK) return rc;
+    if ((rc = ta_dev_reserve(ctx, ctx->d_aoff[0], (n + 1) * sizeof(uint64_t))) != TA_OK) return rc;
+    if ((rc = ta_dev_reserve(ctx, ctx->d_boff[0], (n + 1) * sizeof(uint64_t))) != TA_OK) return rc;
     if ((rc = ta_dev_reserve(ctx, ctx->d_out[0], n * sizeof(uint32_t))) != TA_OK) return rc;
+    uint8_t *buf_a = (uint8_t *)ctx->d_a[0].p + a_skew, *buf_b = (uint8_t *)ctx->d_b[0].p + b_skew;
+    const uint8_t *da = buf_a - a_lo, *db = buf_b - b_lo;  // virtual bases: + off[i] lands inside the buffers
+    uint64_t *da_off = (uint64_t *)ctx->d_aoff[0].p, *db_off = (uint64_t *)ctx->d_boff[0].p;
     uint32_t *d_out = (uint32_t *)ctx->d_out[0].p;
-    switch (op) {
-        case OP_HAMMING: {
-            const uint32_t avg = (uint32_t)std::min<uint64_t>(bs.a_bytes / n, 0xFFFFFFFFull);
-            TA_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, sizeof(uint32_t), st));
-            rc = ta_launch_hamming(ctx, da, da_off, db, db_off, n, avg, d_out, ctx->d_flags, st);
-            break;
+
+    const int chunks = (int)std::max<uint64_t>(1, std::min<uint64_t>({(uint64_t)ta_ctx::MAX_CHUNKS, (uint64_t)n,
+                                                                      (a_bytes + b_bytes) >> 24}));  // >= 16 MB each
+    size_t bound[ta_ctx::MAX_CHUNKS + 1];
+    for (int c = 0; c <= chunks; c++) bound[c] = n * (size_t)c / chunks;
+    TA_CUDA(ctx, cudaEventRecord(ctx->ev_h2d[0], st));  // the copy stream must not overwrite buffers still in use
+    TA_CUDA(ctx, cudaStreamWaitEvent(cp, ctx->ev_h2d[0], 0));
+    for (int c = 0; c < chunks; c++) {
+        const size_t lo = bound[c], hi = bound[c + 1];
+        if (a_off[hi] < a_off[lo] || b_off[hi] < b_off[lo] || a_off[lo] < a_lo || b_off[lo] < b_lo ||
+            a_off[hi] > a_off[n] || b_off[hi] > b_off[n]) {
+            cudaStreamSynchronize(cp);
+            return TA_ERR_BAD_ARG;
         }
-        case OP_LEV_K:
-            rc = ta_launch_lev(ctx, da, da_off, db, db_off, n, nullptr, k, costs, bs.max_len, d_out, st);
-            break;
-        case OP_LEV_EXP:
-            rc = exp_rounds_dev(ctx, da, da_off, db, db_off, n, costs, bs.max_len, d_out, st);
-            break;
+        if (a_off[hi] > a_off[lo])
+            TA_CUDA(ctx, cudaMemcpyAsync(buf_a + (a_off[lo] - a_lo), a + a_off[lo], a_off[hi] - a_off[lo],
+                                         cudaMemcpyHostToDevice, cp));
+        if (b_off[hi] > b_off[lo])
+            TA_CUDA(ctx, cudaMemcpyAsync(buf_b + (b_off[lo] - b_lo), b + b_off[lo], b_off[hi] - b_off[lo],
+                                         cudaMemcpyHostToDevice, cp));
+        TA_CUDA(ctx, cudaMemcpyAsync(da_off + lo, a_off + lo, (hi - lo + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, cp));
+        TA_CUDA(ctx, cudaMemcpyAsync(db_off + lo, b_off + lo, (hi - lo + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, cp));
+        TA_CUDA(ctx, cudaEventRecord(ctx->ev_h2d[c], cp));
+    }
+    BatchStats bs;
+    rc = scan_offsets(a_off, b_off, n, op == OP_HAMMING, bs);
+    if (rc != TA_OK) {
+        cudaStreamSynchronize(cp);
+        return rc;
+    }
+    if (op == OP_HAMMING) TA_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, sizeof(uint32_t), st));
+    for (int c = 0; c < chunks && rc == TA_OK; c++) {
+        const size_t lo = bound[c], cn = bound[c + 1] - bound[c];
+        TA_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_h2d[c], 0));
+        if (cn == 0) continue;
+        switch (op) {
+            case OP_HAMMING: {
+                const uint32_t avg = (uint32_t)std::min<uint64_t>(bs.a_bytes / n, 0xFFFFFFFFull);
+                rc = ta_launch_hamming(ctx, da, da_off + lo, db, db_off + lo, cn, avg, d_out + lo, ctx->d_flags, st);
+                break;
+            }
+            case OP_LEV_K:
+                rc = ta_launch_lev(ctx, da, da_off + lo, db, db_off + lo, cn, nullptr, k, costs, bs.max_len, d_out + lo, st);
+                break;
+            case OP_LEV_EXP:
+                rc = exp_rounds_dev(ctx, da, da_off + lo, db, db_off + lo, cn, costs, bs.max_len, d_out + lo, st);
+                break;
+        }
+        if (rc == TA_OK)
+            TA_CUDA(ctx, cudaMemcpyAsync(out + lo, d_out + lo, cn * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     }
     if (rc != TA_OK) {
+        cudaStreamSynchronize(cp);
         cudaStreamSynchronize(st);
         return rc;
     }
-    TA_CUDA(ctx, cudaMemcpyAsync(out, d_out, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     TA_CUDA(ctx, cudaStreamSynchronize(st));
     return TA_OK;
 }

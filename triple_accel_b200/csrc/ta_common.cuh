@@ -23,8 +23,8 @@ struct ta_ctx {
     std::mutex mu;
     cudaStream_t stream = nullptr;   // compute + D2H
     cudaStream_t stream2 = nullptr;  // H2D of the next chunk
-    cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
-    cudaEvent_t ev_done[2] = {nullptr, nullptr};
+    static constexpr int MAX_CHUNKS = 8;
+    cudaEvent_t ev_h2d[MAX_CHUNKS] = {};  // "chunk c is in device memory"
     DevBuf d_a[2], d_b[2], d_aoff[2], d_boff[2], d_out[2], d_work[4];
     DevBuf h_pin[4];         // pinned staging for pageable inputs / outputs
     uint32_t *d_flags = nullptr;  // [0] = deferred error code of *_dev kernels, [1..] scratch counters
