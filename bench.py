@@ -152,7 +152,11 @@ def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = min(n, args.cpu_sample if op != "search" else max(1, args.cpu_sample // 100))
+    # the reference arm works on a larger bounded sample than the in-line cpu_baseline (it has the run to itself)
+    ref_sample = max(args.cpu_sample, 1_000_000)
+    sample = min(n, ref_sample if op != "search" else max(1, ref_sample // 100))
+    if op == "exp":
+        sample = min(sample, 100_000)
     a, ao, b, bo = make_inputs(op, sample, length, k, costs, 1234)
     threads = orc.max_threads()
 
