@@ -23,7 +23,7 @@ int main(int argc, char** argv) {
         if (mode == 0) { lb = rng() % (it % 7 == 0 ? 200 : 40); for (int i = 0; i < lb; i++) b[i] = rng() % alpha; }
         else { // mutate
             std::vector<uint8_t> s(a, a + la);
-            int ne = rng() % 12;
+            int ne = rng() % (it % 5 == 0 ? 70 : 12);
             for (int e = 0; e < ne; e++) {
                 int kind = rng() % 4;
                 if (kind == 0 && !s.empty()) s[rng() % s.size()] = rng() % alpha;
@@ -39,7 +39,11 @@ int main(int argc, char** argv) {
             orc_costs c = {1, 1, 0, (uint8_t)trans};
             uint32_t want = orc_levenshtein_naive_k_with_opts(a, la, b, lb, k, c, NULL, NULL);
             static uint32_t tab[128];
-            uint32_t got2 = (it & 1) ? (trans ? bitpar::pair_unit_costs_tab<true,1>(a, la, b, lb, k, (uint8_t*)tab, 2) : bitpar::pair_unit_costs_tab<false,1>(a, la, b, lb, k, (uint8_t*)tab, 2)) : (trans ? bitpar::pair_unit_costs_tab<true,2>(a, la, b, lb, k, (uint8_t*)tab, 2) : bitpar::pair_unit_costs_tab<false,2>(a, la, b, lb, k, (uint8_t*)tab, 2));
+            uint32_t got2 = (it & 1) ? (trans ? bitpar::pair_unit_costs_tab<true,1,uint32_t>(a, la, b, lb, k, (uint8_t*)tab, 2) : bitpar::pair_unit_costs_tab<false,1,uint32_t>(a, la, b, lb, k, (uint8_t*)tab, 2)) : (trans ? bitpar::pair_unit_costs_tab<true,2,uint32_t>(a, la, b, lb, k, (uint8_t*)tab, 2) : bitpar::pair_unit_costs_tab<false,2,uint32_t>(a, la, b, lb, k, (uint8_t*)tab, 2));
+            { static uint64_t tab64[64]; uint32_t k64 = rng() % (trans ? 63 : 64); uint32_t want64 = orc_levenshtein_naive_k_with_opts(a, la, b, lb, k64, c, NULL, NULL);
+              uint32_t got64 = trans ? bitpar::pair_unit_costs_tab<true,2,uint64_t>(a, la, b, lb, k64, (uint8_t*)tab64, 3) : bitpar::pair_unit_costs_tab<false,2,uint64_t>(a, la, b, lb, k64, (uint8_t*)tab64, 3);
+              for (int q = 0; q < 64; q++) if (tab64[q]) { printf("table64 not clean\n"); bad++; tab64[q] = 0; }
+              if (got64 != want64) { if (bad++ < 10) printf("TAB64 MISMATCH trans=%d k=%u la=%d lb=%d want=%u got=%u\n", trans, k64, la, lb, want64, got64); } }
             for (int q = 0; q < 128; q++) if (tab[q]) { printf("table not clean\n"); bad++; tab[q] = 0; }
             if (got2 != want) { if (bad++ < 10) printf("TAB MISMATCH trans=%d k=%u la=%d lb=%d want=%u got=%u\n", trans, k, la, lb, want, got2); }
             uint32_t got = trans ? bitpar::pair_unit_costs<true>(a, la, b, lb, k) : bitpar::pair_unit_costs<false>(a, la, b, lb, k);

@@ -250,7 +250,7 @@ def test_lev_k_random_short(eng, costs):
 
 
 @pytest.mark.parametrize("length,k", [(128, 8), (128, 16), (512, 16), (300, 30), (1024, 30), (100, 64), (77, 200),
-                                      (2000, 5)])
+                                      (2000, 5), (300, 45), (1024, 63), (600, 62), (200, 32)])
 @pytest.mark.parametrize("costs", [(1, 1, 0, 0), (1, 1, 0, 1), (2, 1, 3, 0), (2, 2, 1, 3)], ids=str)
 def test_lev_k_mutated(eng, length, k, costs):
     """the BASELINE shapes at reduced batch size: mutated pairs (within k) and unrelated pairs (None)"""

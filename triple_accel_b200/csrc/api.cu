@@ -26,7 +26,7 @@ int ta_launch_lev(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const ui
                   cudaStream_t st) {
     static const bool force_band = getenv("TA_FORCE_BAND") != nullptr;  // testing: exercise the general kernel
     if (!force_band && ta_bitpar_can_handle(k, costs, max_len))
-        return ta_launch_lev_bitpar(ctx, a, a_off, b, b_off, n, idx, k, costs, out, st);
+        return ta_launch_lev_bitpar(ctx, a, a_off, b, b_off, n, idx, k, costs, max_len, out, st);
     return ta_launch_lev_band(ctx, a, a_off, b, b_off, n, idx, k, costs, max_len, out, st);
 }
 

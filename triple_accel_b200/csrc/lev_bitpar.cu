@@ -1,7 +1,7 @@
 // lev_bitpar.cu -- bit-parallel fast paths for unit costs (LEVENSHTEIN_COSTS / RDAMERAU_COSTS) on sm_100a.
 //
-//  * lev_bitpar32_tab_kernel / lev_bitpar32_kernel: k-bounded distance, one thread per pair, band of <= 32
-//    diagonals (k <= 31, or <= 30 with transpositions).  Algorithm and data movement are described in
+//  * lev_bitpar_tab_kernel<TRANS, PLANES, W> / lev_bitpar32_kernel: k-bounded distance, one thread per pair, band of <= 32
+//    diagonals with the 32-bit window (k <= 31, or <= 30 with transpositions) and <= 64 with the 64-bit window.  Algorithm and data movement are described in
 //    lev_bitpar_core.cuh (match-table variant = default; SWAR-compare variant = register-only alternative).  Same
 //    contract as the general kernel in lev_band.cu (reference src/levenshtein.rs:376-545); the dispatcher in api.cu
 //    picks these whenever the cost model is unit and the band fits.
@@ -32,25 +32,26 @@ __global__ void __launch_bounds__(128) lev_bitpar32_kernel(const uint8_t *__rest
 
 // Table variant (lev_bitpar_core.cuh: distance32_tab): persistent threads, each with a private 128-entry column of
 // the block's shared-memory match table (layout [entry][thread]: bank = thread, conflict-free for any bytes).
-template <bool TRANS, int PLANES>
-__global__ void __launch_bounds__(128) lev_bitpar32_tab_kernel(const uint8_t *__restrict__ a,
+template <bool TRANS, int PLANES, typename W>
+__global__ void __launch_bounds__(128) lev_bitpar_tab_kernel(const uint8_t *__restrict__ a,
                                                                const uint64_t *__restrict__ a_off,
                                                                const uint8_t *__restrict__ b,
                                                                const uint64_t *__restrict__ b_off,
                                                                const uint32_t *__restrict__ idx, size_t n, uint32_t k,
                                                                uint32_t *__restrict__ out) {
-    extern __shared__ uint32_t tabs[];
+    extern __shared__ __align__(16) uint8_t tabs_raw[];
+    W *tabs = (W *)tabs_raw;
     const uint32_t nt = blockDim.x;
     for (uint32_t q = threadIdx.x; q < (128u >> (PLANES - 1)) * nt; q += nt) tabs[q] = 0;
     __syncthreads();
     uint8_t *tab = (uint8_t *)(tabs + threadIdx.x);
-    const uint32_t pitch_log2 = 31u - (uint32_t)__clz((int)(nt * 4u));  // blockDim is a power of two
+    const uint32_t pitch_log2 = 31u - (uint32_t)__clz((int)(nt * (uint32_t)sizeof(W)));  // blockDim is a power of two
     const size_t total = (size_t)gridDim.x * nt;
     for (size_t w = (size_t)blockIdx.x * nt + threadIdx.x; w < n; w += total) {
         const size_t pair = idx ? (size_t)idx[w] : w;
         const uint64_t a0 = a_off[pair], a1 = a_off[pair + 1];
         const uint64_t b0 = b_off[pair], b1 = b_off[pair + 1];
-        out[pair] = bitpar::pair_unit_costs_tab<TRANS, PLANES>(a + a0, a1 - a0, b + b0, b1 - b0, k, tab, pitch_log2);
+        out[pair] = bitpar::pair_unit_costs_tab<TRANS, PLANES, W>(a + a0, a1 - a0, b + b0, b1 - b0, k, tab, pitch_log2);
     }
 }
 
@@ -59,25 +60,38 @@ __global__ void __launch_bounds__(128) lev_bitpar32_tab_kernel(const uint8_t *__
 bool ta_bitpar_can_handle(uint32_t k, ta_costs c, uint32_t max_len) {
     if (!(c.mismatch == 1 && c.gap == 1 && c.start_gap == 0 && c.transpose <= 1)) return false;
     const uint32_t kk = k < max_len ? k : max_len;  // max_k = min(k, n) for unit costs
-    return kk <= (c.transpose ? 30u : 31u);  // band (+ transposition margin) <= 32 rows, see lev_bitpar_core.cuh
+    return kk <= (c.transpose ? 62u : 63u);  // band (+ transposition margin) <= 64 rows, see lev_bitpar_core.cuh
+}
+static bool fits32(uint32_t k, ta_costs c, uint32_t max_len) {
+    const uint32_t kk = k < max_len ? k : max_len;
+    return kk <= (c.transpose ? 30u : 31u);
 }
 
 int ta_launch_lev_bitpar(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b,
                          const uint64_t *b_off, size_t n, const uint32_t *idx, uint32_t k, ta_costs costs,
-                         uint32_t *out, cudaStream_t st) {
+                         uint32_t max_len, uint32_t *out, cudaStream_t st) {
     if (n == 0) return TA_OK;
-    // two implementations of the same per-pair contract: the match-table kernel (default, ~1.25x faster) and the
-    // register-only SWAR-compare kernel; TA_BITPAR=simd|tab forces one (tests pin both to the oracle)
+    // Implementations of the same per-pair contract: the match-table kernel (default; 32-row window, or 64-row window
+    // for 32 <= k <= 63) and the register-only SWAR-compare kernel (32 rows).  TA_BITPAR=simd|tab, TA_BITPAR_PLANES and
+    // TA_BITPAR_THREADS force variants (the tests pin every one of them to the oracle).
     static const char *variant = getenv("TA_BITPAR");
-    static const int tab_threads = getenv("TA_BITPAR_THREADS") ? atoi(getenv("TA_BITPAR_THREADS")) : 128;
-    if (!(variant && variant[0] == 's')) {
-        const int nt = tab_threads;
-        static const int planes = getenv("TA_BITPAR_PLANES") ? atoi(getenv("TA_BITPAR_PLANES")) : 1;
-        const size_t smem = (size_t)(planes == 2 ? 64 : 128) * nt * sizeof(uint32_t);
+    static const int env_threads = getenv("TA_BITPAR_THREADS") ? atoi(getenv("TA_BITPAR_THREADS")) : 0;
+    static const int env_planes = getenv("TA_BITPAR_PLANES") ? atoi(getenv("TA_BITPAR_PLANES")) : 0;
+    const bool wide = !fits32(k, costs, max_len);
+    if (wide || !(variant && variant[0] == 's')) {
+        const int planes = wide ? 2 : (env_planes == 2 ? 2 : 1);
+        const int nt = env_threads ? env_threads : (wide ? 64 : 128);
+        const size_t smem = (size_t)(planes == 2 ? 64 : 128) * nt * (wide ? 8 : 4);
         const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(32, (size_t)(ctx->smem_optin + 1024) / (smem + 1024)));
         const unsigned blocks = (unsigned)std::min<size_t>((n + nt - 1) / nt, (size_t)ctx->sm_count * per_sm);
-        auto kern = planes == 2 ? (costs.transpose ? lev_bitpar32_tab_kernel<true, 2> : lev_bitpar32_tab_kernel<false, 2>)
-                                : (costs.transpose ? lev_bitpar32_tab_kernel<true, 1> : lev_bitpar32_tab_kernel<false, 1>);
+        void (*kern)(const uint8_t *, const uint64_t *, const uint8_t *, const uint64_t *, const uint32_t *, size_t,
+                     uint32_t, uint32_t *);
+        if (wide)
+            kern = costs.transpose ? lev_bitpar_tab_kernel<true, 2, uint64_t> : lev_bitpar_tab_kernel<false, 2, uint64_t>;
+        else if (planes == 2)
+            kern = costs.transpose ? lev_bitpar_tab_kernel<true, 2, uint32_t> : lev_bitpar_tab_kernel<false, 2, uint32_t>;
+        else
+            kern = costs.transpose ? lev_bitpar_tab_kernel<true, 1, uint32_t> : lev_bitpar_tab_kernel<false, 1, uint32_t>;
         TA_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<blocks, nt, smem, st>>>(a, a_off, b, b_off, idx, n, k, out);
         ctx->launches++;

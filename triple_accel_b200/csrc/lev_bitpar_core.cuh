@@ -204,14 +204,14 @@ TA_HD uint32_t distance32(const uint8_t *a, int m, const uint8_t *b, int n, uint
 // clears the bit of the byte that leaves and sets the same bit position for the byte that enters (two read-modify-
 // writes), so a column costs  Eq = rotr(tab[b & 0x7f] & ~(A7 ^ topmask(b)), u mod 32)  -- one LDS, one LOP3, one
 // funnel shift -- instead of 8 SWAR compares.  The table must be all-zero on entry and is left all-zero on exit.
-// `tab` points at this thread's entry 0; entry c lives `c << pitch_log2` BYTES further (pitch = 4 * threads).
-TA_HD uint32_t &tab_at(uint8_t *tab, uint32_t c, uint32_t pitch_log2) {
-    return *(uint32_t *)(tab + ((size_t)c << pitch_log2));
+// `tab` points at this thread's entry 0; entry c lives `c << pitch_log2` BYTES further (pitch = sizeof(W) * threads).
+template <typename W>
+TA_HD W &tab_at(uint8_t *tab, uint32_t c, uint32_t pitch_log2) {
+    return *(W *)(tab + ((size_t)c << pitch_log2));
 }
 TA_HD uint32_t byte_of(uint32_t w, int t) {  // byte t of w, zero-extended (one PRMT)
     return prmt(w, 0u, 0x4440u | (uint32_t)t);
 }
-
 // gathers bit `bitpos` of each of the 16 bytes of w[0..3] into a 16-bit word (byte t of w[i] -> bit 4i + t)
 TA_HD uint32_t gather_bits16(const uint32_t w[4], int bitpos) {
     uint32_t r = 0;
@@ -223,15 +223,39 @@ TA_HD uint32_t gather_bits16(const uint32_t w[4], int bitpos) {
     return r;
 }
 // all-ones iff bit `bitpos` of byte t of w is set
-TA_HD uint32_t bit_mask_of(uint32_t w, int t, int bitpos) {
-    return (uint32_t)((int32_t)(w << (31 - 8 * t - bitpos)) >> 31);
+template <typename W>
+TA_HD W bit_mask_of(uint32_t w, int t, int bitpos) {
+    return (W)(int64_t)((int32_t)(w << (31 - 8 * t - bitpos)) >> 31);
+}
+template <typename W>
+TA_HD W rotr(W x, uint32_t s) {  // s in [0, bits)
+    if (sizeof(W) == 4) return (W)funnel_r((uint32_t)x, (uint32_t)x, s);
+    return s ? (W)((x >> s) | (x << (8 * sizeof(W) - s))) : x;
+}
+TA_HD uint32_t popc_w(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__popc(x);
+#else
+    return (uint32_t)__builtin_popcount(x);
+#endif
 }
 
-// PLANES = 1: 128 table entries (7-bit classes) + the A7 plane; PLANES = 2: 64 entries (6-bit classes) + A6, A7
-// planes -- half the shared memory per thread, twice the resident warps, two more ALU ops per column.
-template <bool TRANS, int PLANES>
-TA_HD uint32_t distance32_tab(const uint8_t *a, int m, const uint8_t *b, int n, uint32_t max_k, uint8_t *tab,
-                              const uint32_t pitch_log2) {
+// ---------------------------------------------------------------------------------------------------------------
+// distance_tab: same recurrence as distance32, but Eq comes from a per-thread match table instead of SIMD compares.
+//
+// tab[c] (c = the byte's low class bits; thread-private column of a shared-memory array) has bit (t mod BITS) set
+// iff pattern-stream byte t is inside the current BITS-row window and its class is c; the bytes' remaining top
+// bits live in register planes with the same circular bit numbering.  Sliding the window clears the bit of the
+// byte that leaves and sets the same bit position for the byte that enters (two read-modify-writes), so a column
+// costs  Eq = rotr(tab[class(b)] & ~miss, u mod BITS)  -- one LDS, two or three LOP3, one rotate -- instead of 8
+// SWAR compares.  The table must be all-zero on entry and is left all-zero on exit.
+//   W = uint32_t: 32-row window (k <= 31; <= 30 with transpositions);  W = uint64_t: 64-row window (k <= 63 / 62).
+//   PLANES = 1: 128 entries (7-bit classes) + the A7 plane;  PLANES = 2: 64 entries (6-bit classes) + A6, A7.
+template <bool TRANS, int PLANES, typename W>
+TA_HD uint32_t distance_tab(const uint8_t *a, int m, const uint8_t *b, int n, uint32_t max_k, uint8_t *tab,
+                            const uint32_t pitch_log2) {
+    constexpr int BITS = 8 * (int)sizeof(W);
+    constexpr int RING = BITS / 4;  // words holding the window's bytes
     constexpr uint32_t CMASK = PLANES == 1 ? 0x7f7f7f7fu : 0x3f3f3f3fu;
     const int diff = n - m;
     // one margin diagonal each side so that the transposition test can see its neighbours' match flags -- only needed
@@ -244,89 +268,87 @@ TA_HD uint32_t distance32_tab(const uint8_t *a, int m, const uint8_t *b, int n, 
     sa.init((intptr_t)a - dhi, (uintptr_t)a, (uintptr_t)a + m - 1);
     sb.init((intptr_t)b, (uintptr_t)b, (uintptr_t)b + n - 1);
 
-    // ring of the pattern-stream bytes currently inside the window (class bits only): chunks c and c+1
-    uint32_t ring[8];
-    uint32_t A7 = 0, A6 = 0;
+    // ring of the pattern-stream bytes currently inside the window (class bits only), oldest chunk first
+    uint32_t ring[RING];
+    W A7 = 0, A6 = 0;
     {
-        uint32_t x[8];
-        sa.take(x);
-        sa.take(x + 4);
-        A7 = gather_bits16(x, 7) | (gather_bits16(x + 4, 7) << 16);
-        if (PLANES == 2) A6 = gather_bits16(x, 6) | (gather_bits16(x + 4, 6) << 16);
+        uint32_t x[RING];
 #pragma unroll
-        for (int w = 0; w < 8; w++) ring[w] = x[w] & CMASK;
+        for (int c = 0; c < RING / 4; c++) sa.take(x + 4 * c);
 #pragma unroll
-        for (int t = 0; t < 32; t++) tab_at(tab, byte_of(ring[t >> 2], t & 3), pitch_log2) |= 1u << t;
+        for (int c = 0; c < RING / 4; c++) {
+            A7 |= (W)gather_bits16(x + 4 * c, 7) << (16 * c);
+            if (PLANES == 2) A6 |= (W)gather_bits16(x + 4 * c, 6) << (16 * c);
+        }
+#pragma unroll
+        for (int w = 0; w < RING; w++) ring[w] = x[w] & CMASK;
+#pragma unroll
+        for (int t = 0; t < BITS; t++) tab_at<W>(tab, byte_of(ring[t >> 2], t & 3), pitch_log2) |= (W)1 << t;
     }
 
-    uint32_t VP = dhi >= 32 ? 0u : (0xffffffffu << dhi);
-    uint32_t VN = ~VP;
-    uint32_t D0prev = 0xffffffffu, Eqprev = 0;
+    W VP = dhi >= BITS ? (W)0 : (W)(~(W)0 << dhi);
+    W VN = ~VP;
+    W D0prev = ~(W)0, Eqprev = 0;
     uint32_t matches = 0;
-    const uint32_t emask = 1u << e;
-    uint32_t half = 0;   // 0 or 16: circular bit position of this chunk's first column, (16 * chunk) mod 32
-    uint32_t bit0 = 1u;  // 1 << half
+    const W emask = (W)1 << e;
+    uint32_t phase = 0;  // circular bit position of this chunk's first column, (16 * chunk) mod BITS
+    W bit0 = 1;          // 1 << phase
 
     for (int j0 = 0; j0 < n; j0 += 16) {
         uint32_t aw[4], bw[4], bc[4];
-        sa.take(aw);  // stream chunk c+2: the bytes that enter during this chunk
+        sa.take(aw);  // the bytes that enter during this chunk
         sb.take(bw);
         // plane bits of the entering bytes, placed at the circular positions they will occupy
-        const uint32_t tops7 = gather_bits16(aw, 7) * bit0;
-        const uint32_t tops6 = PLANES == 2 ? gather_bits16(aw, 6) * bit0 : 0u;
+        const W tops7 = (W)gather_bits16(aw, 7) * bit0;
+        const W tops6 = PLANES == 2 ? (W)((W)gather_bits16(aw, 6) * bit0) : (W)0;
 #pragma unroll
         for (int w = 0; w < 4; w++) {
             aw[w] &= CMASK;
             bc[w] = bw[w] & CMASK;
         }
-        uint32_t hist = 0;
+        W hist = 0;
 #pragma unroll
         for (int u = 0; u < 16; u++) {
-            uint32_t miss = A7 ^ bit_mask_of(bw[u >> 2], u & 3, 7);  // rows whose plane bits differ from the text byte's
-            if (PLANES == 2) miss |= A6 ^ bit_mask_of(bw[u >> 2], u & 3, 6);
-            const uint32_t raw = tab_at(tab, byte_of(bc[u >> 2], u & 3), pitch_log2) & ~miss;
-            const uint32_t Eq = funnel_r(raw, raw, half + (uint32_t)u);  // rotate: window row 0 to bit 0
-            uint32_t D0 = (((Eq & VP) + VP) ^ VP) | Eq | VN;
+            W miss = A7 ^ bit_mask_of<W>(bw[u >> 2], u & 3, 7);  // rows whose plane bits differ from the text byte's
+            if (PLANES == 2) miss |= A6 ^ bit_mask_of<W>(bw[u >> 2], u & 3, 6);
+            const W raw = tab_at<W>(tab, byte_of(bc[u >> 2], u & 3), pitch_log2) & ~miss;
+            const W Eq = rotr<W>(raw, phase + (uint32_t)u);  // rotate: window row 0 to bit 0
+            W D0 = (((Eq & VP) + VP) ^ VP) | Eq | VN;
             if (TRANS) {
                 D0 |= ~D0prev & (Eq << 1) & (Eqprev >> 1);
                 D0prev = D0;
                 Eqprev = Eq;
             }
-            const uint32_t HP = VN | ~(D0 | VP);
-            const uint32_t HN = D0 & VP;
-            const uint32_t X = D0 >> 1;
+            const W HP = VN | ~(D0 | VP);
+            const W HN = D0 & VP;
+            const W X = D0 >> 1;
             VN = X & HP;
             VP = HN | ~(X | HP);
             hist += (D0 & emask) << u;
-            // slide: stream byte 16c + u leaves, byte 16c + 32 + u enters at the same circular bit position
-            const uint32_t bit = bit0 << u;
-            tab_at(tab, byte_of(ring[u >> 2], u & 3), pitch_log2) &= ~bit;
-            tab_at(tab, byte_of(aw[u >> 2], u & 3), pitch_log2) |= bit;
+            // slide: the oldest byte leaves, a new one enters at the same circular bit position
+            const W bit = bit0 << u;
+            tab_at<W>(tab, byte_of(ring[u >> 2], u & 3), pitch_log2) &= ~bit;
+            tab_at<W>(tab, byte_of(aw[u >> 2], u & 3), pitch_log2) |= bit;
             A7 = (A7 & ~bit) | (tops7 & bit);
             if (PLANES == 2) A6 = (A6 & ~bit) | (tops6 & bit);
         }
         const int cols = n - j0;
         const uint32_t valid = cols >= 16 ? 0xffffu : ((1u << cols) - 1u);
-#if defined(__CUDA_ARCH__)
-        matches += __popc((hist >> e) & valid);
-#else
-        matches += (uint32_t)__builtin_popcount((hist >> e) & valid);
-#endif
+        matches += popc_w((uint32_t)(hist >> e) & valid);
 #pragma unroll
-        for (int w = 0; w < 4; w++) {  // ring <- chunks c+1, c+2
-            ring[w] = ring[w + 4];
-            ring[w + 4] = aw[w];
-        }
-        half ^= 16u;
-        bit0 ^= 0x10001u;
+        for (int w = 0; w + 4 < RING; w++) ring[w] = ring[w + 4];  // drop the oldest chunk, append the new one
+#pragma unroll
+        for (int w = 0; w < 4; w++) ring[RING - 4 + w] = aw[w];
+        phase = (phase + 16u) & (uint32_t)(BITS - 1);
+        bit0 = (W)1 << phase;
     }
-    // leave the table clean: every set bit belongs to one of the 32 bytes still in the window
+    // leave the table clean: every set bit belongs to one of the bytes still in the window
 #pragma unroll
-    for (int t = 0; t < 32; t++) tab_at(tab, byte_of(ring[t >> 2], t & 3), pitch_log2) = 0;
+    for (int t = 0; t < BITS; t++) tab_at<W>(tab, byte_of(ring[t >> 2], t & 3), pitch_log2) = 0;
     return (uint32_t)diff + (uint32_t)n - matches;
 }
 
-template <bool TRANS, int PLANES>
+template <bool TRANS, int PLANES, typename W>
 TA_HD uint32_t pair_unit_costs_tab(const uint8_t *a, uint64_t a_len, const uint8_t *b, uint64_t b_len, uint32_t k,
                                    uint8_t *tab, const uint32_t pitch_log2) {
     if (a_len > b_len) {
@@ -342,7 +364,7 @@ TA_HD uint32_t pair_unit_costs_tab(const uint8_t *a, uint64_t a_len, const uint8
     const uint32_t max_k = k < (uint32_t)n ? k : (uint32_t)n;
     if (diff > max_k) return 0xFFFFFFFFu;
     if (m == 0) return (uint32_t)n;
-    const uint32_t d = distance32_tab<TRANS, PLANES>(a, m, b, n, max_k, tab, pitch_log2);
+    const uint32_t d = distance_tab<TRANS, PLANES, W>(a, m, b, n, max_k, tab, pitch_log2);
     return d <= max_k ? d : 0xFFFFFFFFu;
 }
 

@@ -58,7 +58,7 @@ int ta_launch_lev_band(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, con
 bool ta_bitpar_can_handle(uint32_t k, ta_costs c, uint32_t max_len);
 int ta_launch_lev_bitpar(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b,
                          const uint64_t *b_off, size_t n, const uint32_t *idx, uint32_t k, ta_costs costs,
-                         uint32_t *out, cudaStream_t st);
+                         uint32_t max_len, uint32_t *out, cudaStream_t st);
 // dispatcher: bit-parallel kernel when the cost model is unit and the band fits, else the general banded kernel
 int ta_launch_lev(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b, const uint64_t *b_off,
                   size_t n, const uint32_t *idx, uint32_t k, ta_costs costs, uint32_t max_len, uint32_t *out,
