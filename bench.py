@@ -37,6 +37,8 @@ WORKLOADS = {
                             "RDAMERAU_COSTS k=16, 1M pairs len=512, set M (U[0,16] edits incl. swaps)"),
     "lev_k16_len4096": ("lev_k", 65_536, 4096, 16, (1, 1, 0, 0),
                         "levenshtein_simd_k k=16, 64Ki pairs len=4096, unit costs, set M"),
+    "affine_k16_len128": ("lev_k", 1_000_000, 128, 16, (2, 1, 3, 0),
+                          "levenshtein_simd_k_with_opts k=16, 1M pairs len=128, EditCosts(2,1,3,None) (general kernel)"),
     "lev_k60_len1024": ("lev_k", 262_144, 1024, 60, (1, 1, 0, 0),
                         "levenshtein_simd_k k=60, 256Ki pairs len=1024, unit costs, set M (64-row window kernel)"),
     "exp_len1024": ("exp", 1_000_000, 1024, 30, (1, 1, 0, 0),

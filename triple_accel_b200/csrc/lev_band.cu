@@ -4,7 +4,7 @@
 // distance d under EditCosts {mismatch, gap, start_gap (affine), transpose (restricted Damerau)} if d <= k,
 // else TA_NONE.  `max_k`/`unit_k` clamps and the early None follow src/levenshtein.rs:400-430.
 //
-// Design (not a port of the reference's AVX2 lanes): a group of G lanes (G = 8/16/32, several pairs per warp for
+// Design (not a port of the reference's AVX2 lanes): a group of G lanes (G = 2..32, several pairs per warp for
 // narrow bands) owns one pair.  Lane t holds C cells of the current anti-diagonal s = i + j in registers; cell
 // ci = t*C + c sits on diagonal d = dlo + 2*ci + p with p = (s - dlo) & 1, so consecutive anti-diagonals
 // alternate between "even" and "odd" diagonals and only ceil(W/2) cells are live per step (W = band width).
@@ -16,6 +16,8 @@
 // carried as the sender-side pre-minimised values outH = min(D + open, H + gap), outV likewise, so a step costs
 // one shuffle whatever the cost model; the transposition test needs the neighbours' match flags, which ride in
 // bit 0 of the shuffled word.  Strings are staged into shared memory with 16-byte cp.async (LDGSTS) vectors.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "ta_common.cuh"
@@ -464,10 +466,13 @@ int launch_gc(ta_ctx *ctx, const BandArgs &args0, uint32_t max_len, cudaStream_t
 
 template <bool AFFINE, bool TRANS>
 int launch_w(ta_ctx *ctx, const BandArgs &args, uint32_t W, uint32_t max_len, cudaStream_t st) {
-    if (W <= 16) return launch_gc<8, 1, AFFINE, TRANS>(ctx, args, max_len, st);
-    if (W <= 32) return launch_gc<16, 1, AFFINE, TRANS>(ctx, args, max_len, st);
-    if (W <= 64) return launch_gc<32, 1, AFFINE, TRANS>(ctx, args, max_len, st);
-    if (W <= 128) return launch_gc<32, 2, AFFINE, TRANS>(ctx, args, max_len, st);
+    // four cells per lane wherever the band allows it: the shuffle, the character load and the loop bookkeeping are
+    // shared by the lane's cells (measured on cfg 2 with TA_FORCE_BAND=1: 1.08 ms at one cell per lane, 0.82 ms at
+    // two, 0.70 ms at four; eight cells on one or two lanes lose to shared-memory bank conflicts)
+    if (W <= 16) return launch_gc<2, 4, AFFINE, TRANS>(ctx, args, max_len, st);
+    if (W <= 32) return launch_gc<4, 4, AFFINE, TRANS>(ctx, args, max_len, st);
+    if (W <= 64) return launch_gc<8, 4, AFFINE, TRANS>(ctx, args, max_len, st);
+    if (W <= 128) return launch_gc<16, 4, AFFINE, TRANS>(ctx, args, max_len, st);
     if (W <= 256) return launch_gc<32, 4, AFFINE, TRANS>(ctx, args, max_len, st);
     if (W <= 512) return launch_gc<32, 8, AFFINE, TRANS>(ctx, args, max_len, st);
     if (W <= 1024) return launch_gc<32, 16, AFFINE, TRANS>(ctx, args, max_len, st);
@@ -557,10 +562,10 @@ __global__ void __launch_bounds__(128) trace_walk_kernel(const WalkArgs wa) {
 template <bool TRANS>
 int launch_trace_w(ta_ctx *ctx, const BandArgs &args, uint32_t W, uint32_t max_len, cudaStream_t st, uint32_t *wc) {
     // affine formulas are valid for start_gap == 0 too: the TRACE variants are only instantiated with AFFINE = true
-    if (W <= 16) return *wc = 8, launch_gc<8, 1, true, TRANS, true>(ctx, args, max_len, st);
-    if (W <= 32) return *wc = 16, launch_gc<16, 1, true, TRANS, true>(ctx, args, max_len, st);
-    if (W <= 64) return *wc = 32, launch_gc<32, 1, true, TRANS, true>(ctx, args, max_len, st);
-    if (W <= 128) return *wc = 64, launch_gc<32, 2, true, TRANS, true>(ctx, args, max_len, st);
+    if (W <= 16) return *wc = 8, launch_gc<2, 4, true, TRANS, true>(ctx, args, max_len, st);
+    if (W <= 32) return *wc = 16, launch_gc<4, 4, true, TRANS, true>(ctx, args, max_len, st);
+    if (W <= 64) return *wc = 32, launch_gc<8, 4, true, TRANS, true>(ctx, args, max_len, st);
+    if (W <= 128) return *wc = 64, launch_gc<16, 4, true, TRANS, true>(ctx, args, max_len, st);
     if (W <= 256) return *wc = 128, launch_gc<32, 4, true, TRANS, true>(ctx, args, max_len, st);
     if (W <= 512) return *wc = 256, launch_gc<32, 8, true, TRANS, true>(ctx, args, max_len, st);
     if (W <= 1024) return *wc = 512, launch_gc<32, 16, true, TRANS, true>(ctx, args, max_len, st);
