@@ -398,6 +398,33 @@ def test_exp_and_search_device_entry_points(eng):
         assert np.array_equal(goff, woff) and np.array_equal(got, want)
 
 
+def test_search_segment_warmup_is_exact(eng):
+    """With the pre-filter, the exact (cost, length) DP is re-run per flagged 512-byte segment after a warm-up of
+    2N + 2 bytes instead of from the start of the haystack.  Tiny alphabets make length ties the common case, so
+    any dependence of a match's `start` on bytes before the warm-up window would show up here."""
+    rng = random.Random(20261017)
+    for trial in range(10):
+        alpha = rng.choice([2, 2, 3, 4])
+        nlen = rng.choice([3, 5, 8, 13, 21, 32, 40, 64])
+        needle = bytes(rng.randrange(alpha) for _ in range(nlen))
+        hays = []
+        for _ in range(40):
+            h = bytearray(rng.randrange(alpha) for _ in range(rng.randrange(1500, 3200)))
+            for _ in range(rng.randrange(0, 6)):
+                p = rng.randrange(len(h) - nlen)
+                h[p:p + nlen] = _mutate(rng, needle, rng.randrange(0, 4), alpha)[:nlen]
+            hays.append(bytes(h))
+        hay, hoff = _pack(hays)
+        for costs in ((1, 1, 0, 0), (1, 1, 0, 1)):
+            for k in (0, 1, max(1, nlen // 5), nlen // 2):
+                if k >= nlen:
+                    continue
+                for st in (0, 1):
+                    got, goff = eng.levenshtein_search_batch(needle, hay, hoff, k, st, costs)
+                    want, woff = orc.levenshtein_search_batch(needle, hay, hoff, k, st, costs, threads=8)
+                    assert np.array_equal(goff, woff) and np.array_equal(got, want), (alpha, nlen, costs, k, st)
+
+
 def test_search_filter_long_needles_and_transpositions(eng):
     """the bit-parallel pre-filter (needle <= 64, unit costs, with and without transpositions) must never drop a
     haystack that has a match: compare the full match lists with the oracle"""
@@ -571,7 +598,7 @@ def test_cpp_header_mirror(tmp_path):
 
 LEV_TESTS = "test_lev_k_mutated or test_lev_k_random_short or test_nul_bytes or test_lev_exp"
 SEARCH_TESTS = ("test_search_random or test_search_planted or test_kat_search or "
-                "test_search_filter_long_needles_and_transpositions")
+                "test_search_filter_long_needles_and_transpositions or test_search_segment_warmup")
 
 
 @pytest.mark.parametrize("env,select", [

@@ -120,7 +120,7 @@ int ta_launch_lev_bitpar(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, c
 // haystack bytes under unit costs).  The 256-entry match-mask table of the needle lives in shared memory.
 namespace {
 
-constexpr int FILTER_SEG = 512;
+constexpr int FILTER_SEG = TA_SEARCH_SEG;
 
 template <typename W, bool TRANS>
 __global__ void __launch_bounds__(128) search_filter_kernel(const uint8_t *__restrict__ needle, uint32_t N,
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(128) search_filter_kernel(const uint8_t *__res
             hit |= (x >= seg_begin) & (x < seg_end) & (score <= k);
         }
         if (hit) {
-            flags[h] = 1;
+            flags[h * gridDim.y + blockIdx.y] = 1;  // segment (h, s) contains a match end
             return;
         }
     }
@@ -192,16 +192,19 @@ __global__ void collect_flagged_kernel(const uint32_t *__restrict__ flags, size_
 
 }  // namespace
 
-// flags haystacks with at least one end position of unit-cost distance <= k and writes their indices (unordered)
-// to idx_out, the count to *counter.  Needs needle_len in [1, 64]; max_hay = longest haystack.
+// flags the 512-byte haystack segments that contain at least one end position of unit-cost distance <= k and writes
+// their codes (haystack * segs + segment, unordered) to idx_out, the count to *counter; *segs_out = segments per
+// haystack.  Needs needle_len in [1, 64], n * segs < 2^32; max_hay = longest haystack.
 int ta_launch_search_filter(ta_ctx *ctx, const uint8_t *needle_dev, uint32_t needle_len, const uint8_t *hay,
                             const uint64_t *hay_off, size_t n, uint64_t max_hay, uint32_t k, bool transpose,
-                            uint32_t *flags, uint32_t *idx_out, uint32_t *counter, cudaStream_t st) {
+                            uint32_t *flags, uint32_t *idx_out, uint32_t *counter, uint32_t *segs_out,
+                            cudaStream_t st) {
     if (needle_len == 0 || needle_len > 64) return TA_ERR_TOO_LARGE;
+    const uint64_t segs = max_hay ? (max_hay + FILTER_SEG - 1) / FILTER_SEG : 1;
+    *segs_out = (uint32_t)segs;
     if (n == 0 || max_hay == 0) return TA_OK;
-    const uint64_t segs = (max_hay + FILTER_SEG - 1) / FILTER_SEG;
-    if (segs > 65535) return TA_ERR_TOO_LARGE;
-    TA_CUDA(ctx, cudaMemsetAsync(flags, 0, n * sizeof(uint32_t), st));
+    if (segs > 65535 || (uint64_t)n * segs > 0xFFFFFFF0ull) return TA_ERR_TOO_LARGE;
+    TA_CUDA(ctx, cudaMemsetAsync(flags, 0, n * segs * sizeof(uint32_t), st));
     const dim3 grid((unsigned)((n + 127) / 128), (unsigned)segs);
     if (needle_len <= 32) {
         if (transpose)
@@ -216,8 +219,9 @@ int ta_launch_search_filter(ta_ctx *ctx, const uint8_t *needle_dev, uint32_t nee
     }
     ctx->launches++;
     TA_CUDA(ctx, cudaGetLastError());
-    const unsigned cblocks = (unsigned)((n + 255) / 256 < (size_t)ctx->sm_count * 8 ? (n + 255) / 256 : (size_t)ctx->sm_count * 8);
-    collect_flagged_kernel<<<cblocks, 256, 0, st>>>(flags, n, idx_out, counter);
+    const size_t items = n * segs;
+    const unsigned cblocks = (unsigned)((items + 255) / 256 < (size_t)ctx->sm_count * 8 ? (items + 255) / 256 : (size_t)ctx->sm_count * 8);
+    collect_flagged_kernel<<<cblocks, 256, 0, st>>>(flags, items, idx_out, counter);
     ctx->launches++;
     TA_CUDA(ctx, cudaGetLastError());
     return TA_OK;

@@ -23,7 +23,8 @@
 // implemented in lev_bitpar.cu: flags[i] = 1 iff haystack i has an end position with unit-cost distance <= k
 int ta_launch_search_filter(ta_ctx *ctx, const uint8_t *needle_dev, uint32_t needle_len, const uint8_t *hay,
                             const uint64_t *hay_off, size_t n, uint64_t max_hay, uint32_t k, bool transpose,
-                            uint32_t *flags, uint32_t *idx_out, uint32_t *counter, cudaStream_t st);
+                            uint32_t *flags, uint32_t *idx_out, uint32_t *counter, uint32_t *segs_out,
+                            cudaStream_t st);
 
 namespace {
 
@@ -36,7 +37,10 @@ struct SearchArgs {
     const uint8_t *needle;  // device copy
     const uint8_t *hay;
     const uint64_t *hay_off;
-    const uint32_t *idx;  // optional: work item w -> haystack idx[w]
+    const uint32_t *idx;  // optional: work item w -> haystack idx[w] (or a segment code, see segs)
+    uint32_t segs;        // 0: idx holds haystack indices.  > 0: idx holds haystack * segs + segment codes and the
+                          // item covers only that TA_SEARCH_SEG-byte segment after a warm-up of `warm` bytes
+    uint32_t warm;
     size_t n;
     uint32_t needle_len;
     uint32_t k;
@@ -211,14 +215,29 @@ __global__ void __launch_bounds__(128) search_wave_kernel(const SearchArgs args)
     const int t = threadIdx.x & 31;
     const size_t w = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (w >= args.n) return;  // whole warp
-    const uint32_t hidx = args.idx ? args.idx[w] : (uint32_t)w;
+    const uint32_t code = args.idx ? args.idx[w] : (uint32_t)w;
+    const uint32_t hidx = args.segs ? code / args.segs : code;
     const uint64_t h0 = args.hay_off[hidx], h1 = args.hay_off[hidx + 1];
     const uint8_t *hay = args.hay + h0;
-    const uint64_t H = h1 - h0;
+    uint64_t H = h1 - h0;
     const uint32_t N = args.needle_len;
     const uint32_t mism = args.mism, gap = args.gap, sgap = args.sgap, tcost = args.tcost, k = args.k;
     const uint32_t open = sgap + gap;
     const bool anchored = args.anchored != 0;
+    // Segment mode (unanchored only): the column state at x depends on at most 2N + start_gap/gap + 2 earlier
+    // haystack bytes (an optimal alignment of a needle prefix of length j ending at x costs <= j*gap + start_gap,
+    // so it consumes <= 2j + start_gap/gap haystack bytes, and every tied candidate of the reference's length
+    // tie-breaks lies on such a path); a fresh start `warm` bytes before the segment therefore reproduces the
+    // reference's (cost, length) for every end position inside the segment.
+    uint64_t col0 = 0, emit_from = 0;  // columns are numbered from col0; hits are reported for x > emit_from
+    if (args.segs) {
+        const uint64_t seg = code % args.segs;
+        emit_from = seg * TA_SEARCH_SEG;
+        const uint64_t seg_end = emit_from + TA_SEARCH_SEG < H ? emit_from + TA_SEARCH_SEG : H;
+        col0 = emit_from > args.warm ? emit_from - args.warm : 0;
+        hay += col0;
+        H = seg_end - col0;
+    }
     uint64_t iter_len = H;  // src/levenshtein.rs:1650-1661
     if (anchored) {
         const uint64_t lim = (uint64_t)N + (uint64_t)((k > sgap ? k - sgap : 0u) / gap);
@@ -348,13 +367,13 @@ __global__ void __launch_bounds__(128) search_wave_kernel(const SearchArgs args)
                 left_dp = dp;
                 left_len = len;
                 nprev = nc[c];
-                if (c == last_c && t == last_t && dp <= k) {  // :1792-1806 (All threshold; Best on the host)
-                    const unsigned long long slot = atomicAdd(args.hit_count, 1ull);
+                if (c == last_c && t == last_t && dp <= k && (uint64_t)x + col0 > emit_from) {
+                    const unsigned long long slot = atomicAdd(args.hit_count, 1ull);  // :1792-1806 (All threshold)
                     if (slot < args.hit_cap) {
                         Hit h;
                         h.hay = hidx;
                         h.cost = dp;
-                        h.end = (uint64_t)x;
+                        h.end = (uint64_t)x + col0;
                         h.len = len;
                         args.hits[slot] = h;
                     }
@@ -399,22 +418,28 @@ static int search_device(ta_ctx *ctx, cudaStream_t st, const uint8_t *d_needle, 
     const bool unit = costs.mismatch == 1 && costs.gap == 1 && costs.start_gap == 0 && costs.transpose <= 1;
     const uint32_t *d_idx = nullptr;
     size_t work_n = n;
+    uint32_t segs = 0;  // > 0: work items are flagged haystack segments (pre-filter ran)
     static const bool no_filter = getenv("TA_NO_SEARCH_FILTER") != nullptr;  // testing: exact kernel on everything
     if (!no_filter && unit && needle_len <= 64 && !anchored && k < needle_len) {
-        if ((rc = ta_dev_reserve(ctx, ctx->d_work[0], n * sizeof(uint32_t))) != TA_OK) return rc;
-        if ((rc = ta_dev_reserve(ctx, ctx->d_work[2], n * sizeof(uint32_t))) != TA_OK) return rc;
-        uint32_t *counter = ctx->d_flags + 2;
-        TA_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(uint32_t), st));
-        rc = ta_launch_search_filter(ctx, d_needle, (uint32_t)needle_len, d_hay, d_off, n, max_hay, k,
-                                     costs.transpose != 0, (uint32_t *)ctx->d_work[2].p, (uint32_t *)ctx->d_work[0].p,
-                                     counter, st);
-        if (rc == TA_OK) {
-            TA_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags + 2, counter, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-            TA_CUDA(ctx, cudaStreamSynchronize(st));
-            work_n = ctx->h_flags[2];
-            d_idx = (const uint32_t *)ctx->d_work[0].p;
-        } else if (rc != TA_ERR_TOO_LARGE) {
-            return rc;
+        const uint64_t nseg = max_hay ? (max_hay + TA_SEARCH_SEG - 1) / TA_SEARCH_SEG : 1;
+        if ((uint64_t)n * nseg <= 0xFFFFFFF0ull && nseg <= 65535) {
+            if ((rc = ta_dev_reserve(ctx, ctx->d_work[0], n * nseg * sizeof(uint32_t))) != TA_OK) return rc;
+            if ((rc = ta_dev_reserve(ctx, ctx->d_work[2], n * nseg * sizeof(uint32_t))) != TA_OK) return rc;
+            uint32_t *counter = ctx->d_flags + 2;
+            TA_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(uint32_t), st));
+            rc = ta_launch_search_filter(ctx, d_needle, (uint32_t)needle_len, d_hay, d_off, n, max_hay, k,
+                                         costs.transpose != 0, (uint32_t *)ctx->d_work[2].p,
+                                         (uint32_t *)ctx->d_work[0].p, counter, &segs, st);
+            if (rc == TA_OK) {
+                TA_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags + 2, counter, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+                TA_CUDA(ctx, cudaStreamSynchronize(st));
+                work_n = ctx->h_flags[2];
+                d_idx = (const uint32_t *)ctx->d_work[0].p;
+            } else if (rc == TA_ERR_TOO_LARGE) {
+                segs = 0;
+            } else {
+                return rc;
+            }
         }
     }
     if (work_n == 0) return TA_OK;
@@ -434,6 +459,7 @@ static int search_device(ta_ctx *ctx, cudaStream_t st, const uint8_t *d_needle, 
     bool use_wave = wave_ok && (!thread_ok || work_n < (size_t)ctx->sm_count * 256);
     if (force && force[0] == 't' && thread_ok) use_wave = false;
     if (force && force[0] == 'w' && wave_ok) use_wave = true;
+    if (segs) use_wave = true;  // segment work items are only understood by the wave kernel (needle <= 64 here)
     if (!use_wave && !thread_ok) return TA_ERR_TOO_LARGE;
     void (*kern)(const SearchArgs) = nullptr;
     if (use_wave) {
@@ -455,6 +481,7 @@ static int search_device(ta_ctx *ctx, cudaStream_t st, const uint8_t *d_needle, 
         TA_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st));
         SearchArgs sa;
         sa.needle = d_needle, sa.hay = d_hay, sa.hay_off = d_off, sa.idx = d_idx, sa.n = work_n;
+        sa.segs = segs, sa.warm = 2u * (uint32_t)needle_len + costs.start_gap / costs.gap + 2u;
         sa.needle_len = (uint32_t)needle_len, sa.k = k;
         sa.mism = costs.mismatch, sa.gap = costs.gap, sa.sgap = costs.start_gap, sa.tcost = costs.transpose;
         sa.anchored = anchored, sa.hits = (Hit *)ctx->d_work[1].p, sa.hit_count = d_count, sa.hit_cap = cap;

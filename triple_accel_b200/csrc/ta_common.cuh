@@ -9,6 +9,7 @@
 
 #include "../../include/triple_accel_b200.h"
 
+#define TA_SEARCH_SEG 512  // haystack bytes per pre-filter segment (lev_bitpar.cu, search.cu)
 #define TA_INF 0x3FFFFFFFu  // "out of band" cell value; real costs stay below 2^30 (TA_MAX_STRING_LEN)
 
 struct DevBuf {
