@@ -151,9 +151,33 @@ __global__ void __launch_bounds__(128) search_filter_kernel(const uint8_t *__res
     // the haystack is streamed in aligned 16-byte vectors and re-aligned in registers (bitpar::Stream)
     bitpar::Stream hs;
     hs.init((intptr_t)(p + start), (uintptr_t)p, (uintptr_t)(p + H - 1));
+    const W rowmask = N >= 8 * sizeof(W) ? ~(W)0 : (((W)1 << N) - 1);
     for (uint64_t x0 = start; x0 < seg_end; x0 += 16) {
         uint32_t wds[4];
         hs.take(wds);
+        // The score D[N][x] moves by at most one per byte.  While it is more than 16 above k no position of this
+        // 16-byte chunk can be a hit: run the bare recurrence and rebuild the score afterwards from the vertical
+        // deltas (D[N][x] = #VP - #VN over the needle's rows); otherwise track it byte by byte.
+        if (score > k + 16u) {
+#pragma unroll
+            for (int u = 0; u < 16; u++) {
+                const uint32_t ch = (wds[u >> 2] >> (8 * (u & 3))) & 0xffu;
+                const W Eq = peq[ch];
+                W D0 = (((Eq & VP) + VP) ^ VP) | Eq | VN;
+                if (TRANS) {
+                    D0 |= ((~D0prev & Eq) << 1) & Eqprev;
+                    D0prev = D0;
+                    Eqprev = Eq;
+                }
+                const W HP = (VN | ~(D0 | VP)) << 1;  // row 0 of a search has horizontal delta 0
+                const W HN = (D0 & VP) << 1;
+                VP = HN | ~(D0 | HP);
+                VN = D0 & HP;
+            }
+            score = sizeof(W) == 4 ? (uint32_t)(__popc((uint32_t)(VP & rowmask)) - __popc((uint32_t)(VN & rowmask)))
+                                   : (uint32_t)(__popcll((uint64_t)(VP & rowmask)) - __popcll((uint64_t)(VN & rowmask)));
+            continue;
+        }
         bool hit = false;
 #pragma unroll
         for (int u = 0; u < 16; u++) {
@@ -170,7 +194,7 @@ __global__ void __launch_bounds__(128) search_filter_kernel(const uint8_t *__res
             W HN = D0 & VP;
             score += (HP & top) ? 1u : 0u;
             score -= (HN & top) ? 1u : 0u;
-            HP <<= 1;  // row 0 of a search has horizontal delta 0
+            HP <<= 1;
             HN <<= 1;
             VP = HN | ~(D0 | HP);
             VN = D0 & HP;

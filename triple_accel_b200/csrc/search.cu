@@ -517,7 +517,12 @@ static void emit_matches(size_t n, size_t needle_len, uint32_t k, bool best, ta_
     const uint32_t row0 = (uint32_t)needle_len * costs.gap + costs.start_gap;
     size_t hp = 0;
     std::vector<ta_match> cur;
+    result.reserve(hits.size() + (row0 <= k ? n : 0));
     for (size_t i = 0; i < n; i++) {
+        if (row0 > k && (hp >= hits.size() || hits[hp].hay != i)) {  // nothing to report for this haystack
+            moff[i + 1] = result.size();
+            continue;
+        }
         cur.clear();
         uint32_t curr_k = k;
         if (row0 <= curr_k) {
