@@ -604,11 +604,13 @@ SEARCH_TESTS = ("test_search_random or test_search_planted or test_kat_search or
 @pytest.mark.parametrize("env,select", [
     ({"TA_FORCE_BAND": "1"}, LEV_TESTS),
     ({"TA_BITPAR": "simd"}, LEV_TESTS),
-    ({"TA_BITPAR": "tab", "TA_BITPAR_PLANES": "2", "TA_BITPAR_THREADS": "64"}, LEV_TESTS),
+    ({"TA_BITPAR_BITS": "32"}, LEV_TESTS),
+    ({"TA_BITPAR": "tab", "TA_BITPAR_BITS": "32", "TA_BITPAR_PLANES": "2", "TA_BITPAR_THREADS": "64"}, LEV_TESTS),
     ({"TA_NO_SEARCH_FILTER": "1", "TA_SEARCH_KERNEL": "thread"}, SEARCH_TESTS),
     ({"TA_NO_SEARCH_FILTER": "1", "TA_SEARCH_KERNEL": "wave"}, SEARCH_TESTS),
     ({"TA_SEARCH_KERNEL": "thread"}, SEARCH_TESTS),
-], ids=["general-band-kernel", "bitpar-simd-kernel", "bitpar-table-2plane-kernel", "search-thread-kernel-nofilter", "search-wave-kernel-nofilter",
+], ids=["general-band-kernel", "bitpar-simd-kernel", "bitpar-table-32bit-on-narrow-bands",
+        "bitpar-table-2plane-kernel", "search-thread-kernel-nofilter", "search-wave-kernel-nofilter",
         "search-thread-kernel-filter"])
 def test_every_kernel_variant_forced(env, select):
     """The dispatchers pick a kernel from the cost model, band width and batch size (bit-parallel vs general banded

@@ -66,6 +66,10 @@ static bool fits32(uint32_t k, ta_costs c, uint32_t max_len) {
     const uint32_t kk = k < max_len ? k : max_len;
     return kk <= (c.transpose ? 30u : 31u);
 }
+static bool fits16(uint32_t k, ta_costs c, uint32_t max_len) {
+    const uint32_t kk = k < max_len ? k : max_len;
+    return kk <= (c.transpose ? 14u : 15u);
+}
 
 int ta_launch_lev_bitpar(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b,
                          const uint64_t *b_off, size_t n, const uint32_t *idx, uint32_t k, ta_costs costs,
@@ -77,17 +81,23 @@ int ta_launch_lev_bitpar(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, c
     static const char *variant = getenv("TA_BITPAR");
     static const int env_threads = getenv("TA_BITPAR_THREADS") ? atoi(getenv("TA_BITPAR_THREADS")) : 0;
     static const int env_planes = getenv("TA_BITPAR_PLANES") ? atoi(getenv("TA_BITPAR_PLANES")) : 0;
+    static const int env_bits = getenv("TA_BITPAR_BITS") ? atoi(getenv("TA_BITPAR_BITS")) : 0;
     const bool wide = !fits32(k, costs, max_len);
     if (wide || !(variant && variant[0] == 's')) {
-        const int planes = wide ? 2 : (env_planes == 2 ? 2 : 1);
-        const int nt = env_threads ? env_threads : (wide ? 64 : 128);
-        const size_t smem = (size_t)(planes == 2 ? 64 : 128) * nt * (wide ? 8 : 4);
-        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(32, (size_t)(ctx->smem_optin + 1024) / (smem + 1024)));
+        // window width: the narrowest that holds the band (16-bit entries halve the shared memory per thread and
+        // double the resident warps); TA_BITPAR_BITS=32 keeps the 32-row window for narrow bands (measurement)
+        const int bits = wide ? 64 : (fits16(k, costs, max_len) && env_bits != 32 ? 16 : 32);
+        const int planes = bits == 64 ? 2 : (env_planes == 2 && bits == 32 ? 2 : 1);
+        const int nt = env_threads ? env_threads : (bits == 64 ? 64 : 128);
+        const size_t smem = (size_t)(planes == 2 ? 64 : 128) * nt * (bits / 8);
+        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (size_t)(ctx->smem_optin + 1024) / (smem + 1024)));
         const unsigned blocks = (unsigned)std::min<size_t>((n + nt - 1) / nt, (size_t)ctx->sm_count * per_sm);
         void (*kern)(const uint8_t *, const uint64_t *, const uint8_t *, const uint64_t *, const uint32_t *, size_t,
                      uint32_t, uint32_t *);
-        if (wide)
+        if (bits == 64)
             kern = costs.transpose ? lev_bitpar_tab_kernel<true, 2, uint64_t> : lev_bitpar_tab_kernel<false, 2, uint64_t>;
+        else if (bits == 16)
+            kern = costs.transpose ? lev_bitpar_tab_kernel<true, 1, uint16_t> : lev_bitpar_tab_kernel<false, 1, uint16_t>;
         else if (planes == 2)
             kern = costs.transpose ? lev_bitpar_tab_kernel<true, 2, uint32_t> : lev_bitpar_tab_kernel<false, 2, uint32_t>;
         else

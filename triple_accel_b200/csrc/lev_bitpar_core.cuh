@@ -98,15 +98,19 @@ struct Stream {
     }
     // the next 16 logical bytes as four little-endian words; advances the stream
     TA_HD void take(uint32_t out[4]) {
-        const uint32_t v[8] = {cur.x, cur.y, cur.z, cur.w, nxt.x, nxt.y, nxt.z, nxt.w};
-        uint32_t z[7], y[5];
-        const bool s1 = wsel & 1u, s2 = wsel & 2u;
+        if ((wsel | bsh) == 0) {  // 16-byte aligned stream: the vector is the chunk
+            out[0] = cur.x, out[1] = cur.y, out[2] = cur.z, out[3] = cur.w;
+        } else {
+            const uint32_t v[8] = {cur.x, cur.y, cur.z, cur.w, nxt.x, nxt.y, nxt.z, nxt.w};
+            uint32_t z[7], y[5];
+            const bool s1 = wsel & 1u, s2 = wsel & 2u;
 #pragma unroll
-        for (int i = 0; i < 7; i++) z[i] = s1 ? v[i + 1] : v[i];
+            for (int i = 0; i < 7; i++) z[i] = s1 ? v[i + 1] : v[i];
 #pragma unroll
-        for (int i = 0; i < 5; i++) y[i] = s2 ? z[i + 2] : z[i];
+            for (int i = 0; i < 5; i++) y[i] = s2 ? z[i + 2] : z[i];
 #pragma unroll
-        for (int i = 0; i < 4; i++) out[i] = funnel_r(y[i], y[i + 1], bsh);
+            for (int i = 0; i < 4; i++) out[i] = funnel_r(y[i], y[i + 1], bsh);
+        }
         cur = nxt;
         nxt = fetch();
     }
@@ -230,8 +234,20 @@ TA_HD W bit_mask_of(uint32_t w, int t, int bitpos) {
 template <typename W>
 TA_HD W rotr(W x, uint32_t s) {  // s in [0, bits)
     if (sizeof(W) == 4) return (W)funnel_r((uint32_t)x, (uint32_t)x, s);
+    if (sizeof(W) == 2) {  // duplicate into both halves, then one 32-bit shift
+        const uint32_t d = prmt((uint32_t)x, 0u, 0x1010u);
+        return (W)(d >> s);
+    }
     return s ? (W)((x >> s) | (x << (8 * sizeof(W) - s))) : x;
 }
+template <typename W>
+struct WiderOf {
+    typedef uint32_t type;
+};
+template <>
+struct WiderOf<uint64_t> {
+    typedef uint64_t type;
+};
 TA_HD uint32_t popc_w(uint32_t x) {
 #if defined(__CUDA_ARCH__)
     return (uint32_t)__popc(x);
@@ -249,7 +265,8 @@ TA_HD uint32_t popc_w(uint32_t x) {
 // byte that leaves and sets the same bit position for the byte that enters (two read-modify-writes), so a column
 // costs  Eq = rotr(tab[class(b)] & ~miss, u mod BITS)  -- one LDS, two or three LOP3, one rotate -- instead of 8
 // SWAR compares.  The table must be all-zero on entry and is left all-zero on exit.
-//   W = uint32_t: 32-row window (k <= 31; <= 30 with transpositions);  W = uint64_t: 64-row window (k <= 63 / 62).
+//   W = uint16_t: 16-row window (k <= 15 / 14), half the shared memory per thread;  W = uint32_t: 32-row window
+//   (k <= 31; <= 30 with transpositions);  W = uint64_t: 64-row window (k <= 63 / 62).
 //   PLANES = 1: 128 entries (7-bit classes) + the A7 plane;  PLANES = 2: 64 entries (6-bit classes) + A6, A7.
 template <bool TRANS, int PLANES, typename W>
 TA_HD uint32_t distance_tab(const uint8_t *a, int m, const uint8_t *b, int n, uint32_t max_k, uint8_t *tab,
@@ -257,6 +274,7 @@ TA_HD uint32_t distance_tab(const uint8_t *a, int m, const uint8_t *b, int n, ui
     constexpr int BITS = 8 * (int)sizeof(W);
     constexpr int RING = BITS / 4;  // words holding the window's bytes
     constexpr uint32_t CMASK = PLANES == 1 ? 0x7f7f7f7fu : 0x3f3f3f3fu;
+    typedef typename WiderOf<W>::type HistT;  // per-chunk match history: bit e + u, e <= BITS/2
     const int diff = n - m;
     // one margin diagonal each side so that the transposition test can see its neighbours' match flags -- only needed
     // when max_k - diff is odd: with an even budget the gaps needed to reach an extreme diagonal and come back use
@@ -277,74 +295,108 @@ TA_HD uint32_t distance_tab(const uint8_t *a, int m, const uint8_t *b, int n, ui
         for (int c = 0; c < RING / 4; c++) sa.take(x + 4 * c);
 #pragma unroll
         for (int c = 0; c < RING / 4; c++) {
-            A7 |= (W)gather_bits16(x + 4 * c, 7) << (16 * c);
-            if (PLANES == 2) A6 |= (W)gather_bits16(x + 4 * c, 6) << (16 * c);
+            A7 |= (W)((W)gather_bits16(x + 4 * c, 7) << (16 * c));
+            if (PLANES == 2) A6 |= (W)((W)gather_bits16(x + 4 * c, 6) << (16 * c));
         }
 #pragma unroll
         for (int w = 0; w < RING; w++) ring[w] = x[w] & CMASK;
 #pragma unroll
-        for (int t = 0; t < BITS; t++) tab_at<W>(tab, byte_of(ring[t >> 2], t & 3), pitch_log2) |= (W)1 << t;
+        for (int t = 0; t < BITS; t++) tab_at<W>(tab, byte_of(ring[t >> 2], t & 3), pitch_log2) |= (W)((W)1 << t);
     }
 
-    W VP = dhi >= BITS ? (W)0 : (W)(~(W)0 << dhi);
-    W VN = ~VP;
-    W D0prev = ~(W)0, Eqprev = 0;
+    const W ones = (W) ~(W)0;
+    W VP = dhi >= BITS ? (W)0 : (W)(ones << dhi);
+    W VN = (W)~VP;
+    W D0prev = ones, Eqprev = 0;
     uint32_t matches = 0;
-    const W emask = (W)1 << e;
+    const W emask = (W)((W)1 << e);
+    HistT acc = 0;       // (# columns of this chunk whose final-diagonal cell has diagonal delta 0) << e
     uint32_t phase = 0;  // circular bit position of this chunk's first column, (16 * chunk) mod BITS
     W bit0 = 1;          // 1 << phase
+    W tops7 = 0, tops6 = 0;  // plane bits of the chunk's entering bytes at their circular positions
 
-    for (int j0 = 0; j0 < n; j0 += 16) {
-        uint32_t aw[4], bw[4], bc[4];
-        sa.take(aw);  // the bytes that enter during this chunk
+    // one DP column: b7m/b6m = all-ones iff the text byte has bit 7/6 set, bcls = its class bits, lv/en = classes of
+    // the pattern bytes that leave/enter the window after this column, bit = their circular position, rot = the
+    // circular position of window row 0
+    auto column = [&](W b7m, W b6m, uint32_t bcls, uint32_t lv, uint32_t en, W bit, uint32_t rot) {
+        W miss = (W)(A7 ^ b7m);  // rows whose plane bits differ from the text byte's
+        if (PLANES == 2) miss |= (W)(A6 ^ b6m);
+        const W raw = (W)(tab_at<W>(tab, bcls, pitch_log2) & ~miss);
+        const W Eq = rotr<W>(raw, rot);
+        W D0 = (W)((((Eq & VP) + VP) ^ VP) | Eq | VN);
+        if (TRANS) {
+            D0 |= (W)(~D0prev & (Eq << 1) & (Eqprev >> 1));
+            D0prev = D0;
+            Eqprev = Eq;
+        }
+        const W HP = (W)(VN | ~(D0 | VP));
+        const W HN = (W)(D0 & VP);
+        const W X = (W)(D0 >> 1);
+        VN = (W)(X & HP);
+        VP = (W)(HN | ~(X | HP));
+        acc += (HistT)(D0 & emask);
+        tab_at<W>(tab, lv, pitch_log2) &= (W)~bit;
+        tab_at<W>(tab, en, pitch_log2) |= bit;
+        A7 = (W)((A7 & ~bit) | (tops7 & bit));
+        if (PLANES == 2) A6 = (W)((A6 & ~bit) | (tops6 & bit));
+    };
+
+    uint32_t aw[4] = {0, 0, 0, 0}, bw[4], bc[4];
+    int j0 = 0;
+    for (; j0 + 16 <= n; j0 += 16) {  // full 16-column chunks: every selector and shift below is a constant
+        sa.take(aw);                  // the bytes that enter during this chunk
         sb.take(bw);
-        // plane bits of the entering bytes, placed at the circular positions they will occupy
-        const W tops7 = (W)gather_bits16(aw, 7) * bit0;
-        const W tops6 = PLANES == 2 ? (W)((W)gather_bits16(aw, 6) * bit0) : (W)0;
+        tops7 = (W)((W)gather_bits16(aw, 7) * bit0);
+        if (PLANES == 2) tops6 = (W)((W)gather_bits16(aw, 6) * bit0);
 #pragma unroll
         for (int w = 0; w < 4; w++) {
             aw[w] &= CMASK;
             bc[w] = bw[w] & CMASK;
         }
-        W hist = 0;
 #pragma unroll
-        for (int u = 0; u < 16; u++) {
-            W miss = A7 ^ bit_mask_of<W>(bw[u >> 2], u & 3, 7);  // rows whose plane bits differ from the text byte's
-            if (PLANES == 2) miss |= A6 ^ bit_mask_of<W>(bw[u >> 2], u & 3, 6);
-            const W raw = tab_at<W>(tab, byte_of(bc[u >> 2], u & 3), pitch_log2) & ~miss;
-            const W Eq = rotr<W>(raw, phase + (uint32_t)u);  // rotate: window row 0 to bit 0
-            W D0 = (((Eq & VP) + VP) ^ VP) | Eq | VN;
-            if (TRANS) {
-                D0 |= ~D0prev & (Eq << 1) & (Eqprev >> 1);
-                D0prev = D0;
-                Eqprev = Eq;
-            }
-            const W HP = VN | ~(D0 | VP);
-            const W HN = D0 & VP;
-            const W X = D0 >> 1;
-            VN = X & HP;
-            VP = HN | ~(X | HP);
-            hist += (D0 & emask) << u;
-            // slide: the oldest byte leaves, a new one enters at the same circular bit position
-            const W bit = bit0 << u;
-            tab_at<W>(tab, byte_of(ring[u >> 2], u & 3), pitch_log2) &= ~bit;
-            tab_at<W>(tab, byte_of(aw[u >> 2], u & 3), pitch_log2) |= bit;
-            A7 = (A7 & ~bit) | (tops7 & bit);
-            if (PLANES == 2) A6 = (A6 & ~bit) | (tops6 & bit);
-        }
-        const int cols = n - j0;
-        const uint32_t valid = cols >= 16 ? 0xffffu : ((1u << cols) - 1u);
-        matches += popc_w((uint32_t)(hist >> e) & valid);
+        for (int u = 0; u < 16; u++)
+            column(bit_mask_of<W>(bw[u >> 2], u & 3, 7), PLANES == 2 ? bit_mask_of<W>(bw[u >> 2], u & 3, 6) : (W)0,
+                   byte_of(bc[u >> 2], u & 3), byte_of(ring[u >> 2], u & 3), byte_of(aw[u >> 2], u & 3),
+                   (W)(bit0 << u), phase + (uint32_t)u);
+        matches += (uint32_t)(acc >> e);
+        acc = 0;
 #pragma unroll
         for (int w = 0; w + 4 < RING; w++) ring[w] = ring[w + 4];  // drop the oldest chunk, append the new one
 #pragma unroll
         for (int w = 0; w < 4; w++) ring[RING - 4 + w] = aw[w];
         phase = (phase + 16u) & (uint32_t)(BITS - 1);
-        bit0 = (W)1 << phase;
+        bit0 = (W)((W)1 << phase);
     }
-    // leave the table clean: every set bit belongs to one of the bytes still in the window
+    if (j0 < n) {  // last n % 16 columns: the same column step, rolled, bytes shifted out of the chunk's words
+        sa.take(aw);
+        sb.take(bw);
+        tops7 = (W)((W)gather_bits16(aw, 7) * bit0);
+        if (PLANES == 2) tops6 = (W)((W)gather_bits16(aw, 6) * bit0);
+#pragma unroll
+        for (int w = 0; w < 4; w++) aw[w] &= CMASK;
+        uint32_t ea[4] = {aw[0], aw[1], aw[2], aw[3]};
+        uint32_t lv[4] = {ring[0], ring[1], ring[2], ring[3]};
+        for (int u = 0; u < n - j0; u++) {
+            const uint32_t bch = bw[0] & 0xffu;
+            column((W)(0u - (W)(bch >> 7)), (W)(0u - (W)((bch >> 6) & 1u)), bch & (CMASK & 0xffu), lv[0] & 0xffu,
+                   ea[0] & 0xffu, (W)(bit0 << u), phase + (uint32_t)u);
+#pragma unroll
+            for (int w = 0; w < 3; w++) {
+                bw[w] = funnel_r(bw[w], bw[w + 1], 8);
+                ea[w] = funnel_r(ea[w], ea[w + 1], 8);
+                lv[w] = funnel_r(lv[w], lv[w + 1], 8);
+            }
+            bw[3] >>= 8;
+            ea[3] >>= 8;
+            lv[3] >>= 8;
+        }
+        matches += (uint32_t)(acc >> e);
+    }
+    // leave the table clean: every set bit belongs to a byte of the ring or of the last chunk taken
 #pragma unroll
     for (int t = 0; t < BITS; t++) tab_at<W>(tab, byte_of(ring[t >> 2], t & 3), pitch_log2) = 0;
+#pragma unroll
+    for (int t = 0; t < 16; t++) tab_at<W>(tab, byte_of(aw[t >> 2], t & 3), pitch_log2) = 0;
     return (uint32_t)diff + (uint32_t)n - matches;
 }
 
