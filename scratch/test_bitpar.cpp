@@ -39,13 +39,13 @@ int main(int argc, char** argv) {
             orc_costs c = {1, 1, 0, (uint8_t)trans};
             uint32_t want = orc_levenshtein_naive_k_with_opts(a, la, b, lb, k, c, NULL, NULL);
             static uint32_t tab[128];
-            uint32_t got2 = (it & 1) ? (trans ? bitpar::pair_unit_costs_tab<true,1,uint32_t>(a, la, b, lb, k, (uint8_t*)tab, 2) : bitpar::pair_unit_costs_tab<false,1,uint32_t>(a, la, b, lb, k, (uint8_t*)tab, 2)) : (trans ? bitpar::pair_unit_costs_tab<true,2,uint32_t>(a, la, b, lb, k, (uint8_t*)tab, 2) : bitpar::pair_unit_costs_tab<false,2,uint32_t>(a, la, b, lb, k, (uint8_t*)tab, 2));
+            uint32_t got2 = (it & 1) ? (trans ? bitpar::pair_unit_costs_tab<true,1,uint32_t>(a, la, b, lb, k, (uint8_t*)tab, 4) : bitpar::pair_unit_costs_tab<false,1,uint32_t>(a, la, b, lb, k, (uint8_t*)tab, 4)) : (trans ? bitpar::pair_unit_costs_tab<true,2,uint32_t>(a, la, b, lb, k, (uint8_t*)tab, 4) : bitpar::pair_unit_costs_tab<false,2,uint32_t>(a, la, b, lb, k, (uint8_t*)tab, 4));
             { static uint16_t tab16[128]; uint32_t k16 = rng() % (trans ? 15 : 16); uint32_t want16 = orc_levenshtein_naive_k_with_opts(a, la, b, lb, k16, c, NULL, NULL);
-              uint32_t got16 = trans ? bitpar::pair_unit_costs_tab<true,1,uint16_t>(a, la, b, lb, k16, (uint8_t*)tab16, 1) : bitpar::pair_unit_costs_tab<false,1,uint16_t>(a, la, b, lb, k16, (uint8_t*)tab16, 1);
+              uint32_t got16 = trans ? bitpar::pair_unit_costs_tab<true,1,uint16_t>(a, la, b, lb, k16, (uint8_t*)tab16, 2) : bitpar::pair_unit_costs_tab<false,1,uint16_t>(a, la, b, lb, k16, (uint8_t*)tab16, 2);
               for (int q = 0; q < 128; q++) if (tab16[q]) { printf("table16 not clean\n"); bad++; tab16[q] = 0; }
               if (got16 != want16) { if (bad++ < 10) printf("TAB16 MISMATCH trans=%d k=%u la=%d lb=%d want=%u got=%u\n", trans, k16, la, lb, want16, got16); } }
             { static uint64_t tab64[64]; uint32_t k64 = rng() % (trans ? 63 : 64); uint32_t want64 = orc_levenshtein_naive_k_with_opts(a, la, b, lb, k64, c, NULL, NULL);
-              uint32_t got64 = trans ? bitpar::pair_unit_costs_tab<true,2,uint64_t>(a, la, b, lb, k64, (uint8_t*)tab64, 3) : bitpar::pair_unit_costs_tab<false,2,uint64_t>(a, la, b, lb, k64, (uint8_t*)tab64, 3);
+              uint32_t got64 = trans ? bitpar::pair_unit_costs_tab<true,2,uint64_t>(a, la, b, lb, k64, (uint8_t*)tab64, 8) : bitpar::pair_unit_costs_tab<false,2,uint64_t>(a, la, b, lb, k64, (uint8_t*)tab64, 8);
               for (int q = 0; q < 64; q++) if (tab64[q]) { printf("table64 not clean\n"); bad++; tab64[q] = 0; }
               if (got64 != want64) { if (bad++ < 10) printf("TAB64 MISMATCH trans=%d k=%u la=%d lb=%d want=%u got=%u\n", trans, k64, la, lb, want64, got64); } }
             for (int q = 0; q < 128; q++) if (tab[q]) { printf("table not clean\n"); bad++; tab[q] = 0; }

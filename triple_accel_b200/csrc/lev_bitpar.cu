@@ -45,13 +45,13 @@ __global__ void __launch_bounds__(128) lev_bitpar_tab_kernel(const uint8_t *__re
     for (uint32_t q = threadIdx.x; q < (128u >> (PLANES - 1)) * nt; q += nt) tabs[q] = 0;
     __syncthreads();
     uint8_t *tab = (uint8_t *)(tabs + threadIdx.x);
-    const uint32_t pitch_log2 = 31u - (uint32_t)__clz((int)(nt * (uint32_t)sizeof(W)));  // blockDim is a power of two
+    const uint32_t pitch = nt * (uint32_t)sizeof(W);  // bytes between consecutive entries of one thread
     const size_t total = (size_t)gridDim.x * nt;
     for (size_t w = (size_t)blockIdx.x * nt + threadIdx.x; w < n; w += total) {
         const size_t pair = idx ? (size_t)idx[w] : w;
         const uint64_t a0 = a_off[pair], a1 = a_off[pair + 1];
         const uint64_t b0 = b_off[pair], b1 = b_off[pair + 1];
-        out[pair] = bitpar::pair_unit_costs_tab<TRANS, PLANES, W>(a + a0, a1 - a0, b + b0, b1 - b0, k, tab, pitch_log2);
+        out[pair] = bitpar::pair_unit_costs_tab<TRANS, PLANES, W>(a + a0, a1 - a0, b + b0, b1 - b0, k, tab, pitch);
     }
 }
 

@@ -208,10 +208,11 @@ TA_HD uint32_t distance32(const uint8_t *a, int m, const uint8_t *b, int n, uint
 // clears the bit of the byte that leaves and sets the same bit position for the byte that enters (two read-modify-
 // writes), so a column costs  Eq = rotr(tab[b & 0x7f] & ~(A7 ^ topmask(b)), u mod 32)  -- one LDS, one LOP3, one
 // funnel shift -- instead of 8 SWAR compares.  The table must be all-zero on entry and is left all-zero on exit.
-// `tab` points at this thread's entry 0; entry c lives `c << pitch_log2` BYTES further (pitch = sizeof(W) * threads).
+// `tab` points at this thread's entry 0; entry c lives c * pitch BYTES further (pitch = sizeof(W) * threads).  The
+// address is one multiply-add (IMAD, FMA pipe) -- a shift + add would cost an extra ALU-pipe slot per access.
 template <typename W>
-TA_HD W &tab_at(uint8_t *tab, uint32_t c, uint32_t pitch_log2) {
-    return *(W *)(tab + ((size_t)c << pitch_log2));
+TA_HD W &tab_at(uint8_t *tab, uint32_t c, uint32_t pitch) {
+    return *(W *)(tab + c * pitch);
 }
 TA_HD uint32_t byte_of(uint32_t w, int t) {  // byte t of w, zero-extended (one PRMT)
     return prmt(w, 0u, 0x4440u | (uint32_t)t);
@@ -270,7 +271,7 @@ TA_HD uint32_t popc_w(uint32_t x) {
 //   PLANES = 1: 128 entries (7-bit classes) + the A7 plane;  PLANES = 2: 64 entries (6-bit classes) + A6, A7.
 template <bool TRANS, int PLANES, typename W>
 TA_HD uint32_t distance_tab(const uint8_t *a, int m, const uint8_t *b, int n, uint32_t max_k, uint8_t *tab,
-                            const uint32_t pitch_log2) {
+                            const uint32_t pitch) {
     constexpr int BITS = 8 * (int)sizeof(W);
     constexpr int RING = BITS / 4;  // words holding the window's bytes
     constexpr uint32_t CMASK = PLANES == 1 ? 0x7f7f7f7fu : 0x3f3f3f3fu;
@@ -301,7 +302,7 @@ TA_HD uint32_t distance_tab(const uint8_t *a, int m, const uint8_t *b, int n, ui
 #pragma unroll
         for (int w = 0; w < RING; w++) ring[w] = x[w] & CMASK;
 #pragma unroll
-        for (int t = 0; t < BITS; t++) tab_at<W>(tab, byte_of(ring[t >> 2], t & 3), pitch_log2) |= (W)((W)1 << t);
+        for (int t = 0; t < BITS; t++) tab_at<W>(tab, byte_of(ring[t >> 2], t & 3), pitch) |= (W)((W)1 << t);
     }
 
     const W ones = (W) ~(W)0;
@@ -318,10 +319,12 @@ TA_HD uint32_t distance_tab(const uint8_t *a, int m, const uint8_t *b, int n, ui
     // one DP column: b7m/b6m = all-ones iff the text byte has bit 7/6 set, bcls = its class bits, lv/en = classes of
     // the pattern bytes that leave/enter the window after this column, bit = their circular position, rot = the
     // circular position of window row 0
-    auto column = [&](W b7m, W b6m, uint32_t bcls, uint32_t lv, uint32_t en, W bit, uint32_t rot) {
-        W miss = (W)(A7 ^ b7m);  // rows whose plane bits differ from the text byte's
-        if (PLANES == 2) miss |= (W)(A6 ^ b6m);
-        const W raw = (W)(tab_at<W>(tab, bcls, pitch_log2) & ~miss);
+    // (a7v/a6v = the planes as of this column; upd = false when the caller derives them itself)
+    auto column = [&](W b7m, W b6m, uint32_t bcls, uint32_t lv, uint32_t en, W bit, uint32_t rot, W a7v, W a6v,
+                      const bool upd) {
+        W miss = (W)(a7v ^ b7m);  // rows whose plane bits differ from the text byte's
+        if (PLANES == 2) miss |= (W)(a6v ^ b6m);
+        const W raw = (W)(tab_at<W>(tab, bcls, pitch) & ~miss);
         const W Eq = rotr<W>(raw, rot);
         W D0 = (W)((((Eq & VP) + VP) ^ VP) | Eq | VN);
         if (TRANS) {
@@ -335,10 +338,12 @@ TA_HD uint32_t distance_tab(const uint8_t *a, int m, const uint8_t *b, int n, ui
         VN = (W)(X & HP);
         VP = (W)(HN | ~(X | HP));
         acc += (HistT)(D0 & emask);
-        tab_at<W>(tab, lv, pitch_log2) &= (W)~bit;
-        tab_at<W>(tab, en, pitch_log2) |= bit;
-        A7 = (W)((A7 & ~bit) | (tops7 & bit));
-        if (PLANES == 2) A6 = (W)((A6 & ~bit) | (tops6 & bit));
+        tab_at<W>(tab, lv, pitch) &= (W)~bit;
+        tab_at<W>(tab, en, pitch) |= bit;
+        if (upd) {
+            A7 = (W)((A7 & ~bit) | (tops7 & bit));
+            if (PLANES == 2) A6 = (W)((A6 & ~bit) | (tops6 & bit));
+        }
     };
 
     uint32_t aw[4] = {0, 0, 0, 0}, bw[4], bc[4];
@@ -354,10 +359,25 @@ TA_HD uint32_t distance_tab(const uint8_t *a, int m, const uint8_t *b, int n, ui
             bc[w] = bw[w] & CMASK;
         }
 #pragma unroll
-        for (int u = 0; u < 16; u++)
-            column(bit_mask_of<W>(bw[u >> 2], u & 3, 7), PLANES == 2 ? bit_mask_of<W>(bw[u >> 2], u & 3, 6) : (W)0,
-                   byte_of(bc[u >> 2], u & 3), byte_of(ring[u >> 2], u & 3), byte_of(aw[u >> 2], u & 3),
-                   (W)(bit0 << u), phase + (uint32_t)u);
+        for (int u = 0; u < 16; u++) {
+            if (BITS == 16) {
+                // 16-row window: a chunk is one full turn of the circular numbering, so the planes as of column u
+                // are a constant-mask select between the chunk-start planes and the entering bytes' planes
+                const W lm = (W)((1u << u) - 1u);
+                column(bit_mask_of<W>(bw[u >> 2], u & 3, 7), PLANES == 2 ? bit_mask_of<W>(bw[u >> 2], u & 3, 6) : (W)0,
+                       byte_of(bc[u >> 2], u & 3), byte_of(ring[u >> 2], u & 3), byte_of(aw[u >> 2], u & 3),
+                       (W)(1u << u), (uint32_t)u, (W)((A7 & ~lm) | (tops7 & lm)),
+                       PLANES == 2 ? (W)((A6 & ~lm) | (tops6 & lm)) : (W)0, false);
+            } else {
+                column(bit_mask_of<W>(bw[u >> 2], u & 3, 7), PLANES == 2 ? bit_mask_of<W>(bw[u >> 2], u & 3, 6) : (W)0,
+                       byte_of(bc[u >> 2], u & 3), byte_of(ring[u >> 2], u & 3), byte_of(aw[u >> 2], u & 3),
+                       (W)(bit0 << u), phase + (uint32_t)u, A7, A6, true);
+            }
+        }
+        if (BITS == 16) {
+            A7 = tops7;
+            A6 = tops6;
+        }
         matches += (uint32_t)(acc >> e);
         acc = 0;
 #pragma unroll
@@ -379,7 +399,7 @@ TA_HD uint32_t distance_tab(const uint8_t *a, int m, const uint8_t *b, int n, ui
         for (int u = 0; u < n - j0; u++) {
             const uint32_t bch = bw[0] & 0xffu;
             column((W)(0u - (W)(bch >> 7)), (W)(0u - (W)((bch >> 6) & 1u)), bch & (CMASK & 0xffu), lv[0] & 0xffu,
-                   ea[0] & 0xffu, (W)(bit0 << u), phase + (uint32_t)u);
+                   ea[0] & 0xffu, (W)(bit0 << u), phase + (uint32_t)u, A7, A6, true);
 #pragma unroll
             for (int w = 0; w < 3; w++) {
                 bw[w] = funnel_r(bw[w], bw[w + 1], 8);
@@ -394,15 +414,15 @@ TA_HD uint32_t distance_tab(const uint8_t *a, int m, const uint8_t *b, int n, ui
     }
     // leave the table clean: every set bit belongs to a byte of the ring or of the last chunk taken
 #pragma unroll
-    for (int t = 0; t < BITS; t++) tab_at<W>(tab, byte_of(ring[t >> 2], t & 3), pitch_log2) = 0;
+    for (int t = 0; t < BITS; t++) tab_at<W>(tab, byte_of(ring[t >> 2], t & 3), pitch) = 0;
 #pragma unroll
-    for (int t = 0; t < 16; t++) tab_at<W>(tab, byte_of(aw[t >> 2], t & 3), pitch_log2) = 0;
+    for (int t = 0; t < 16; t++) tab_at<W>(tab, byte_of(aw[t >> 2], t & 3), pitch) = 0;
     return (uint32_t)diff + (uint32_t)n - matches;
 }
 
 template <bool TRANS, int PLANES, typename W>
 TA_HD uint32_t pair_unit_costs_tab(const uint8_t *a, uint64_t a_len, const uint8_t *b, uint64_t b_len, uint32_t k,
-                                   uint8_t *tab, const uint32_t pitch_log2) {
+                                   uint8_t *tab, const uint32_t pitch) {
     if (a_len > b_len) {
         const uint8_t *tp = a;
         a = b;
@@ -416,7 +436,7 @@ TA_HD uint32_t pair_unit_costs_tab(const uint8_t *a, uint64_t a_len, const uint8
     const uint32_t max_k = k < (uint32_t)n ? k : (uint32_t)n;
     if (diff > max_k) return 0xFFFFFFFFu;
     if (m == 0) return (uint32_t)n;
-    const uint32_t d = distance_tab<TRANS, PLANES, W>(a, m, b, n, max_k, tab, pitch_log2);
+    const uint32_t d = distance_tab<TRANS, PLANES, W>(a, m, b, n, max_k, tab, pitch);
     return d <= max_k ? d : 0xFFFFFFFFu;
 }
 
