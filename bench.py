@@ -35,8 +35,8 @@ WORKLOADS = {
                        "levenshtein_simd_k k=16, 1M pairs len=128, unit costs, set M (b = a after U[0,16] edits)"),
     "rdamerau_k16_len512": ("lev_k", 1_000_000, 512, 16, (1, 1, 0, 1),
                             "RDAMERAU_COSTS k=16, 1M pairs len=512, set M (U[0,16] edits incl. swaps)"),
-    "lev_k16_len4096": ("lev_k", 65_536, 4096, 16, (1, 1, 0, 0),
-                        "levenshtein_simd_k k=16, 64Ki pairs len=4096, unit costs, set M"),
+    "lev_k16_len4096": ("lev_k", 262_144, 4096, 16, (1, 1, 0, 0),
+                        "levenshtein_simd_k k=16, 256Ki pairs len=4096, unit costs, set M"),
     "affine_k16_len128": ("lev_k", 1_000_000, 128, 16, (2, 1, 3, 0),
                           "levenshtein_simd_k_with_opts k=16, 1M pairs len=128, EditCosts(2,1,3,None) (general kernel)"),
     "lev_k60_len1024": ("lev_k", 262_144, 1024, 60, (1, 1, 0, 0),
