@@ -250,7 +250,8 @@ def test_lev_k_random_short(eng, costs):
 
 
 @pytest.mark.parametrize("length,k", [(128, 8), (128, 16), (512, 16), (300, 30), (1024, 30), (100, 64), (77, 200),
-                                      (2000, 5), (300, 45), (1024, 63), (600, 62), (200, 32)])
+                                      (2000, 5), (300, 45), (1024, 63), (600, 62), (200, 32),
+                                      (130, 15), (131, 17), (200, 24), (96, 25), (47, 23)])
 @pytest.mark.parametrize("costs", [(1, 1, 0, 0), (1, 1, 0, 1), (2, 1, 3, 0), (2, 2, 1, 3)], ids=str)
 def test_lev_k_mutated(eng, length, k, costs):
     """the BASELINE shapes at reduced batch size: mutated pairs (within k) and unrelated pairs (None)"""
@@ -604,12 +605,18 @@ SEARCH_TESTS = ("test_search_random or test_search_planted or test_kat_search or
 @pytest.mark.parametrize("env,select", [
     ({"TA_FORCE_BAND": "1"}, LEV_TESTS),
     ({"TA_BITPAR": "simd"}, LEV_TESTS),
-    ({"TA_BITPAR_BITS": "32"}, LEV_TESTS),
+    ({"TA_BITPAR": "tab"}, LEV_TESTS),
+    ({"TA_BITPAR": "tab", "TA_BITPAR_BITS": "32"}, LEV_TESTS),
+    ({"TA_BLK_PLANES": "0", "TA_BLK_MAD": "7"}, LEV_TESTS),
+    ({"TA_BLK_PLANES": "1", "TA_BLK_MAD": "3", "TA_BLK_C": "8"}, LEV_TESTS),
+    ({"TA_BLK_PLANES": "0", "TA_BLK_MAD": "0", "TA_BLK_C": "8", "TA_BITPAR_THREADS": "64"}, LEV_TESTS),
     ({"TA_BITPAR": "tab", "TA_BITPAR_BITS": "32", "TA_BITPAR_PLANES": "2", "TA_BITPAR_THREADS": "64"}, LEV_TESTS),
     ({"TA_NO_SEARCH_FILTER": "1", "TA_SEARCH_KERNEL": "thread"}, SEARCH_TESTS),
     ({"TA_NO_SEARCH_FILTER": "1", "TA_SEARCH_KERNEL": "wave"}, SEARCH_TESTS),
     ({"TA_SEARCH_KERNEL": "thread"}, SEARCH_TESTS),
-], ids=["general-band-kernel", "bitpar-simd-kernel", "bitpar-table-32bit-on-narrow-bands",
+], ids=["general-band-kernel", "bitpar-simd-kernel", "bitpar-sliding-table-kernel",
+        "bitpar-sliding-table-32bit-on-narrow-bands", "bitpar-block-table-256-entries-mad",
+        "bitpar-block-table-8-blocks-mad", "bitpar-block-table-256-entries-8-blocks",
         "bitpar-table-2plane-kernel", "search-thread-kernel-nofilter", "search-wave-kernel-nofilter",
         "search-thread-kernel-filter"])
 def test_every_kernel_variant_forced(env, select):

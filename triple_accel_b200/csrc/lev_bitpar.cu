@@ -13,6 +13,10 @@
 #include "lev_bitpar_core.cuh"
 #include "ta_common.cuh"
 
+// defaults of the block-table kernel (measured on B200, profiles/README.md)
+#define TA_BLK_DEFAULT_PLANES 1
+#define TA_BLK_DEFAULT_MAD 0
+
 namespace {
 
 template <bool TRANS>
@@ -55,6 +59,48 @@ __global__ void __launch_bounds__(128) lev_bitpar_tab_kernel(const uint8_t *__re
     }
 }
 
+
+// Block-table variant (lev_bitpar_core.cuh: distance_blk), bands of <= 33 - C diagonals.  Same table layout
+// ([entry][thread] u32, 128 or 256 entries per thread).
+template <bool TRANS, int PLANES, int C, int MAD>
+__global__ void __launch_bounds__(256) lev_bitpar_blk_kernel(const uint8_t *__restrict__ a,
+                                                             const uint64_t *__restrict__ a_off,
+                                                             const uint8_t *__restrict__ b,
+                                                             const uint64_t *__restrict__ b_off,
+                                                             const uint32_t *__restrict__ idx, size_t n, uint32_t k,
+                                                             uint32_t *__restrict__ out) {
+    extern __shared__ __align__(16) uint8_t tabs_raw[];
+    uint32_t *tabs = (uint32_t *)tabs_raw;
+    const uint32_t nt = blockDim.x;
+    for (uint32_t q = threadIdx.x; q < (PLANES ? 128u : 256u) * nt; q += nt) tabs[q] = 0;
+    __syncthreads();
+    uint8_t *tab = (uint8_t *)(tabs + threadIdx.x);
+    const uint32_t pitch = nt * 4u;
+    const size_t total = (size_t)gridDim.x * nt;
+    for (size_t w = (size_t)blockIdx.x * nt + threadIdx.x; w < n; w += total) {
+        const size_t pair = idx ? (size_t)idx[w] : w;
+        const uint64_t a0 = a_off[pair], a1 = a_off[pair + 1];
+        const uint64_t b0 = b_off[pair], b1 = b_off[pair + 1];
+        out[pair] = bitpar::pair_unit_costs_blk<TRANS, PLANES, C, MAD>(a + a0, a1 - a0, b + b0, b1 - b0, k, tab, pitch);
+    }
+}
+
+typedef void (*lev_kern_t)(const uint8_t *, const uint64_t *, const uint8_t *, const uint64_t *, const uint32_t *,
+                           size_t, uint32_t, uint32_t *);
+template <bool TRANS, int C, int PLANES>
+lev_kern_t pick_blk_mad(int mad) {
+    switch (mad) {
+        case 1: return lev_bitpar_blk_kernel<TRANS, PLANES, C, 1>;
+        case 3: return lev_bitpar_blk_kernel<TRANS, PLANES, C, 3>;
+        case 7: return lev_bitpar_blk_kernel<TRANS, PLANES, C, 7>;
+        default: return lev_bitpar_blk_kernel<TRANS, PLANES, C, 0>;
+    }
+}
+template <bool TRANS, int C>
+lev_kern_t pick_blk(int planes, int mad) {
+    return planes ? pick_blk_mad<TRANS, C, 1>(mad) : pick_blk_mad<TRANS, C, 0>(mad);
+}
+
 }  // namespace
 
 bool ta_bitpar_can_handle(uint32_t k, ta_costs c, uint32_t max_len) {
@@ -82,6 +128,34 @@ int ta_launch_lev_bitpar(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, c
     static const int env_threads = getenv("TA_BITPAR_THREADS") ? atoi(getenv("TA_BITPAR_THREADS")) : 0;
     static const int env_planes = getenv("TA_BITPAR_PLANES") ? atoi(getenv("TA_BITPAR_PLANES")) : 0;
     static const int env_bits = getenv("TA_BITPAR_BITS") ? atoi(getenv("TA_BITPAR_BITS")) : 0;
+    // block-table kernel (default whenever the band fits 33 - C diagonals): TA_BLK_PLANES=0|1 (256 entries / 128
+    // entries + top-bit plane), TA_BLK_MAD=0|1|3|7 (which shifts run as multiply-adds on the FMA pipe), TA_BLK_C=8
+    // forces 8-position blocks on narrow bands
+    static const int blk_planes = getenv("TA_BLK_PLANES") ? atoi(getenv("TA_BLK_PLANES")) : TA_BLK_DEFAULT_PLANES;
+    static const int blk_mad = getenv("TA_BLK_MAD") ? atoi(getenv("TA_BLK_MAD")) : TA_BLK_DEFAULT_MAD;
+    static const int blk_c = getenv("TA_BLK_C") ? atoi(getenv("TA_BLK_C")) : 0;
+    {
+        const uint32_t kk = k < max_len ? k : max_len;
+        const uint32_t wmax = kk + 1 + (costs.transpose ? 1u : 0u);  // widest band any pair of the batch can have
+        const bool use_blk = !(variant && (variant[0] == 's' || variant[0] == 't')) && wmax <= 25;
+        if (use_blk) {
+            const int C = (wmax <= 17 && blk_c != 8) ? 16 : 8;
+            const int nt = env_threads ? env_threads : (blk_planes ? 128 : 224);
+            const size_t smem = (size_t)(blk_planes ? 128 : 256) * nt * 4;
+            const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (size_t)(ctx->smem_optin + 1024) / (smem + 1024)));
+            const unsigned blocks = (unsigned)std::min<size_t>((n + nt - 1) / nt, (size_t)ctx->sm_count * per_sm);
+            lev_kern_t kern;
+            if (C == 16)
+                kern = costs.transpose ? pick_blk<true, 16>(blk_planes, blk_mad) : pick_blk<false, 16>(blk_planes, blk_mad);
+            else
+                kern = costs.transpose ? pick_blk<true, 8>(blk_planes, blk_mad) : pick_blk<false, 8>(blk_planes, blk_mad);
+            TA_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<blocks, nt, smem, st>>>(a, a_off, b, b_off, idx, n, k, out);
+            ctx->launches++;
+            TA_CUDA(ctx, cudaGetLastError());
+            return TA_OK;
+        }
+    }
     const bool wide = !fits32(k, costs, max_len);
     if (wide || !(variant && variant[0] == 's')) {
         // window width: the narrowest that holds the band (16-bit entries halve the shared memory per thread and
@@ -136,7 +210,8 @@ template <typename W, bool TRANS>
 __global__ void __launch_bounds__(128) search_filter_kernel(const uint8_t *__restrict__ needle, uint32_t N,
                                                             const uint8_t *__restrict__ hay,
                                                             const uint64_t *__restrict__ hay_off, size_t n, uint32_t k,
-                                                            uint32_t *__restrict__ flags) {
+                                                            uint32_t *__restrict__ idx_out,
+                                                            uint32_t *__restrict__ counter) {
     __shared__ W peq[256];
     for (int c = threadIdx.x; c < 256; c += blockDim.x) peq[c] = 0;
     __syncthreads();
@@ -212,50 +287,38 @@ __global__ void __launch_bounds__(128) search_filter_kernel(const uint8_t *__res
             hit |= (x >= seg_begin) & (x < seg_end) & (score <= k);
         }
         if (hit) {
-            flags[h * gridDim.y + blockIdx.y] = 1;  // segment (h, s) contains a match end
+            // segment (h, s) contains a match end: append its code (rare event, one atomic)
+            idx_out[atomicAdd(counter, 1u)] = (uint32_t)(h * gridDim.y + blockIdx.y);
             return;
         }
     }
 }
 
-__global__ void collect_flagged_kernel(const uint32_t *__restrict__ flags, size_t n, uint32_t *__restrict__ idx_out,
-                                       uint32_t *__restrict__ counter) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        if (flags[i]) idx_out[atomicAdd(counter, 1u)] = (uint32_t)i;
-}
-
 }  // namespace
 
-// flags the 512-byte haystack segments that contain at least one end position of unit-cost distance <= k and writes
-// their codes (haystack * segs + segment, unordered) to idx_out, the count to *counter; *segs_out = segments per
-// haystack.  Needs needle_len in [1, 64], n * segs < 2^32; max_hay = longest haystack.
+// appends the codes (haystack * segs + segment, unordered) of the 512-byte haystack segments that contain at least
+// one end position of unit-cost distance <= k to idx_out, counting them in *counter (must be zero on entry);
+// *segs_out = segments per haystack.  Needs needle_len in [1, 64], n * segs < 2^32; max_hay = longest haystack.
 int ta_launch_search_filter(ta_ctx *ctx, const uint8_t *needle_dev, uint32_t needle_len, const uint8_t *hay,
                             const uint64_t *hay_off, size_t n, uint64_t max_hay, uint32_t k, bool transpose,
-                            uint32_t *flags, uint32_t *idx_out, uint32_t *counter, uint32_t *segs_out,
-                            cudaStream_t st) {
+                            uint32_t *idx_out, uint32_t *counter, uint32_t *segs_out, cudaStream_t st) {
     if (needle_len == 0 || needle_len > 64) return TA_ERR_TOO_LARGE;
     const uint64_t segs = max_hay ? (max_hay + FILTER_SEG - 1) / FILTER_SEG : 1;
     *segs_out = (uint32_t)segs;
     if (n == 0 || max_hay == 0) return TA_OK;
     if (segs > 65535 || (uint64_t)n * segs > 0xFFFFFFF0ull) return TA_ERR_TOO_LARGE;
-    TA_CUDA(ctx, cudaMemsetAsync(flags, 0, n * segs * sizeof(uint32_t), st));
     const dim3 grid((unsigned)((n + 127) / 128), (unsigned)segs);
     if (needle_len <= 32) {
         if (transpose)
-            search_filter_kernel<uint32_t, true><<<grid, 128, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, k, flags);
+            search_filter_kernel<uint32_t, true><<<grid, 128, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, k, idx_out, counter);
         else
-            search_filter_kernel<uint32_t, false><<<grid, 128, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, k, flags);
+            search_filter_kernel<uint32_t, false><<<grid, 128, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, k, idx_out, counter);
     } else {
         if (transpose)
-            search_filter_kernel<uint64_t, true><<<grid, 128, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, k, flags);
+            search_filter_kernel<uint64_t, true><<<grid, 128, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, k, idx_out, counter);
         else
-            search_filter_kernel<uint64_t, false><<<grid, 128, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, k, flags);
+            search_filter_kernel<uint64_t, false><<<grid, 128, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, k, idx_out, counter);
     }
-    ctx->launches++;
-    TA_CUDA(ctx, cudaGetLastError());
-    const size_t items = n * segs;
-    const unsigned cblocks = (unsigned)((items + 255) / 256 < (size_t)ctx->sm_count * 8 ? (items + 255) / 256 : (size_t)ctx->sm_count * 8);
-    collect_flagged_kernel<<<cblocks, 256, 0, st>>>(flags, items, idx_out, counter);
     ctx->launches++;
     TA_CUDA(ctx, cudaGetLastError());
     return TA_OK;

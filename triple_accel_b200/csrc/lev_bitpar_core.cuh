@@ -49,7 +49,12 @@ TA_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 #else
     uint64_t v = ((uint64_t)b << 32) | a;
     uint32_t r = 0;
-    for (int i = 0; i < 4; i++) r |= (uint32_t)((v >> (8 * ((sel >> (4 * i)) & 7))) & 0xff) << (8 * i);
+    for (int i = 0; i < 4; i++) {
+        const uint32_t nib = (sel >> (4 * i)) & 15u;
+        uint32_t byte = (uint32_t)((v >> (8 * (nib & 7))) & 0xff);
+        if (nib & 8u) byte = (byte & 0x80u) ? 0xffu : 0u;  // default mode: bit 3 replicates the byte's sign bit
+        r |= byte << (8 * i);
+    }
     return r;
 #endif
 }
@@ -418,6 +423,246 @@ TA_HD uint32_t distance_tab(const uint8_t *a, int m, const uint8_t *b, int n, ui
 #pragma unroll
     for (int t = 0; t < 16; t++) tab_at<W>(tab, byte_of(aw[t >> 2], t & 3), pitch) = 0;
     return (uint32_t)diff + (uint32_t)n - matches;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// distance_blk: the match-table recurrence with BLOCK-wise table maintenance (bands of <= 33 - C diagonals).
+//
+// Only the band's W rows have to see their exact match flags; every other row of the 32-row window merely has to
+// stay an upper bound of the true DP, i.e. its Eq bits may be dropped but never invented.  So the table does not
+// have to follow the window column by column.  It is a 32-position circular frame cut into blocks of C positions
+// (C = 16: the two halves of an entry; C = 8: its four bytes) and holds stream bytes [g, g + 32) for the C columns
+// of the chunk that starts at stream position g.  Inside a chunk nothing is written; a column's Eq is
+//     rotr(tab[class(b)] [& plane], (g + u') mod 32)
+// Between chunks the block that left the window is ZEROED BY VALUE -- a sub-word store of 0 to the entry of each of
+// its bytes: no read, no mask, because every bit of that sub-word belongs to the same block -- and the block that
+// enters is OR-ed in.  W <= 33 - C guarantees that the band's rows of every column of the chunk lie inside
+// [g, g + 32).  In column u' of a chunk the rotation wraps the u' bytes that already left the window into rows
+// p >= 32 - u' >= 33 - C, where they can INVENT matches.  That is harmless: with unit costs every change of
+// diagonal costs 1, the path starts on row dhi and ends on row e, so a path through such a cell costs at least
+// (p - dhi) + (p - e) >= 66 - 2C - (W - 1) >= 34 - C > max_k (max_k <= W <= 33 - C); it can neither lower a distance
+// that is <= max_k nor pull one that is > max_k below the threshold.  Chunks are unrolled 32 columns deep so that every rotation, mask and
+// bit is an immediate.  The last n mod 16 columns slide the table column by column like distance_tab.
+//   PLANES = 1: 128 entries (7-bit classes) + the A7 plane;  PLANES = 0: 256 entries, no plane.
+//   MAD (bit mask): which shifts are issued as multiply-adds on the FMA pipe instead of ALU-pipe instructions:
+//   1 = the match count (acc = hi32((D0 << (31 - e)) * 2) + acc, two IMADs instead of LOP3 + IADD3),
+//   2 = X = D0 >> 1 as hi32(D0 * 2^31),  4 = the table rotation as hi32(raw * 2^(32-s)) | lo32(raw * 2^(32-s)), the
+//   OR folding into the recurrence's LOP3s.  `tab` = the thread's entry 0, `pitch` = bytes between entries.
+// multiply-add forms of shifts: IMAD / IMAD.HI run on the FMA pipe, which the recurrence leaves idle, whereas SHF /
+// LOP3 / PRMT share the (binding) ALU pipe
+TA_HD uint32_t mad_hi(uint32_t a, uint32_t b, uint32_t c) {  // high word of a * b, plus c
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32) + c;
+#endif
+}
+TA_HD uint32_t mul_lo(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("mul.lo.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+#else
+    return a * b;
+#endif
+}
+TA_HD uint8_t *blk_entry(uint8_t *tab, uint32_t w, int t, uint32_t pitch) { return tab + byte_of(w, t) * pitch; }
+// raw rotated right by the constant s (1..31) = hi | lo, both halves produced on the FMA pipe
+TA_HD void blk_rot_mad(uint32_t raw, uint32_t s, uint32_t one, uint32_t &hi, uint32_t &lo) {
+    const uint64_t p = (uint64_t)raw * (uint64_t)(one << (32 - s));  // `one` is an opaque 1: IMAD.SHL + IMAD.WIDE
+    hi = (uint32_t)(p >> 32);                                        // raw >> s
+    lo = (uint32_t)p;                                                // raw << (32 - s)
+}
+template <int V>
+struct IntC {
+    static constexpr int value = V;
+};
+
+template <bool TRANS, int PLANES, int C, int MAD>
+TA_HD uint32_t distance_blk(const uint8_t *a, int m, const uint8_t *b, int n, uint32_t max_k, uint8_t *tab,
+                            const uint32_t pitch) {
+    static_assert(C == 8 || C == 16, "block = a byte or a half of the entry");
+    static_assert(PLANES == 0 || PLANES == 1, "");
+    typedef uint32_t W;
+    constexpr uint32_t CMASK = PLANES == 1 ? 0x7f7f7f7fu : 0xffffffffu;
+    const int diff = n - m;
+    const int e = (int)((max_k - (uint32_t)diff) >> 1) + ((TRANS && ((max_k - (uint32_t)diff) & 1u)) ? 1 : 0);
+    const int dhi = diff + e;  // window row p of column j is matrix row i = j - dhi + p
+
+    Stream sa, sb;
+    sa.init((intptr_t)a - dhi, (uintptr_t)a, (uintptr_t)a + m - 1);
+    sb.init((intptr_t)b, (uintptr_t)b, (uintptr_t)b + n - 1);
+
+    // the table is all-zero on entry: reading it gives a 0 the compiler cannot see through (MAD variants)
+    const uint32_t opaque0 = MAD ? *(const volatile uint32_t *)tab : 0u;
+    uint32_t ring[8];  // class bits of the 32 stream bytes the table holds at a 16-column boundary
+    W A7 = 0;
+    {
+        uint32_t x[8];
+        sa.take(x);
+        sa.take(x + 4);
+        if (PLANES) A7 = gather_bits16(x, 7) | (gather_bits16(x + 4, 7) << 16);
+#pragma unroll
+        for (int w = 0; w < 8; w++) ring[w] = x[w] & CMASK;
+#pragma unroll
+        for (int t = 0; t < 32; t++) *(W *)blk_entry(tab, ring[t >> 2], t & 3, pitch) |= 1u << t;
+    }
+
+    W VP = dhi >= 32 ? 0u : (0xffffffffu << dhi);
+    W VN = ~VP;
+    W D0prev = 0xffffffffu, Eqprev = 0;
+    uint32_t matches = 0;
+    const W emask = 1u << e;
+    uint32_t acc = 0;
+    uint32_t aw[4] = {0, 0, 0, 0}, bw[4], bc[4];
+
+    // runtime copies of the multipliers (kept opaque so that the multiplies are not strength-reduced into shifts)
+    const uint32_t opaque1 = 1u | opaque0;
+    const uint32_t m_e = (MAD & 1) ? ((1u << (31 - e)) | opaque0) : 0u;       // moves bit e to bit 31
+    const uint32_t m_two = 2u | opaque0, m_half = 0x80000000u | opaque0;
+    // the recurrence for one column given its match word
+    auto step = [&](const W Eq) {
+        W D0 = (((Eq & VP) + VP) ^ VP) | Eq | VN;
+        if (TRANS) {
+            D0 |= ~D0prev & (Eq << 1) & (Eqprev >> 1);
+            D0prev = D0;
+            Eqprev = Eq;
+        }
+        const W HP = VN | ~(D0 | VP);
+        const W HN = D0 & VP;
+        const W X = (MAD & 2) ? mad_hi(D0, m_half, 0u) : (D0 >> 1);
+        VN = X & HP;
+        VP = HN | ~(X | HP);
+        if (MAD & 1)
+            acc = mad_hi(mul_lo(D0, m_e), m_two, acc);
+        else
+            acc += D0 & emask;
+    };
+    // 16 columns whose first column sits at circular position PH (0 or 16)
+    auto superstep = [&](auto phc) {
+        constexpr uint32_t PH = (uint32_t)decltype(phc)::value;
+        sa.take(aw);  // stream bytes [16 s + 32, 16 s + 48): they enter the table during this superstep
+        sb.take(bw);
+        W tops7 = 0;
+        if (PLANES) tops7 = gather_bits16(aw, 7) << PH;
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            aw[w] &= CMASK;
+            bc[w] = bw[w] & CMASK;
+        }
+#pragma unroll
+        for (int q = 0; q < 16 / C; q++) {
+#pragma unroll
+            for (int v = 0; v < C; v++) {
+                const int u = C * q + v;
+                W raw = *(const W *)blk_entry(tab, bc[u >> 2], u & 3, pitch);
+                if (PLANES) raw &= ~(A7 ^ prmt(bw[u >> 2], 0u, 0x8888u | (uint32_t)((u & 3) * 0x1111)));
+                const uint32_t sft = (PH + (uint32_t)u) & 31u;
+                if ((MAD & 4) && sft != 0) {
+                    uint32_t hi, lo;
+                    blk_rot_mad(raw, sft, opaque1, hi, lo);
+                    step(hi | lo);
+                } else {
+                    step(funnel_r(raw, raw, sft));
+                }
+            }
+            // the block of columns just done left the window: zero it by value, then OR the entering block in
+            const uint32_t pos = (PH + (uint32_t)(C * q)) & 31u;  // circular position of the block (a constant once unrolled)
+#pragma unroll
+            for (int t = C * q; t < C * q + C; t++) {
+                uint8_t *p = blk_entry(tab, ring[t >> 2], t & 3, pitch) + pos / 8;
+                if (C == 16)
+                    *(uint16_t *)p = 0;
+                else
+                    *p = 0;
+            }
+#pragma unroll
+            for (int t = C * q; t < C * q + C; t++)
+                *(W *)blk_entry(tab, aw[t >> 2], t & 3, pitch) |= 1u << ((PH + (uint32_t)t) & 31u);
+            if (PLANES) {
+                const W blk = (C == 16 ? 0xffffu : 0xffu) << pos;
+                A7 = (A7 & ~blk) | (tops7 & blk);
+            }
+        }
+        if (!(MAD & 1)) {
+            matches += acc >> e;
+            acc = 0;
+        }
+#pragma unroll
+        for (int w = 0; w < 4; w++) ring[w] = ring[w + 4];
+#pragma unroll
+        for (int w = 0; w < 4; w++) ring[4 + w] = aw[w];
+    };
+
+    int j0 = 0;
+    for (; j0 + 32 <= n; j0 += 32) {
+        superstep(IntC<0>());
+        superstep(IntC<16>());
+    }
+    uint32_t phase = 0;
+    if (j0 + 16 <= n) {
+        superstep(IntC<0>());
+        j0 += 16;
+        phase = 16;
+    }
+    if (j0 < n) {  // last n % 16 columns: slide the table column by column (exact clear + set), rolled
+        sa.take(aw);
+        sb.take(bw);
+        const W tops7 = PLANES ? (gather_bits16(aw, 7) << phase) : 0u;
+#pragma unroll
+        for (int w = 0; w < 4; w++) aw[w] &= CMASK;
+        uint32_t ea[4] = {aw[0], aw[1], aw[2], aw[3]};
+        uint32_t lv[4] = {ring[0], ring[1], ring[2], ring[3]};
+        for (int u = 0; u < n - j0; u++) {
+            const uint32_t bch = bw[0] & 0xffu;
+            W raw = *(const W *)blk_entry(tab, bch & (CMASK & 0xffu), 0, pitch);
+            if (PLANES) raw &= ~(A7 ^ (0u - (bch >> 7)));
+            const uint32_t rot = phase + (uint32_t)u;
+            step(funnel_r(raw, raw, rot));
+            const W bit = 1u << rot;
+            *(W *)blk_entry(tab, lv[0] & 0xffu, 0, pitch) &= ~bit;
+            *(W *)blk_entry(tab, ea[0] & 0xffu, 0, pitch) |= bit;
+            if (PLANES) A7 = (A7 & ~bit) | (tops7 & bit);
+#pragma unroll
+            for (int w = 0; w < 3; w++) {
+                bw[w] = funnel_r(bw[w], bw[w + 1], 8);
+                ea[w] = funnel_r(ea[w], ea[w + 1], 8);
+                lv[w] = funnel_r(lv[w], lv[w + 1], 8);
+            }
+            bw[3] >>= 8;
+            ea[3] >>= 8;
+            lv[3] >>= 8;
+        }
+    }
+    matches += (MAD & 1) ? acc : (acc >> e);
+    // leave the table clean: every set bit belongs to a byte of the ring or of the last chunk taken
+#pragma unroll
+    for (int t = 0; t < 32; t++) *(W *)blk_entry(tab, ring[t >> 2], t & 3, pitch) = 0;
+#pragma unroll
+    for (int t = 0; t < 16; t++) *(W *)blk_entry(tab, aw[t >> 2], t & 3, pitch) = 0;
+    return (uint32_t)diff + (uint32_t)n - matches;
+}
+
+template <bool TRANS, int PLANES, int C, int MAD>
+TA_HD uint32_t pair_unit_costs_blk(const uint8_t *a, uint64_t a_len, const uint8_t *b, uint64_t b_len, uint32_t k,
+                                   uint8_t *tab, const uint32_t pitch) {
+    if (a_len > b_len) {
+        const uint8_t *tp = a;
+        a = b;
+        b = tp;
+        const uint64_t tl = a_len;
+        a_len = b_len;
+        b_len = tl;
+    }
+    const int m = (int)a_len, n = (int)b_len;
+    const uint32_t diff = (uint32_t)(n - m);
+    const uint32_t max_k = k < (uint32_t)n ? k : (uint32_t)n;
+    if (diff > max_k) return 0xFFFFFFFFu;
+    if (m == 0) return (uint32_t)n;
+    const uint32_t d = distance_blk<TRANS, PLANES, C, MAD>(a, m, b, n, max_k, tab, pitch);
+    return d <= max_k ? d : 0xFFFFFFFFu;
 }
 
 template <bool TRANS, int PLANES, typename W>

@@ -23,8 +23,7 @@
 // implemented in lev_bitpar.cu: flags[i] = 1 iff haystack i has an end position with unit-cost distance <= k
 int ta_launch_search_filter(ta_ctx *ctx, const uint8_t *needle_dev, uint32_t needle_len, const uint8_t *hay,
                             const uint64_t *hay_off, size_t n, uint64_t max_hay, uint32_t k, bool transpose,
-                            uint32_t *flags, uint32_t *idx_out, uint32_t *counter, uint32_t *segs_out,
-                            cudaStream_t st);
+                            uint32_t *idx_out, uint32_t *counter, uint32_t *segs_out, cudaStream_t st);
 
 namespace {
 
@@ -42,6 +41,7 @@ struct SearchArgs {
                           // item covers only that TA_SEARCH_SEG-byte segment after a warm-up of `warm` bytes
     uint32_t warm;
     size_t n;
+    const uint32_t *n_dev;  // optional: the number of work items lives on the device (written by the pre-filter)
     uint32_t needle_len;
     uint32_t k;
     uint32_t mism, gap, sgap, tcost;
@@ -213,8 +213,11 @@ template <int C, bool TRANS>
 __global__ void __launch_bounds__(128) search_wave_kernel(const SearchArgs args) {
     const unsigned full = 0xffffffffu;
     const int t = threadIdx.x & 31;
-    const size_t w = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (w >= args.n) return;  // whole warp
+    // persistent warps: the item count may only exist on the device (pre-filter output), so the grid is sized from an
+    // upper bound and every warp strides over the items
+    const size_t n_items = args.n_dev ? (size_t)*args.n_dev : args.n;
+    const size_t n_warps = (size_t)gridDim.x * (blockDim.x >> 5);
+    for (size_t w = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < n_items; w += n_warps) {
     const uint32_t code = args.idx ? args.idx[w] : (uint32_t)w;
     const uint32_t hidx = args.segs ? code / args.segs : code;
     const uint64_t h0 = args.hay_off[hidx], h1 = args.hay_off[hidx + 1];
@@ -401,6 +404,7 @@ __global__ void __launch_bounds__(128) search_wave_kernel(const SearchArgs args)
             out_hgl = hgap_len;
         }
     }
+    }  // work items
 }
 
 size_t exact_smem_bytes(uint32_t needle_len, bool trans, int threads) {
@@ -409,31 +413,34 @@ size_t exact_smem_bytes(uint32_t needle_len, bool trans, int threads) {
 
 }  // namespace
 
-// Device phase: optional bit-parallel pre-filter, then the exact kernel on the surviving haystacks; returns every
-// end position with cost <= k as a Hit (unordered).  Caller holds ctx->mu and has set the device.
+// Device phase: optional bit-parallel pre-filter, then the exact kernel on the surviving segments / haystacks; returns
+// every end position with cost <= k as a Hit (unordered).  Caller holds ctx->mu and has set the device.
+// With the pre-filter the whole phase is queued without a host round trip: the filter appends the codes of the
+// segments that contain a match end to a device list, the (persistent) wave kernel reads the list's length from the
+// device, and one synchronisation at the end brings back both counters together with the first SPEC_HITS hits.
 static int search_device(ta_ctx *ctx, cudaStream_t st, const uint8_t *d_needle, size_t needle_len,
                          const uint8_t *d_hay, const uint64_t *d_off, size_t n, uint64_t max_hay, uint32_t k,
                          ta_costs costs, int anchored, std::vector<Hit> &hits) {
     int rc;
+    constexpr size_t SPEC_HITS = 16384;  // hits copied back speculatively with the counters (384 KB, pinned)
     const bool unit = costs.mismatch == 1 && costs.gap == 1 && costs.start_gap == 0 && costs.transpose <= 1;
     const uint32_t *d_idx = nullptr;
-    size_t work_n = n;
-    uint32_t segs = 0;  // > 0: work items are flagged haystack segments (pre-filter ran)
+    const uint32_t *d_work_n = nullptr;  // device-side item count (pre-filter path)
+    size_t work_n = n;                   // items, or their upper bound while the count is still on the device
+    uint32_t segs = 0;                   // > 0: work items are flagged haystack segments (pre-filter ran)
     static const bool no_filter = getenv("TA_NO_SEARCH_FILTER") != nullptr;  // testing: exact kernel on everything
+    uint32_t *counter = ctx->d_flags + 2;
+    unsigned long long *d_count = (unsigned long long *)(ctx->d_flags + 4);
+    TA_CUDA(ctx, cudaMemsetAsync(counter, 0, 4 * sizeof(uint32_t), st));  // item counter, pad, 64-bit hit counter
     if (!no_filter && unit && needle_len <= 64 && !anchored && k < needle_len) {
         const uint64_t nseg = max_hay ? (max_hay + TA_SEARCH_SEG - 1) / TA_SEARCH_SEG : 1;
         if ((uint64_t)n * nseg <= 0xFFFFFFF0ull && nseg <= 65535) {
             if ((rc = ta_dev_reserve(ctx, ctx->d_work[0], n * nseg * sizeof(uint32_t))) != TA_OK) return rc;
-            if ((rc = ta_dev_reserve(ctx, ctx->d_work[2], n * nseg * sizeof(uint32_t))) != TA_OK) return rc;
-            uint32_t *counter = ctx->d_flags + 2;
-            TA_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(uint32_t), st));
             rc = ta_launch_search_filter(ctx, d_needle, (uint32_t)needle_len, d_hay, d_off, n, max_hay, k,
-                                         costs.transpose != 0, (uint32_t *)ctx->d_work[2].p,
-                                         (uint32_t *)ctx->d_work[0].p, counter, &segs, st);
+                                         costs.transpose != 0, (uint32_t *)ctx->d_work[0].p, counter, &segs, st);
             if (rc == TA_OK) {
-                TA_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags + 2, counter, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-                TA_CUDA(ctx, cudaStreamSynchronize(st));
-                work_n = ctx->h_flags[2];
+                work_n = n * nseg;
+                d_work_n = counter;
                 d_idx = (const uint32_t *)ctx->d_work[0].p;
             } else if (rc == TA_ERR_TOO_LARGE) {
                 segs = 0;
@@ -474,32 +481,41 @@ static int search_device(ta_ctx *ctx, cudaStream_t st, const uint8_t *d_needle, 
         kern = trans ? search_exact_kernel<true> : search_exact_kernel<false>;
         TA_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    unsigned long long cap = std::max<unsigned long long>(4096, work_n * 8);
+    if ((rc = ta_pin_reserve(ctx, ctx->h_pin[3], SPEC_HITS * sizeof(Hit))) != TA_OK) return rc;
+    // hit buffer: sized from the item count when the host knows it, else a generous default; an overflow is detected
+    // from the final counter and the exact kernel re-run once with the exact size
+    unsigned long long cap = d_work_n ? std::max<unsigned long long>(1ull << 18, n / 4)
+                                      : std::max<unsigned long long>(4096, work_n * 8);
     for (int attempt = 0; attempt < 2; attempt++) {
         if ((rc = ta_dev_reserve(ctx, ctx->d_work[1], cap * sizeof(Hit))) != TA_OK) return rc;
-        unsigned long long *d_count = (unsigned long long *)(ctx->d_flags + 4);
-        TA_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st));
+        if (attempt) TA_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st));
         SearchArgs sa;
-        sa.needle = d_needle, sa.hay = d_hay, sa.hay_off = d_off, sa.idx = d_idx, sa.n = work_n;
+        sa.needle = d_needle, sa.hay = d_hay, sa.hay_off = d_off, sa.idx = d_idx, sa.n = work_n, sa.n_dev = d_work_n;
         sa.segs = segs, sa.warm = 2u * (uint32_t)needle_len + costs.start_gap / costs.gap + 2u;
         sa.needle_len = (uint32_t)needle_len, sa.k = k;
         sa.mism = costs.mismatch, sa.gap = costs.gap, sa.sgap = costs.start_gap, sa.tcost = costs.transpose;
         sa.anchored = anchored, sa.hits = (Hit *)ctx->d_work[1].p, sa.hit_count = d_count, sa.hit_cap = cap;
         const size_t per_block = use_wave ? (size_t)threads / 32 : (size_t)threads;
-        const unsigned blocks = (unsigned)((work_n + per_block - 1) / per_block);
-        kern<<<blocks, threads, smem, st>>>(sa);
+        size_t blocks = (work_n + per_block - 1) / per_block;
+        if (use_wave) blocks = std::min<size_t>(blocks, (size_t)ctx->sm_count * 16);  // persistent warps
+        kern<<<(unsigned)blocks, threads, smem, st>>>(sa);
         ctx->launches++;
         TA_CUDA(ctx, cudaGetLastError());
-        TA_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags + 4, d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        const size_t spec = (size_t)std::min<unsigned long long>(cap, SPEC_HITS);
+        TA_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags + 2, counter, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        TA_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin[3].p, ctx->d_work[1].p, spec * sizeof(Hit), cudaMemcpyDeviceToHost, st));
         TA_CUDA(ctx, cudaStreamSynchronize(st));
         unsigned long long got;
         memcpy(&got, ctx->h_flags + 4, sizeof got);
         if (got <= cap) {
             hits.resize((size_t)got);
-            if (got)
-                TA_CUDA(ctx, cudaMemcpyAsync(hits.data(), ctx->d_work[1].p, (size_t)got * sizeof(Hit),
-                                             cudaMemcpyDeviceToHost, st));
-            TA_CUDA(ctx, cudaStreamSynchronize(st));
+            const size_t head = (size_t)std::min<unsigned long long>(got, spec);
+            if (head) memcpy(hits.data(), ctx->h_pin[3].p, head * sizeof(Hit));
+            if (got > head) {
+                TA_CUDA(ctx, cudaMemcpyAsync(hits.data() + head, (const Hit *)ctx->d_work[1].p + head,
+                                             (size_t)(got - head) * sizeof(Hit), cudaMemcpyDeviceToHost, st));
+                TA_CUDA(ctx, cudaStreamSynchronize(st));
+            }
             return TA_OK;
         }
         cap = got;  // exact size known now: rerun once
@@ -519,8 +535,10 @@ static void emit_matches(size_t n, size_t needle_len, uint32_t k, bool best, ta_
     std::vector<ta_match> cur;
     result.reserve(hits.size() + (row0 <= k ? n : 0));
     for (size_t i = 0; i < n; i++) {
-        if (row0 > k && (hp >= hits.size() || hits[hp].hay != i)) {  // nothing to report for this haystack
-            moff[i + 1] = result.size();
+        if (row0 > k && (hp >= hits.size() || hits[hp].hay != i)) {  // a run of haystacks with nothing to report
+            const size_t stop = hp < hits.size() ? (size_t)hits[hp].hay : n;
+            std::fill(moff + i + 1, moff + stop + 1, (uint64_t)result.size());
+            i = stop - 1;
             continue;
         }
         cur.clear();
@@ -591,7 +609,8 @@ extern "C" int ta_levenshtein_search_batch(ta_ctx *ctx, const uint8_t *needle, s
     if (n) total_hay = hay_off[n] - hay_off[0];
     if (total_hay && !hay) return TA_ERR_BAD_ARG;
 
-    uint64_t *moff = (uint64_t *)calloc(n + 1, sizeof(uint64_t));
+    uint64_t *moff = (uint64_t *)malloc((n + 1) * sizeof(uint64_t));
+    if (moff) moff[0] = 0;
     if (!moff) return TA_ERR_NOMEM;
     std::vector<ta_match> result;
 
@@ -667,7 +686,8 @@ extern "C" int ta_levenshtein_search_batch_dev(ta_ctx *ctx, const uint8_t *needl
     if (!ta_costs_valid_search(costs)) return TA_ERR_BAD_COSTS;
     if (n && (!hay_off || !hay)) return TA_ERR_BAD_ARG;
     if (n > 0xFFFFFFF0ull || needle_len > TA_MAX_STRING_LEN) return TA_ERR_TOO_LARGE;
-    uint64_t *moff = (uint64_t *)calloc(n + 1, sizeof(uint64_t));
+    uint64_t *moff = (uint64_t *)malloc((n + 1) * sizeof(uint64_t));
+    if (moff) moff[0] = 0;
     if (!moff) return TA_ERR_NOMEM;
     std::vector<ta_match> result;
     if (n == 0) return export_matches(result, moff, out_matches, out_match_off);
