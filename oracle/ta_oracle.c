@@ -624,6 +624,46 @@ static void search_range(void *p, size_t lo, size_t hi) {
                                                            x->c, x->anchored, &x->per[i]);
 }
 
+/* ---- batch drivers over the AVX2 restatement of the reference's SIMD path (ta_ref_avx2.c): CPU baseline only ---- */
+static void lev_simd_k_range(void *p, size_t lo, size_t hi) {
+    batch_ctx *x = (batch_ctx *)p;
+    for (size_t i = lo; i < hi; i++)
+        x->out[i] = orc_levenshtein_simd_k_with_opts(x->a + x->a_off[i], x->a_off[i + 1] - x->a_off[i],
+                                                     x->b + x->b_off[i], x->b_off[i + 1] - x->b_off[i], x->k, x->c, NULL);
+}
+static void lev_simd_exp_range(void *p, size_t lo, size_t hi) {
+    batch_ctx *x = (batch_ctx *)p;
+    for (size_t i = lo; i < hi; i++)
+        x->out[i] = orc_levenshtein_simd_exp_with_opts(x->a + x->a_off[i], x->a_off[i + 1] - x->a_off[i],
+                                                       x->b + x->b_off[i], x->b_off[i + 1] - x->b_off[i], x->c);
+}
+static void hamming_simd_range(void *p, size_t lo, size_t hi) {
+    batch_ctx *x = (batch_ctx *)p;
+    for (size_t i = lo; i < hi; i++) {
+        int64_t r = orc_hamming_simd(x->a + x->a_off[i], x->a_off[i + 1] - x->a_off[i], x->b + x->b_off[i],
+                                     x->b_off[i + 1] - x->b_off[i]);
+        x->out[i] = r < 0 ? ORC_NONE : (uint32_t)r;
+    }
+}
+void orc_levenshtein_simd_k_batch(const uint8_t *a, const uint64_t *a_off, const uint8_t *b, const uint64_t *b_off,
+                                  size_t n, uint32_t k, orc_costs c, uint32_t *out, int n_threads) {
+    batch_ctx x = {0};
+    x.a = a, x.b = b, x.a_off = a_off, x.b_off = b_off, x.out = out, x.k = k, x.c = c;
+    parallel_for(n, 256, n_threads, lev_simd_k_range, &x);
+}
+void orc_levenshtein_simd_exp_batch(const uint8_t *a, const uint64_t *a_off, const uint8_t *b, const uint64_t *b_off,
+                                    size_t n, orc_costs c, uint32_t *out, int n_threads) {
+    batch_ctx x = {0};
+    x.a = a, x.b = b, x.a_off = a_off, x.b_off = b_off, x.out = out, x.c = c;
+    parallel_for(n, 64, n_threads, lev_simd_exp_range, &x);
+}
+void orc_hamming_simd_batch(const uint8_t *a, const uint64_t *a_off, const uint8_t *b, const uint64_t *b_off, size_t n,
+                            uint32_t *out, int n_threads) {
+    batch_ctx x = {0};
+    x.a = a, x.b = b, x.a_off = a_off, x.b_off = b_off, x.out = out;
+    parallel_for(n, 1024, n_threads, hamming_simd_range, &x);
+}
+
 void orc_hamming_batch(const uint8_t *a, const uint64_t *a_off, const uint8_t *b, const uint64_t *b_off, size_t n,
                        uint32_t *out, int n_threads) {
     batch_ctx x = {0};

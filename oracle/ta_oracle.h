@@ -96,6 +96,22 @@ int64_t orc_levenshtein_search_batch(const uint8_t *needle, size_t needle_len, c
 void orc_free(void *p);
 int orc_max_threads(void);
 
+/* ---- ta_ref_avx2.c: restatement of the reference's AVX2 path (Avx1x32x8 core, Avx::count_mismatches) used as the
+ * CPU baseline; NOT the parity oracle (it reproduces the SIMD path's documented deviations from the scalar contract) */
+int orc_simd_available(void); /* AVX2 present on this host */
+int orc_simd_covers(size_t a_len, size_t b_len, uint32_t k, orc_costs c); /* the reference would pick Avx1x32x8 */
+uint32_t orc_levenshtein_simd_k_with_opts(const uint8_t *a, size_t a_len, const uint8_t *b, size_t b_len, uint32_t k,
+                                          orc_costs c, int *covered);
+uint32_t orc_levenshtein_simd_exp_with_opts(const uint8_t *a, size_t a_len, const uint8_t *b, size_t b_len,
+                                            orc_costs c);
+int64_t orc_hamming_simd(const uint8_t *a, size_t a_len, const uint8_t *b, size_t b_len);
+void orc_levenshtein_simd_k_batch(const uint8_t *a, const uint64_t *a_off, const uint8_t *b, const uint64_t *b_off,
+                                  size_t n, uint32_t k, orc_costs c, uint32_t *out, int n_threads);
+void orc_levenshtein_simd_exp_batch(const uint8_t *a, const uint64_t *a_off, const uint8_t *b, const uint64_t *b_off,
+                                    size_t n, orc_costs c, uint32_t *out, int n_threads);
+void orc_hamming_simd_batch(const uint8_t *a, const uint64_t *a_off, const uint8_t *b, const uint64_t *b_off, size_t n,
+                            uint32_t *out, int n_threads);
+
 #ifdef __cplusplus
 }
 #endif

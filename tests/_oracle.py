@@ -33,7 +33,7 @@ _lib = None
 
 def build():
     so = os.path.join(ORACLE_DIR, "libta_oracle.so")
-    src = [os.path.join(ORACLE_DIR, f) for f in ("ta_oracle.c", "ta_oracle.h")]
+    src = [os.path.join(ORACLE_DIR, f) for f in ("ta_oracle.c", "ta_ref_avx2.c", "ta_oracle.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"])
     return so
@@ -84,6 +84,23 @@ def lib():
                                                    C.c_void_p, C.c_int]
         L.orc_free.argtypes = [C.c_void_p]
         L.orc_max_threads.restype = C.c_int
+        # AVX2 restatement of the reference's SIMD path (CPU baseline only, oracle/ta_ref_avx2.c)
+        L.orc_simd_available.restype = C.c_int
+        L.orc_simd_covers.restype = C.c_int
+        L.orc_simd_covers.argtypes = [C.c_size_t, C.c_size_t, C.c_uint32, Costs]
+        L.orc_levenshtein_simd_k_with_opts.restype = C.c_uint32
+        L.orc_levenshtein_simd_k_with_opts.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_uint32,
+                                                       Costs, C.POINTER(C.c_int)]
+        L.orc_levenshtein_simd_exp_with_opts.restype = C.c_uint32
+        L.orc_levenshtein_simd_exp_with_opts.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, Costs]
+        L.orc_hamming_simd.restype = C.c_int64
+        L.orc_hamming_simd.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
+        L.orc_levenshtein_simd_k_batch.restype = None
+        L.orc_levenshtein_simd_k_batch.argtypes = L.orc_levenshtein_k_batch.argtypes
+        L.orc_levenshtein_simd_exp_batch.restype = None
+        L.orc_levenshtein_simd_exp_batch.argtypes = L.orc_levenshtein_exp_batch.argtypes
+        L.orc_hamming_simd_batch.restype = None
+        L.orc_hamming_simd_batch.argtypes = L.orc_hamming_batch.argtypes
         _lib = L
     return _lib
 
@@ -221,3 +238,40 @@ def levenshtein_search_batch(needle, hay, hay_off, k, search_type=0, costs=LEVEN
 
 def max_threads():
     return lib().orc_max_threads()
+
+
+# ---- AVX2 restatement of the reference's SIMD path (CPU baseline; NOT the parity oracle) -----------------------
+def simd_available():
+    return bool(lib().orc_simd_available())
+
+
+def levenshtein_simd_k_with_opts(a, b, k, costs=LEVENSHTEIN_COSTS):
+    """(distance | None, covered): covered is False when the reference would use a wider Jewel type than Avx1x32x8"""
+    cov = C.c_int(0)
+    d = lib().orc_levenshtein_simd_k_with_opts(a, len(a), b, len(b), k, Costs(*costs), C.byref(cov))
+    return (None if d == NONE else d), bool(cov.value)
+
+
+def hamming_simd(a, b):
+    return lib().orc_hamming_simd(a, len(a), b, len(b))
+
+
+def levenshtein_simd_k_batch(a, a_off, b, b_off, k, costs=LEVENSHTEIN_COSTS, threads=1):
+    n = len(a_off) - 1
+    out = np.empty(n, np.uint32)
+    lib().orc_levenshtein_simd_k_batch(_p(a), _p(a_off), _p(b), _p(b_off), n, k, Costs(*costs), _p(out), threads)
+    return out
+
+
+def levenshtein_simd_exp_batch(a, a_off, b, b_off, costs=LEVENSHTEIN_COSTS, threads=1):
+    n = len(a_off) - 1
+    out = np.empty(n, np.uint32)
+    lib().orc_levenshtein_simd_exp_batch(_p(a), _p(a_off), _p(b), _p(b_off), n, Costs(*costs), _p(out), threads)
+    return out
+
+
+def hamming_simd_batch(a, a_off, b, b_off, threads=1):
+    n = len(a_off) - 1
+    out = np.empty(n, np.uint32)
+    lib().orc_hamming_simd_batch(_p(a), _p(a_off), _p(b), _p(b_off), n, _p(out), threads)
+    return out

@@ -27,11 +27,11 @@ static void check_clean(const char *what, T (&t)[N]) {
         }
 }
 
-// block-table variants (MAD = which shifts are written as multiply-adds)
-template <bool TRANS, int PLANES, int C, int MAD>
+// block-table variants
+template <bool TRANS, int PLANES, int C>
 static uint32_t run_blk(const uint8_t *a, int la, const uint8_t *b, int lb, uint32_t k) {
     static uint32_t tab[256];
-    const uint32_t got = bitpar::pair_unit_costs_blk<TRANS, PLANES, C, MAD>(a, la, b, lb, k, (uint8_t *)tab, 4u);
+    const uint32_t got = bitpar::pair_unit_costs_blk<TRANS, PLANES, C>(a, la, b, lb, k, (uint8_t *)tab, 4u);
     check_clean("blk", tab);
     return got;
 }
@@ -116,24 +116,20 @@ int main(int argc, char **argv) {
                 const uint32_t k = (uint32_t)(rng() % (trans ? 16 : 17));
                 const uint32_t want = want_for(k);
                 uint32_t got;
-                switch ((it >> 1) & 3) {
-                    case 0: got = trans ? run_blk<true, 1, 16, 0>(a, la, b, lb, k) : run_blk<false, 1, 16, 0>(a, la, b, lb, k); break;
-                    case 1: got = trans ? run_blk<true, 0, 16, 1>(a, la, b, lb, k) : run_blk<false, 0, 16, 1>(a, la, b, lb, k); break;
-                    case 2: got = trans ? run_blk<true, 1, 16, 3>(a, la, b, lb, k) : run_blk<false, 1, 16, 3>(a, la, b, lb, k); break;
-                    default: got = trans ? run_blk<true, 0, 16, 7>(a, la, b, lb, k) : run_blk<false, 0, 16, 7>(a, la, b, lb, k); break;
-                }
+                if ((it >> 1) & 1)
+                    got = trans ? run_blk<true, 1, 16>(a, la, b, lb, k) : run_blk<false, 1, 16>(a, la, b, lb, k);
+                else
+                    got = trans ? run_blk<true, 0, 16>(a, la, b, lb, k) : run_blk<false, 0, 16>(a, la, b, lb, k);
                 if (got != want) report("BLK16", trans, k, la, lb, want, got);
             }
             {  // block table, 8-position blocks: bands of <= 25 diagonals
                 const uint32_t k = (uint32_t)(rng() % (trans ? 24 : 25));
                 const uint32_t want = want_for(k);
                 uint32_t got;
-                switch ((it >> 1) & 3) {
-                    case 0: got = trans ? run_blk<true, 1, 8, 0>(a, la, b, lb, k) : run_blk<false, 1, 8, 0>(a, la, b, lb, k); break;
-                    case 1: got = trans ? run_blk<true, 0, 8, 1>(a, la, b, lb, k) : run_blk<false, 0, 8, 1>(a, la, b, lb, k); break;
-                    case 2: got = trans ? run_blk<true, 1, 8, 3>(a, la, b, lb, k) : run_blk<false, 1, 8, 3>(a, la, b, lb, k); break;
-                    default: got = trans ? run_blk<true, 0, 8, 7>(a, la, b, lb, k) : run_blk<false, 0, 8, 7>(a, la, b, lb, k); break;
-                }
+                if ((it >> 1) & 1)
+                    got = trans ? run_blk<true, 1, 8>(a, la, b, lb, k) : run_blk<false, 1, 8>(a, la, b, lb, k);
+                else
+                    got = trans ? run_blk<true, 0, 8>(a, la, b, lb, k) : run_blk<false, 0, 8>(a, la, b, lb, k);
                 if (got != want) report("BLK8", trans, k, la, lb, want, got);
             }
             tests++;

@@ -1,0 +1,101 @@
+"""oracle/ta_ref_avx2.c -- the C restatement of the reference's AVX2 path (Avx1x32x8 core, Avx::count_mismatches) that
+bench.py times as the CPU baseline -- pinned to (1) every SIMD-named known-answer test of the reference
+(tests/golden/kat.json, parsed from tests/basic_tests.rs and the doc-tests) and (2) the scalar oracle on random inputs
+for the cost models on which the reference's scalar and SIMD paths agree (everything without a transposition cost;
+SURVEY.md Appendix B)."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+import _oracle as orc
+
+KAT = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "kat.json")))
+
+pytestmark = pytest.mark.skipif(not orc.simd_available(), reason="host has no AVX2")
+
+
+def _b(h):
+    return bytes.fromhex(h)
+
+
+def test_simd_k_kats():
+    n = 0
+    for r in KAT:
+        if r["fn"] not in ("levenshtein_simd_k_with_opts", "levenshtein_simd_k"):
+            continue
+        if str(r.get("src", "")).startswith("hand"):
+            continue  # scalar-contract regression cases, not reference SIMD outputs
+        costs = tuple(r.get("costs", orc.LEVENSHTEIN_COSTS))
+        got, covered = orc.levenshtein_simd_k_with_opts(_b(r["a"]), _b(r["b"]), r["k"], costs)
+        want = None if r["expect"].get("none") else r["expect"]["dist"]
+        assert got == want, (r["src"], got, want)
+        n += 1
+    assert n >= 20
+
+
+def test_exp_and_full_kats():
+    n = 0
+    for r in KAT:
+        if r["fn"] in ("levenshtein_exp", "rdamerau_exp", "levenshtein_exp_with_opts"):
+            costs = tuple(r.get("costs", orc.RDAMERAU_COSTS if r["fn"] == "rdamerau_exp" else orc.LEVENSHTEIN_COSTS))
+            got = orc.lib().orc_levenshtein_simd_exp_with_opts(_b(r["a"]), len(_b(r["a"])), _b(r["b"]), len(_b(r["b"])),
+                                                               orc.Costs(*costs))
+            assert got == r["expect"]["dist"], (r["src"], got)
+            n += 1
+    assert n >= 10
+
+
+def test_hamming_kats():
+    n = 0
+    for r in KAT:
+        if r["fn"] in ("hamming_simd_parallel", "hamming"):
+            assert orc.hamming_simd(_b(r["a"]), _b(r["b"])) == r["expect"]["dist"], r["src"]
+            n += 1
+    assert n >= 4
+    rng = random.Random(5)
+    for _ in range(300):
+        ln = rng.choice([0, 1, 31, 32, 33, 64, 100, 255 * 32 + 40, 9000])
+        a = bytes(rng.randrange(4) for _ in range(ln))
+        b = bytes(rng.randrange(4) for _ in range(ln))
+        assert orc.hamming_simd(a, b) == orc.hamming_naive(a, b)
+
+
+@pytest.mark.parametrize("costs", [(1, 1, 0, 0), (1, 1, 2, 0), (2, 1, 2, 0), (2, 3, 0, 0)], ids=str)
+def test_simd_equals_scalar_without_transpositions(costs):
+    """the equality the reference's own bench asserts (benches/rand_benchmarks.rs:65-67, 88-90)"""
+    rng = random.Random(hash(costs) & 0xffff)
+    A, B = [], []
+    for i in range(4000):
+        alpha = rng.choice([2, 4, 26, 255])
+        la = rng.randrange(0, 140)
+        a = bytes(1 + rng.randrange(alpha) for _ in range(la))
+        if rng.random() < 0.7:
+            s = bytearray(a)
+            for _ in range(rng.randrange(0, 12)):
+                kind = rng.randrange(3)
+                if kind == 0 and s:
+                    s[rng.randrange(len(s))] = 1 + rng.randrange(alpha)
+                elif kind == 1:
+                    s.insert(rng.randrange(len(s) + 1), 1 + rng.randrange(alpha))
+                elif s:
+                    del s[rng.randrange(len(s))]
+            b = bytes(s)
+        else:
+            b = bytes(1 + rng.randrange(alpha) for _ in range(rng.randrange(0, 140)))
+        A.append(a)
+        B.append(b)
+    a = np.frombuffer(b"".join(A), np.uint8)
+    b = np.frombuffer(b"".join(B), np.uint8)
+    ao = np.concatenate([[0], np.cumsum([len(x) for x in A])]).astype(np.uint64)
+    bo = np.concatenate([[0], np.cumsum([len(x) for x in B])]).astype(np.uint64)
+    for k in (0, 1, 3, 8, 16, 30):
+        got = orc.levenshtein_simd_k_batch(a, ao, b, bo, k, costs, threads=4)
+        want = orc.levenshtein_k_batch(a, ao, b, bo, k, costs, threads=4)
+        bad = np.nonzero(got != want)[0]
+        assert len(bad) == 0, (k, A[bad[0]], B[bad[0]], int(got[bad[0]]), int(want[bad[0]]))
+    got = orc.levenshtein_simd_exp_batch(a, ao, b, bo, costs, threads=4)
+    want = orc.levenshtein_exp_batch(a, ao, b, bo, costs, threads=4)
+    assert np.array_equal(got, want)

@@ -15,7 +15,6 @@
 
 // defaults of the block-table kernel (measured on B200, profiles/README.md)
 #define TA_BLK_DEFAULT_PLANES 1
-#define TA_BLK_DEFAULT_MAD 0
 
 namespace {
 
@@ -61,8 +60,34 @@ __global__ void __launch_bounds__(128) lev_bitpar_tab_kernel(const uint8_t *__re
 
 
 // Block-table variant (lev_bitpar_core.cuh: distance_blk), bands of <= 33 - C diagonals.  Same table layout
-// ([entry][thread] u32, 128 or 256 entries per thread).
-template <bool TRANS, int PLANES, int C, int MAD>
+// ([entry][thread] u32, 128 or 256 entries per thread).  The persistent pair loop is software-pipelined: the CSR
+// offsets are loaded two pairs ahead and the first lines of the next pair's strings are pulled into L2 one pair
+// ahead, so a pair never starts with two dependent DRAM round trips (offsets -> bytes).
+struct PairRef {
+    uint64_t a0, b0;
+    uint32_t alen, blen;
+    size_t pair;
+};
+__device__ __forceinline__ PairRef load_pair_ref(const uint64_t *__restrict__ a_off, const uint64_t *__restrict__ b_off,
+                                                 const uint32_t *__restrict__ idx, size_t w, size_t n) {
+    PairRef r;
+    r.a0 = r.b0 = 0, r.alen = r.blen = 0, r.pair = 0;
+    if (w < n) {
+        r.pair = idx ? (size_t)idx[w] : w;
+        r.a0 = a_off[r.pair];
+        r.b0 = b_off[r.pair];
+        r.alen = (uint32_t)(a_off[r.pair + 1] - r.a0);
+        r.blen = (uint32_t)(b_off[r.pair + 1] - r.b0);
+    }
+    return r;
+}
+__device__ __forceinline__ void prefetch_l2(const uint8_t *p, uint32_t len) {
+    if (len == 0) return;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    if (((uintptr_t)p & 127) + len > 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 128));
+}
+
+template <bool TRANS, int PLANES, int C>
 __global__ void __launch_bounds__(256) lev_bitpar_blk_kernel(const uint8_t *__restrict__ a,
                                                              const uint64_t *__restrict__ a_off,
                                                              const uint8_t *__restrict__ b,
@@ -77,28 +102,24 @@ __global__ void __launch_bounds__(256) lev_bitpar_blk_kernel(const uint8_t *__re
     uint8_t *tab = (uint8_t *)(tabs + threadIdx.x);
     const uint32_t pitch = nt * 4u;
     const size_t total = (size_t)gridDim.x * nt;
-    for (size_t w = (size_t)blockIdx.x * nt + threadIdx.x; w < n; w += total) {
-        const size_t pair = idx ? (size_t)idx[w] : w;
-        const uint64_t a0 = a_off[pair], a1 = a_off[pair + 1];
-        const uint64_t b0 = b_off[pair], b1 = b_off[pair + 1];
-        out[pair] = bitpar::pair_unit_costs_blk<TRANS, PLANES, C, MAD>(a + a0, a1 - a0, b + b0, b1 - b0, k, tab, pitch);
+    size_t w = (size_t)blockIdx.x * nt + threadIdx.x;
+    PairRef cur = load_pair_ref(a_off, b_off, idx, w, n);
+    PairRef nxt = load_pair_ref(a_off, b_off, idx, w + total, n);
+    for (; w < n; w += total) {
+        const PairRef nn = load_pair_ref(a_off, b_off, idx, w + 2 * total, n);  // in flight during this pair
+        prefetch_l2(a + nxt.a0, nxt.alen);
+        prefetch_l2(b + nxt.b0, nxt.blen);
+        out[cur.pair] = bitpar::pair_unit_costs_blk<TRANS, PLANES, C>(a + cur.a0, cur.alen, b + cur.b0, cur.blen, k, tab, pitch);
+        cur = nxt;
+        nxt = nn;
     }
 }
 
 typedef void (*lev_kern_t)(const uint8_t *, const uint64_t *, const uint8_t *, const uint64_t *, const uint32_t *,
                            size_t, uint32_t, uint32_t *);
-template <bool TRANS, int C, int PLANES>
-lev_kern_t pick_blk_mad(int mad) {
-    switch (mad) {
-        case 1: return lev_bitpar_blk_kernel<TRANS, PLANES, C, 1>;
-        case 3: return lev_bitpar_blk_kernel<TRANS, PLANES, C, 3>;
-        case 7: return lev_bitpar_blk_kernel<TRANS, PLANES, C, 7>;
-        default: return lev_bitpar_blk_kernel<TRANS, PLANES, C, 0>;
-    }
-}
 template <bool TRANS, int C>
-lev_kern_t pick_blk(int planes, int mad) {
-    return planes ? pick_blk_mad<TRANS, C, 1>(mad) : pick_blk_mad<TRANS, C, 0>(mad);
+lev_kern_t pick_blk(int planes) {
+    return planes ? lev_bitpar_blk_kernel<TRANS, 1, C> : lev_bitpar_blk_kernel<TRANS, 0, C>;
 }
 
 }  // namespace
@@ -129,10 +150,8 @@ int ta_launch_lev_bitpar(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, c
     static const int env_planes = getenv("TA_BITPAR_PLANES") ? atoi(getenv("TA_BITPAR_PLANES")) : 0;
     static const int env_bits = getenv("TA_BITPAR_BITS") ? atoi(getenv("TA_BITPAR_BITS")) : 0;
     // block-table kernel (default whenever the band fits 33 - C diagonals): TA_BLK_PLANES=0|1 (256 entries / 128
-    // entries + top-bit plane), TA_BLK_MAD=0|1|3|7 (which shifts run as multiply-adds on the FMA pipe), TA_BLK_C=8
-    // forces 8-position blocks on narrow bands
+    // entries + top-bit plane), TA_BLK_C=8 forces 8-position blocks on narrow bands
     static const int blk_planes = getenv("TA_BLK_PLANES") ? atoi(getenv("TA_BLK_PLANES")) : TA_BLK_DEFAULT_PLANES;
-    static const int blk_mad = getenv("TA_BLK_MAD") ? atoi(getenv("TA_BLK_MAD")) : TA_BLK_DEFAULT_MAD;
     static const int blk_c = getenv("TA_BLK_C") ? atoi(getenv("TA_BLK_C")) : 0;
     {
         const uint32_t kk = k < max_len ? k : max_len;
@@ -146,9 +165,9 @@ int ta_launch_lev_bitpar(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, c
             const unsigned blocks = (unsigned)std::min<size_t>((n + nt - 1) / nt, (size_t)ctx->sm_count * per_sm);
             lev_kern_t kern;
             if (C == 16)
-                kern = costs.transpose ? pick_blk<true, 16>(blk_planes, blk_mad) : pick_blk<false, 16>(blk_planes, blk_mad);
+                kern = costs.transpose ? pick_blk<true, 16>(blk_planes) : pick_blk<false, 16>(blk_planes);
             else
-                kern = costs.transpose ? pick_blk<true, 8>(blk_planes, blk_mad) : pick_blk<false, 8>(blk_planes, blk_mad);
+                kern = costs.transpose ? pick_blk<true, 8>(blk_planes) : pick_blk<false, 8>(blk_planes);
             TA_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             kern<<<blocks, nt, smem, st>>>(a, a_off, b, b_off, idx, n, k, out);
             ctx->launches++;

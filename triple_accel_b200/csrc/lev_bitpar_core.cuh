@@ -45,7 +45,9 @@ TA_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) {  // low 32 bits 
 
 TA_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 #if defined(__CUDA_ARCH__)
-    return __byte_perm(a, b, sel);
+    uint32_t r;  // inline PTX: __byte_perm() ignores bit 3 of a selector nibble (the sign-replicate mode used below)
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
 #else
     uint64_t v = ((uint64_t)b << 32) | a;
     uint32_t r = 0;
@@ -426,67 +428,42 @@ TA_HD uint32_t distance_tab(const uint8_t *a, int m, const uint8_t *b, int n, ui
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// distance_blk: the match-table recurrence with BLOCK-wise table maintenance (bands of <= 33 - C diagonals).
+// distance_blk: the match-table recurrence with BLOCK-wise table maintenance (bands of W <= 33 - C diagonals).
 //
 // Only the band's W rows have to see their exact match flags; every other row of the 32-row window merely has to
 // stay an upper bound of the true DP, i.e. its Eq bits may be dropped but never invented.  So the table does not
-// have to follow the window column by column.  It is a 32-position circular frame cut into blocks of C positions
-// (C = 16: the two halves of an entry; C = 8: its four bytes) and holds stream bytes [g, g + 32) for the C columns
-// of the chunk that starts at stream position g.  Inside a chunk nothing is written; a column's Eq is
-//     rotr(tab[class(b)] [& plane], (g + u') mod 32)
-// Between chunks the block that left the window is ZEROED BY VALUE -- a sub-word store of 0 to the entry of each of
-// its bytes: no read, no mask, because every bit of that sub-word belongs to the same block -- and the block that
-// enters is OR-ed in.  W <= 33 - C guarantees that the band's rows of every column of the chunk lie inside
-// [g, g + 32).  In column u' of a chunk the rotation wraps the u' bytes that already left the window into rows
-// p >= 32 - u' >= 33 - C, where they can INVENT matches.  That is harmless: with unit costs every change of
-// diagonal costs 1, the path starts on row dhi and ends on row e, so a path through such a cell costs at least
-// (p - dhi) + (p - e) >= 66 - 2C - (W - 1) >= 34 - C > max_k (max_k <= W <= 33 - C); it can neither lower a distance
-// that is <= max_k nor pull one that is > max_k below the threshold.  Chunks are unrolled 32 columns deep so that every rotation, mask and
-// bit is an immediate.  The last n mod 16 columns slide the table column by column like distance_tab.
+// have to follow the window exactly.  It is a 32-position circular frame (stream byte t sits at bit t mod 32) cut
+// into blocks of C positions (C = 16: the two halves of an entry; C = 8: its four bytes).  With L = 32 - C:
+//   * before column j is looked up, stream byte j + L is OR-ed in (one read-modify-write per column, independent of
+//     the recurrence, so its latency hides behind it) -- the band's last row of column j is byte j + W - 1 <= j + L;
+//   * at the start of each chunk of C columns [g, g + C) the block [g - C, g), which left the window, is ZEROED BY
+//     VALUE: a sub-word store of 0 to the entry of each of its bytes -- no read, no mask, because every bit of that
+//     sub-word belongs to the same (dead) block.  These are the positions the chunk's entering bytes will use.
+// A column's Eq is rotr(tab[class(b)] [& plane], j mod 32).  The rotation wraps bytes that already left the window
+// (up to C - 1 of them, not yet zeroed) into rows p >= 33 - C, where they can INVENT matches.  That is harmless: with
+// unit costs every change of diagonal costs 1, the path starts on row dhi and ends on row e, so a path through such
+// a cell costs at least (p - dhi) + (p - e) >= 66 - 2C - (W - 1) >= 34 - C > max_k (max_k <= W <= 33 - C); it can
+// neither lower a distance that is <= max_k nor pull one that is > max_k below the threshold.
+// Columns are unrolled 32 deep so that every rotation, bit and sub-word offset is an immediate.  The last n mod 16
+// columns slide the table column by column with an exact clear (rolled code).
 //   PLANES = 1: 128 entries (7-bit classes) + the A7 plane;  PLANES = 0: 256 entries, no plane.
-//   MAD (bit mask): which shifts are issued as multiply-adds on the FMA pipe instead of ALU-pipe instructions:
-//   1 = the match count (acc = hi32((D0 << (31 - e)) * 2) + acc, two IMADs instead of LOP3 + IADD3),
-//   2 = X = D0 >> 1 as hi32(D0 * 2^31),  4 = the table rotation as hi32(raw * 2^(32-s)) | lo32(raw * 2^(32-s)), the
-//   OR folding into the recurrence's LOP3s.  `tab` = the thread's entry 0, `pitch` = bytes between entries.
-// multiply-add forms of shifts: IMAD / IMAD.HI run on the FMA pipe, which the recurrence leaves idle, whereas SHF /
-// LOP3 / PRMT share the (binding) ALU pipe
-TA_HD uint32_t mad_hi(uint32_t a, uint32_t b, uint32_t c) {  // high word of a * b, plus c
-#if defined(__CUDA_ARCH__)
-    uint32_t r;
-    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
-    return r;
-#else
-    return (uint32_t)(((uint64_t)a * b) >> 32) + c;
-#endif
-}
-TA_HD uint32_t mul_lo(uint32_t a, uint32_t b) {
-#if defined(__CUDA_ARCH__)
-    uint32_t r;
-    asm("mul.lo.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
-    return r;
-#else
-    return a * b;
-#endif
-}
+//   `tab` = the thread's entry 0, `pitch` = bytes between entries; the table is all-zero on entry and on exit.
 TA_HD uint8_t *blk_entry(uint8_t *tab, uint32_t w, int t, uint32_t pitch) { return tab + byte_of(w, t) * pitch; }
-// raw rotated right by the constant s (1..31) = hi | lo, both halves produced on the FMA pipe
-TA_HD void blk_rot_mad(uint32_t raw, uint32_t s, uint32_t one, uint32_t &hi, uint32_t &lo) {
-    const uint64_t p = (uint64_t)raw * (uint64_t)(one << (32 - s));  // `one` is an opaque 1: IMAD.SHL + IMAD.WIDE
-    hi = (uint32_t)(p >> 32);                                        // raw >> s
-    lo = (uint32_t)p;                                                // raw << (32 - s)
-}
 template <int V>
 struct IntC {
     static constexpr int value = V;
 };
 
-template <bool TRANS, int PLANES, int C, int MAD>
+template <bool TRANS, int PLANES, int C>
 TA_HD uint32_t distance_blk(const uint8_t *a, int m, const uint8_t *b, int n, uint32_t max_k, uint8_t *tab,
                             const uint32_t pitch) {
     static_assert(C == 8 || C == 16, "block = a byte or a half of the entry");
     static_assert(PLANES == 0 || PLANES == 1, "");
     typedef uint32_t W;
     constexpr uint32_t CMASK = PLANES == 1 ? 0x7f7f7f7fu : 0xffffffffu;
+    constexpr int L = 32 - C;              // lead of the inserted byte over the column
+    constexpr int NT = C == 16 ? 1 : 2;    // 16-byte takes of the pattern stream the table runs ahead of the text
+    constexpr int NW = 8 + 4 * NT;         // window words: stream bytes [16 s - 16, 16 s + 16 (NT + 1))
     const int diff = n - m;
     const int e = (int)((max_k - (uint32_t)diff) >> 1) + ((TRANS && ((max_k - (uint32_t)diff) & 1u)) ? 1 : 0);
     const int dhi = diff + e;  // window row p of column j is matrix row i = j - dhi + p
@@ -495,19 +472,25 @@ TA_HD uint32_t distance_blk(const uint8_t *a, int m, const uint8_t *b, int n, ui
     sa.init((intptr_t)a - dhi, (uintptr_t)a, (uintptr_t)a + m - 1);
     sb.init((intptr_t)b, (uintptr_t)b, (uintptr_t)b + n - 1);
 
-    // the table is all-zero on entry: reading it gives a 0 the compiler cannot see through (MAD variants)
-    const uint32_t opaque0 = MAD ? *(const volatile uint32_t *)tab : 0u;
-    uint32_t ring[8];  // class bits of the 32 stream bytes the table holds at a 16-column boundary
+    // win = class bits of pattern-stream bytes [16 s - 16, ...) at superstep s; g7 = top bits of the last takes
+    uint32_t win[NW];
+    uint32_t g7prev = 0, g7cur = 0;
     W A7 = 0;
+#pragma unroll
+    for (int w = 0; w < NW; w++) win[w] = 0;
     {
-        uint32_t x[8];
-        sa.take(x);
-        sa.take(x + 4);
-        if (PLANES) A7 = gather_bits16(x, 7) | (gather_bits16(x + 4, 7) << 16);
+        uint32_t x[4 * NT];
 #pragma unroll
-        for (int w = 0; w < 8; w++) ring[w] = x[w] & CMASK;
+        for (int c = 0; c < NT; c++) sa.take(x + 4 * c);
+        if (PLANES) {
+            g7cur = gather_bits16(x + 4 * (NT - 1), 7);
+            if (NT == 2) g7prev = gather_bits16(x, 7);
+            A7 = NT == 1 ? g7cur : (g7prev | ((g7cur & 0xffu) << 16));
+        }
 #pragma unroll
-        for (int t = 0; t < 32; t++) *(W *)blk_entry(tab, ring[t >> 2], t & 3, pitch) |= 1u << t;
+        for (int w = 0; w < 4 * NT; w++) win[4 + w] = x[w] & CMASK;
+#pragma unroll
+        for (int t = 0; t < L; t++) *(W *)blk_entry(tab, win[4 + (t >> 2)], t & 3, pitch) |= 1u << t;
     }
 
     W VP = dhi >= 32 ? 0u : (0xffffffffu << dhi);
@@ -516,12 +499,8 @@ TA_HD uint32_t distance_blk(const uint8_t *a, int m, const uint8_t *b, int n, ui
     uint32_t matches = 0;
     const W emask = 1u << e;
     uint32_t acc = 0;
-    uint32_t aw[4] = {0, 0, 0, 0}, bw[4], bc[4];
+    uint32_t bw[4], bc[4];
 
-    // runtime copies of the multipliers (kept opaque so that the multiplies are not strength-reduced into shifts)
-    const uint32_t opaque1 = 1u | opaque0;
-    const uint32_t m_e = (MAD & 1) ? ((1u << (31 - e)) | opaque0) : 0u;       // moves bit e to bit 31
-    const uint32_t m_two = 2u | opaque0, m_half = 0x80000000u | opaque0;
     // the recurrence for one column given its match word
     auto step = [&](const W Eq) {
         W D0 = (((Eq & VP) + VP) ^ VP) | Eq | VN;
@@ -532,68 +511,81 @@ TA_HD uint32_t distance_blk(const uint8_t *a, int m, const uint8_t *b, int n, ui
         }
         const W HP = VN | ~(D0 | VP);
         const W HN = D0 & VP;
-        const W X = (MAD & 2) ? mad_hi(D0, m_half, 0u) : (D0 >> 1);
+        const W X = D0 >> 1;
         VN = X & HP;
         VP = HN | ~(X | HP);
-        if (MAD & 1)
-            acc = mad_hi(mul_lo(D0, m_e), m_two, acc);
-        else
-            acc += D0 & emask;
+        acc += D0 & emask;
     };
-    // 16 columns whose first column sits at circular position PH (0 or 16)
-    auto superstep = [&](auto phc) {
-        constexpr uint32_t PH = (uint32_t)decltype(phc)::value;
-        sa.take(aw);  // stream bytes [16 s + 32, 16 s + 48): they enter the table during this superstep
-        sb.take(bw);
-        W tops7 = 0;
-        if (PLANES) tops7 = gather_bits16(aw, 7) << PH;
-#pragma unroll
-        for (int w = 0; w < 4; w++) {
-            aw[w] &= CMASK;
-            bc[w] = bw[w] & CMASK;
+    // fetch the next 16 pattern-stream bytes into the top of the window
+    auto take_pattern = [&]() {
+        uint32_t x[4];
+        sa.take(x);
+        if (PLANES) {
+            g7prev = g7cur;
+            g7cur = gather_bits16(x, 7);
         }
 #pragma unroll
-        for (int q = 0; q < 16 / C; q++) {
+        for (int w = 0; w < 4; w++) win[NW - 4 + w] = x[w] & CMASK;
+    };
+    auto slide_window = [&]() {
 #pragma unroll
-            for (int v = 0; v < C; v++) {
-                const int u = C * q + v;
-                W raw = *(const W *)blk_entry(tab, bc[u >> 2], u & 3, pitch);
-                if (PLANES) raw &= ~(A7 ^ prmt(bw[u >> 2], 0u, 0x8888u | (uint32_t)((u & 3) * 0x1111)));
-                const uint32_t sft = (PH + (uint32_t)u) & 31u;
-                if ((MAD & 4) && sft != 0) {
-                    uint32_t hi, lo;
-                    blk_rot_mad(raw, sft, opaque1, hi, lo);
-                    step(hi | lo);
-                } else {
-                    step(funnel_r(raw, raw, sft));
-                }
+        for (int w = 0; w + 4 < NW; w++) win[w] = win[w + 4];
+    };
+
+    // 16 columns whose first column sits at circular position PH (0 or 16).  The read-modify-write that ORs byte
+    // j + L in is software-pipelined by hand: its load is issued one column early (right after the previous store,
+    // which it must follow because two entering bytes may share an entry), so neither the store nor the look-up that
+    // follows it waits for shared-memory latency.
+    auto superstep = [&](auto phc) {
+        constexpr uint32_t PH = (uint32_t)decltype(phc)::value;
+        take_pattern();
+        sb.take(bw);
+#pragma unroll
+        for (int w = 0; w < 4; w++) bc[w] = bw[w] & CMASK;
+        // start of chunk q: planes of the entering bytes (their positions' old bits are dead), dead block zeroed by value
+        auto begin_chunk = [&](const int q) {
+            const uint32_t pos = (PH + (uint32_t)(C * q + L)) & 31u;  // circular position of the dying / entering block
+            if (PLANES) {
+                const W blk = (C == 16 ? 0xffffu : 0xffu) << pos;
+                W tops;
+                if (C == 16)
+                    tops = g7cur << pos;
+                else
+                    tops = (q == 0 ? (g7prev >> 8) : (g7cur & 0xffu)) << pos;
+                A7 = (A7 & ~blk) | (tops & blk);
             }
-            // the block of columns just done left the window: zero it by value, then OR the entering block in
-            const uint32_t pos = (PH + (uint32_t)(C * q)) & 31u;  // circular position of the block (a constant once unrolled)
 #pragma unroll
-            for (int t = C * q; t < C * q + C; t++) {
-                uint8_t *p = blk_entry(tab, ring[t >> 2], t & 3, pitch) + pos / 8;
+            for (int t = 0; t < C; t++) {
+                const int o = 16 - C + C * q + t;  // byte offset of the dead byte inside the window
+                uint8_t *p = blk_entry(tab, win[o >> 2], o & 3, pitch) + pos / 8;
                 if (C == 16)
                     *(uint16_t *)p = 0;
                 else
                     *p = 0;
             }
+        };
+        auto enter_addr = [&](const int u) {  // entry of stream byte j + L for column u of this superstep
+            const int o = 16 + u + L;
+            return (W *)blk_entry(tab, win[o >> 2], o & 3, pitch);
+        };
+        begin_chunk(0);
+        W *pend = enter_addr(0);
+        W pend_val = *pend;
 #pragma unroll
-            for (int t = C * q; t < C * q + C; t++)
-                *(W *)blk_entry(tab, aw[t >> 2], t & 3, pitch) |= 1u << ((PH + (uint32_t)t) & 31u);
-            if (PLANES) {
-                const W blk = (C == 16 ? 0xffffu : 0xffu) << pos;
-                A7 = (A7 & ~blk) | (tops7 & blk);
+        for (int u = 0; u < 16; u++) {
+            *pend = pend_val | (1u << ((PH + (uint32_t)(u + L)) & 31u));
+            W raw = *(const W *)blk_entry(tab, bc[u >> 2], u & 3, pitch);
+            if (PLANES) raw &= ~(A7 ^ prmt(bw[u >> 2], 0u, 0x8888u | (uint32_t)((u & 3) * 0x1111)));
+            if (u + 1 < 16) {
+                if ((u + 1) % C == 0) begin_chunk((u + 1) / C);
+                pend = enter_addr(u + 1);
+                pend_val = *pend;
             }
+            step(funnel_r(raw, raw, (PH + (uint32_t)u) & 31u));
         }
-        if (!(MAD & 1)) {
-            matches += acc >> e;
-            acc = 0;
-        }
-#pragma unroll
-        for (int w = 0; w < 4; w++) ring[w] = ring[w + 4];
-#pragma unroll
-        for (int w = 0; w < 4; w++) ring[4 + w] = aw[w];
+        matches += acc >> e;
+        acc = 0;
+        slide_window();
     };
 
     int j0 = 0;
@@ -607,45 +599,50 @@ TA_HD uint32_t distance_blk(const uint8_t *a, int m, const uint8_t *b, int n, ui
         j0 += 16;
         phase = 16;
     }
+    // the table now holds stream bytes [j0 - C, j0 + L) = window bytes from offset 16 - C
+    constexpr int SW0 = (16 - C) / 4;
+    uint32_t sw[NW - SW0];
     if (j0 < n) {  // last n % 16 columns: slide the table column by column (exact clear + set), rolled
-        sa.take(aw);
+        take_pattern();
         sb.take(bw);
-        const W tops7 = PLANES ? (gather_bits16(aw, 7) << phase) : 0u;
 #pragma unroll
-        for (int w = 0; w < 4; w++) aw[w] &= CMASK;
-        uint32_t ea[4] = {aw[0], aw[1], aw[2], aw[3]};
-        uint32_t lv[4] = {ring[0], ring[1], ring[2], ring[3]};
+        for (int w = 0; w < NW - SW0; w++) sw[w] = win[SW0 + w];
+        W tops = 0;
+        if (PLANES) {
+            if (C == 16)
+                tops = g7cur << ((phase + 16u) & 31u);
+            else
+                tops = ((g7prev >> 8) << ((phase + 24u) & 31u)) | ((g7cur & 0xffu) << phase);
+        }
         for (int u = 0; u < n - j0; u++) {
+            // byte j - C (sw byte 0) is dead and byte j + L (sw byte 32) takes over its position
+            const W bit = 1u << ((phase + (uint32_t)(u + L)) & 31u);
+            *(W *)blk_entry(tab, sw[0] & 0xffu, 0, pitch) &= ~bit;
+            *(W *)blk_entry(tab, sw[8] & 0xffu, 0, pitch) |= bit;
+            if (PLANES) A7 = (A7 & ~bit) | (tops & bit);
             const uint32_t bch = bw[0] & 0xffu;
             W raw = *(const W *)blk_entry(tab, bch & (CMASK & 0xffu), 0, pitch);
             if (PLANES) raw &= ~(A7 ^ (0u - (bch >> 7)));
-            const uint32_t rot = phase + (uint32_t)u;
-            step(funnel_r(raw, raw, rot));
-            const W bit = 1u << rot;
-            *(W *)blk_entry(tab, lv[0] & 0xffu, 0, pitch) &= ~bit;
-            *(W *)blk_entry(tab, ea[0] & 0xffu, 0, pitch) |= bit;
-            if (PLANES) A7 = (A7 & ~bit) | (tops7 & bit);
+            step(funnel_r(raw, raw, (phase + (uint32_t)u) & 31u));
 #pragma unroll
-            for (int w = 0; w < 3; w++) {
-                bw[w] = funnel_r(bw[w], bw[w + 1], 8);
-                ea[w] = funnel_r(ea[w], ea[w + 1], 8);
-                lv[w] = funnel_r(lv[w], lv[w + 1], 8);
-            }
+            for (int w = 0; w < 3; w++) bw[w] = funnel_r(bw[w], bw[w + 1], 8);
             bw[3] >>= 8;
-            ea[3] >>= 8;
-            lv[3] >>= 8;
+#pragma unroll
+            for (int w = 0; w + 1 < NW - SW0; w++) sw[w] = funnel_r(sw[w], sw[w + 1], 8);
+            sw[NW - 1 - SW0] >>= 8;
         }
+        matches += acc >> e;
+    } else {
+#pragma unroll
+        for (int w = 0; w < NW - SW0; w++) sw[w] = win[SW0 + w];
     }
-    matches += (MAD & 1) ? acc : (acc >> e);
-    // leave the table clean: every set bit belongs to a byte of the ring or of the last chunk taken
+    // leave the table clean: it holds exactly the 32 stream bytes sw[0..7]
 #pragma unroll
-    for (int t = 0; t < 32; t++) *(W *)blk_entry(tab, ring[t >> 2], t & 3, pitch) = 0;
-#pragma unroll
-    for (int t = 0; t < 16; t++) *(W *)blk_entry(tab, aw[t >> 2], t & 3, pitch) = 0;
+    for (int t = 0; t < 32; t++) *(W *)blk_entry(tab, sw[t >> 2], t & 3, pitch) = 0;
     return (uint32_t)diff + (uint32_t)n - matches;
 }
 
-template <bool TRANS, int PLANES, int C, int MAD>
+template <bool TRANS, int PLANES, int C>
 TA_HD uint32_t pair_unit_costs_blk(const uint8_t *a, uint64_t a_len, const uint8_t *b, uint64_t b_len, uint32_t k,
                                    uint8_t *tab, const uint32_t pitch) {
     if (a_len > b_len) {
@@ -661,7 +658,7 @@ TA_HD uint32_t pair_unit_costs_blk(const uint8_t *a, uint64_t a_len, const uint8
     const uint32_t max_k = k < (uint32_t)n ? k : (uint32_t)n;
     if (diff > max_k) return 0xFFFFFFFFu;
     if (m == 0) return (uint32_t)n;
-    const uint32_t d = distance_blk<TRANS, PLANES, C, MAD>(a, m, b, n, max_k, tab, pitch);
+    const uint32_t d = distance_blk<TRANS, PLANES, C>(a, m, b, n, max_k, tab, pitch);
     return d <= max_k ? d : 0xFFFFFFFFu;
 }
 

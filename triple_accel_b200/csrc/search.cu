@@ -12,10 +12,12 @@
 //    rules.  DP rows live in shared memory laid out [array][row][thread] (bank = thread, conflict-free).
 //  * (lev_bitpar.cu) search_filter -- bit-parallel pre-filter for unit costs that flags the haystacks containing
 //    at least one end position with cost <= k, so the exact kernel only runs on those.
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <vector>
 
 #include "ta_common.cuh"
@@ -703,11 +705,24 @@ extern "C" int ta_levenshtein_search_batch_dev(ta_ctx *ctx, const uint8_t *needl
             return search_device(ctx, st, (const uint8_t *)ctx->d_b[0].p, needle_len, hay, hay_off, n, max_hay_len, k,
                                  costs, anchored, hits);
         };
+        static const bool trace = getenv("TA_TRACE_SEARCH") != nullptr;  // host-side phase times (profiling aid)
+        const auto t0 = std::chrono::steady_clock::now();
         const int rc = run();
         if (rc != TA_OK) {
             cudaStreamSynchronize((cudaStream_t)stream);
             free(moff);
             return rc;
+        }
+        if (trace) {
+            const auto t1 = std::chrono::steady_clock::now();
+            emit_matches(n, needle_len, k, search_type == TA_SEARCH_BEST, costs, hits, moff, result);
+            const auto t2 = std::chrono::steady_clock::now();
+            const int rc2 = export_matches(result, moff, out_matches, out_match_off);
+            const auto t3 = std::chrono::steady_clock::now();
+            auto us = [](auto x, auto y) { return (double)std::chrono::duration_cast<std::chrono::nanoseconds>(y - x).count() / 1e3; };
+            fprintf(stderr, "[ta search] device phase %.1f us, emit %.1f us (%zu hits), export %.1f us (%zu matches)\n",
+                    us(t0, t1), us(t1, t2), hits.size(), us(t2, t3), result.size());
+            return rc2;
         }
     }
     emit_matches(n, needle_len, k, search_type == TA_SEARCH_BEST, costs, hits, moff, result);
