@@ -143,7 +143,61 @@ void *ta_host_alloc(size_t bytes) {
 void ta_host_free(void *p) {
     if (p) cudaFreeHost(p);
 }
-void ta_free(void *p) { free(p); }
+// Output arrays (match lists, per-unit offsets, edit lists) are handed to the caller and come back through ta_free.
+// Fresh multi-hundred-KB mallocs are mmap'ed and page-faulted in on first touch (~1 us per 4 KB page: 0.2 ms for the
+// offsets of 100 k haystacks), so freed blocks are parked in a small cache and reused by the next call of similar size.
+namespace {
+struct OutHdr {
+    uint64_t magic, cap;
+};
+constexpr uint64_t OUT_MAGIC = 0x74615f6f75745f31ull;
+constexpr int OUT_SLOTS = 6;
+std::mutex g_out_mu;
+OutHdr *g_out_cache[OUT_SLOTS] = {};
+}  // namespace
+
+void *ta_out_alloc(size_t bytes) {
+    if (bytes == 0) bytes = 1;
+    {
+        std::lock_guard<std::mutex> lock(g_out_mu);
+        for (int i = 0; i < OUT_SLOTS; i++) {
+            OutHdr *h = g_out_cache[i];
+            if (h && h->cap >= bytes && h->cap <= 2 * bytes + (64u << 10)) {
+                g_out_cache[i] = nullptr;
+                return h + 1;
+            }
+        }
+    }
+    OutHdr *h = (OutHdr *)malloc(sizeof(OutHdr) + bytes);
+    if (!h) return nullptr;
+    h->magic = OUT_MAGIC;
+    h->cap = bytes;
+    return h + 1;
+}
+
+void ta_free(void *p) {
+    if (!p) return;
+    OutHdr *h = (OutHdr *)p - 1;
+    if (h->magic != OUT_MAGIC) return;  // not a (live) pointer this library returned: leave it alone
+    if (h->cap >= (64u << 10) && h->cap <= (256u << 20)) {
+        std::lock_guard<std::mutex> lock(g_out_mu);
+        int victim = -1;
+        for (int i = 0; i < OUT_SLOTS; i++) {
+            if (!g_out_cache[i]) {
+                g_out_cache[i] = h;
+                return;
+            }
+            if (g_out_cache[i]->cap < h->cap && (victim < 0 || g_out_cache[i]->cap < g_out_cache[victim]->cap)) victim = i;
+        }
+        if (victim >= 0) {  // keep the larger block
+            OutHdr *old = g_out_cache[victim];
+            g_out_cache[victim] = h;
+            h = old;
+        }
+    }
+    h->magic = 0;
+    free(h);
+}
 
 int ta_costs_valid(ta_costs c) {  // EditCosts::new, reference src/levenshtein.rs:44-52
     if (c.mismatch == 0 || c.gap == 0) return 0;
@@ -448,7 +502,8 @@ int trace_batch(ta_ctx *ctx, bool exp_mode, const uint8_t *a, const uint64_t *a_
     if (rc != TA_OK) return rc;
     if (n && (!a_off || !b_off || !out_dist)) return TA_ERR_BAD_ARG;
     if (n > 0xFFFFFFF0ull) return TA_ERR_TOO_LARGE;
-    uint64_t *eoff = (uint64_t *)calloc(n + 1, sizeof(uint64_t));
+    uint64_t *eoff = (uint64_t *)ta_out_alloc((n + 1) * sizeof(uint64_t));
+    if (eoff) memset(eoff, 0, (n + 1) * sizeof(uint64_t));
     if (!eoff) return TA_ERR_NOMEM;
     std::vector<ta_edit> pool;
     std::vector<uint64_t> pos(n, 0);
@@ -506,14 +561,14 @@ int trace_batch(ta_ctx *ctx, bool exp_mode, const uint8_t *a, const uint64_t *a_
         rc = run();
         if (rc != TA_OK) {
             cudaStreamSynchronize(ctx->stream);
-            free(eoff);
+            ta_free(eoff);
             return rc;
         }
     }
     for (size_t i = 0; i < n; i++) eoff[i + 1] = eoff[i] + num[i];
-    ta_edit *ed = (ta_edit *)malloc((eoff[n] ? eoff[n] : 1) * sizeof(ta_edit));
+    ta_edit *ed = (ta_edit *)ta_out_alloc((eoff[n] ? eoff[n] : 1) * sizeof(ta_edit));
     if (!ed) {
-        free(eoff);
+        ta_free(eoff);
         return TA_ERR_NOMEM;
     }
     for (size_t i = 0; i < n; i++)

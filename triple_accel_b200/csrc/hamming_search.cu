@@ -76,13 +76,14 @@ extern "C" int ta_hamming_search_batch(ta_ctx *ctx, const uint8_t *needle, size_
     }
     if (n) total_hay = hay_off[n] - hay_off[0];
     if (total_hay && !hay) return TA_ERR_BAD_ARG;
-    uint64_t *moff = (uint64_t *)calloc(n + 1, sizeof(uint64_t));
+    uint64_t *moff = (uint64_t *)ta_out_alloc((n + 1) * sizeof(uint64_t));
+    if (moff) memset(moff, 0, (n + 1) * sizeof(uint64_t));
     if (!moff) return TA_ERR_NOMEM;
     std::vector<ta_match> result;
     auto finish = [&]() {
-        ta_match *m = (ta_match *)malloc((result.size() ? result.size() : 1) * sizeof(ta_match));
+        ta_match *m = (ta_match *)ta_out_alloc((result.size() ? result.size() : 1) * sizeof(ta_match));
         if (!m) {
-            free(moff);
+            ta_free(moff);
             return (int)TA_ERR_NOMEM;
         }
         if (!result.empty()) memcpy(m, result.data(), result.size() * sizeof(ta_match));
@@ -142,7 +143,7 @@ extern "C" int ta_hamming_search_batch(ta_ctx *ctx, const uint8_t *needle, size_
         const int rc = run();
         if (rc != TA_OK) {
             cudaStreamSynchronize(ctx->stream);
-            free(moff);
+            ta_free(moff);
             return rc;
         }
     }

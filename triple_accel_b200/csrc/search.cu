@@ -578,9 +578,9 @@ static void emit_matches(size_t n, size_t needle_len, uint32_t k, bool best, ta_
 
 static int export_matches(const std::vector<ta_match> &result, uint64_t *moff, ta_match **out_matches,
                           uint64_t **out_match_off) {
-    ta_match *m = (ta_match *)malloc((result.size() ? result.size() : 1) * sizeof(ta_match));
+    ta_match *m = (ta_match *)ta_out_alloc((result.size() ? result.size() : 1) * sizeof(ta_match));
     if (!m) {
-        free(moff);
+        ta_free(moff);
         return TA_ERR_NOMEM;
     }
     if (!result.empty()) memcpy(m, result.data(), result.size() * sizeof(ta_match));
@@ -611,7 +611,7 @@ extern "C" int ta_levenshtein_search_batch(ta_ctx *ctx, const uint8_t *needle, s
     if (n) total_hay = hay_off[n] - hay_off[0];
     if (total_hay && !hay) return TA_ERR_BAD_ARG;
 
-    uint64_t *moff = (uint64_t *)malloc((n + 1) * sizeof(uint64_t));
+    uint64_t *moff = (uint64_t *)ta_out_alloc((n + 1) * sizeof(uint64_t));
     if (moff) moff[0] = 0;
     if (!moff) return TA_ERR_NOMEM;
     std::vector<ta_match> result;
@@ -637,7 +637,7 @@ extern "C" int ta_levenshtein_search_batch(ta_ctx *ctx, const uint8_t *needle, s
         return export_matches(result, moff, out_matches, out_match_off);
     }
     if (!ta_costs_valid_search(costs)) {  // src/levenshtein.rs:1647
-        free(moff);
+        ta_free(moff);
         return TA_ERR_BAD_COSTS;
     }
     if (n == 0) return export_matches(result, moff, out_matches, out_match_off);
@@ -666,7 +666,7 @@ extern "C" int ta_levenshtein_search_batch(ta_ctx *ctx, const uint8_t *needle, s
         const int rc = run();
         if (rc != TA_OK) {
             cudaStreamSynchronize(ctx->stream);
-            free(moff);
+            ta_free(moff);
             return rc;
         }
     }
@@ -688,7 +688,7 @@ extern "C" int ta_levenshtein_search_batch_dev(ta_ctx *ctx, const uint8_t *needl
     if (!ta_costs_valid_search(costs)) return TA_ERR_BAD_COSTS;
     if (n && (!hay_off || !hay)) return TA_ERR_BAD_ARG;
     if (n > 0xFFFFFFF0ull || needle_len > TA_MAX_STRING_LEN) return TA_ERR_TOO_LARGE;
-    uint64_t *moff = (uint64_t *)malloc((n + 1) * sizeof(uint64_t));
+    uint64_t *moff = (uint64_t *)ta_out_alloc((n + 1) * sizeof(uint64_t));
     if (moff) moff[0] = 0;
     if (!moff) return TA_ERR_NOMEM;
     std::vector<ta_match> result;
@@ -710,7 +710,7 @@ extern "C" int ta_levenshtein_search_batch_dev(ta_ctx *ctx, const uint8_t *needl
         const int rc = run();
         if (rc != TA_OK) {
             cudaStreamSynchronize((cudaStream_t)stream);
-            free(moff);
+            ta_free(moff);
             return rc;
         }
         if (trace) {

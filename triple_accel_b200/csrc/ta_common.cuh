@@ -38,6 +38,8 @@ struct ta_ctx {
 int ta_dev_reserve(ta_ctx *ctx, DevBuf &b, size_t bytes);
 int ta_pin_reserve(ta_ctx *ctx, DevBuf &b, size_t bytes);
 int ta_cuda_fail(ta_ctx *ctx, cudaError_t e, const char *what);
+// caller-owned output arrays (released with ta_free); freed blocks are cached for reuse, see api.cu
+extern "C" void *ta_out_alloc(size_t bytes);
 
 #define TA_CUDA(ctx, call)                                        \
     do {                                                          \
