@@ -39,9 +39,9 @@ static uint32_t run_blk(const uint8_t *a, int la, const uint8_t *b, int lb, uint
 int main(int argc, char **argv) {
     const int iters = argc > 1 ? atoi(argv[1]) : 100000;
     std::mt19937_64 rng(argc > 2 ? atoll(argv[2]) : 12345);
-    std::vector<uint8_t> arena(1 << 16);
+    std::vector<uint8_t> arena(1 << 16);  // strings live at base + {0, 1024, 4096, 6144} + small offsets
     uint8_t *base = (uint8_t *)(((uintptr_t)arena.data() + 4096) & ~(uintptr_t)15);
-    long tests = 0;
+    long tests = 0, duo_tests = 0;
     for (int it = 0; it < iters; it++) {
         const int alphas[5] = {2, 3, 4, 26, 256};
         const int alpha = alphas[rng() % 5];
@@ -50,7 +50,7 @@ int main(int argc, char **argv) {
         const int mode = (int)(rng() % 3);
         const size_t offa = rng() % 64, offb = 1024 + rng() % 64;
         uint8_t *a = base + offa, *b = base + offb;
-        for (int i = 0; i < 2048; i++) base[i] = (uint8_t)rng();  // junk around the strings
+        for (int i = 0; i < 8192; i++) base[i] = (uint8_t)rng();  // junk around the strings
         for (int i = 0; i < la; i++) a[i] = (uint8_t)(rng() % alpha);
         if (mode == 0) {
             lb = (int)(rng() % maxlen);
@@ -134,7 +134,47 @@ int main(int argc, char **argv) {
             }
             tests++;
         }
+        {  // two pairs per thread (bands <= 9 diagonals): this iteration's pair + a partner with the same superstep count
+            // partner = a mutation of this pair with similar lengths
+            std::vector<uint8_t> qa(a, a + la), qb(b, b + lb);
+            for (int rep = 0; rep < 2; rep++) {
+                std::vector<uint8_t> &v = rep ? qb : qa;
+                const int ne = (int)(rng() % 4);
+                for (int e = 0; e < ne; e++) {
+                    const int kind = (int)(rng() % 3);
+                    if (kind == 0 && !v.empty()) v[rng() % v.size()] = (uint8_t)(rng() % alpha);
+                    else if (kind == 1) v.insert(v.begin() + rng() % (v.size() + 1), (uint8_t)(rng() % alpha));
+                    else if (!v.empty()) v.erase(v.begin() + rng() % v.size());
+                }
+            }
+            uint8_t *a2 = base + 4096 + rng() % 64, *b2 = base + 6144 + rng() % 64;
+            memcpy(a2, qa.data(), qa.size());
+            memcpy(b2, qb.data(), qb.size());
+            const uint32_t k = (uint32_t)(rng() % 9);
+            const orc_costs c = {1, 1, 0, 0};
+            const uint32_t want1 = orc_levenshtein_naive_k_with_opts(a, la, b, lb, k, c, NULL, NULL);
+            const uint32_t want2 = orc_levenshtein_naive_k_with_opts(a2, qa.size(), b2, qb.size(), k, c, NULL, NULL);
+            const uint8_t *x1 = a, *y1 = b, *x2 = a2, *y2 = b2;
+            uint64_t lx1 = la, ly1 = lb, lx2 = qa.size(), ly2 = qb.size();
+            uint32_t mk1, mk2, o1 = 0, o2 = 0;
+            const bool dp1 = bitpar::unit_costs_prepare(x1, lx1, y1, ly1, k, mk1, &o1);
+            const bool dp2 = bitpar::unit_costs_prepare(x2, lx2, y2, ly2, k, mk2, &o2);
+            if (dp1 && dp2 && (ly1 >> 4) == (ly2 >> 4)) {
+                static uint32_t tab[128];
+                uint32_t d1, d2;
+                bitpar::distance_duo(x1, (int)lx1, y1, (int)ly1, mk1, x2, (int)lx2, y2, (int)ly2, mk2, (uint8_t *)tab, 4u, d1, d2);
+                check_clean("duo", tab);
+                d1 = d1 <= mk1 ? d1 : 0xFFFFFFFFu;
+                d2 = d2 <= mk2 ? d2 : 0xFFFFFFFFu;
+                if (d1 != want1) report("DUO-A", 0, k, la, lb, want1, d1);
+                if (d2 != want2) report("DUO-B", 0, k, (int)qa.size(), (int)qb.size(), want2, d2);
+                duo_tests++;
+            } else {
+                if (!dp1 && o1 != want1) report("PREP-A", 0, k, la, lb, want1, o1);
+                if (!dp2 && o2 != want2) report("PREP-B", 0, k, (int)qa.size(), (int)qb.size(), want2, o2);
+            }
+        }
     }
-    printf("tests %ld bad %ld\n", tests, bad);
+    printf("tests %ld (duo %ld) bad %ld\n", tests, duo_tests, bad);
     return bad != 0;
 }

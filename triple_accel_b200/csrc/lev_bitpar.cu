@@ -115,6 +115,57 @@ __global__ void __launch_bounds__(256) lev_bitpar_blk_kernel(const uint8_t *__re
     }
 }
 
+// Two pairs per thread (lev_bitpar_core.cuh: distance_duo): bands of <= 9 diagonals, unit costs without
+// transpositions.  Work item w = pairs 2w and 2w + 1; when the two cannot share a recurrence (different numbers of
+// 16-column supersteps, an answer known without DP, an odd last pair) each goes through the single-pair routine.
+__global__ void __launch_bounds__(128, 3) lev_bitpar_duo_kernel(const uint8_t *__restrict__ a,
+                                                                const uint64_t *__restrict__ a_off,
+                                                                const uint8_t *__restrict__ b,
+                                                                const uint64_t *__restrict__ b_off,
+                                                                const uint32_t *__restrict__ idx, size_t n, uint32_t k,
+                                                                uint32_t *__restrict__ out) {
+    extern __shared__ __align__(16) uint8_t tabs_raw[];
+    uint32_t *tabs = (uint32_t *)tabs_raw;
+    const uint32_t nt = blockDim.x;
+    for (uint32_t q = threadIdx.x; q < 128u * nt; q += nt) tabs[q] = 0;
+    __syncthreads();
+    uint8_t *tab = (uint8_t *)(tabs + threadIdx.x);
+    const uint32_t pitch = nt * 4u;
+    const size_t total = (size_t)gridDim.x * nt;
+    const size_t items = (n + 1) / 2;
+    size_t w = (size_t)blockIdx.x * nt + threadIdx.x;
+    PairRef cur0 = load_pair_ref(a_off, b_off, idx, 2 * w, n), cur1 = load_pair_ref(a_off, b_off, idx, 2 * w + 1, n);
+    for (; w < items; w += total) {
+        const size_t wn = w + total;
+        const PairRef nx0 = load_pair_ref(a_off, b_off, idx, 2 * wn, n);  // in flight during this item
+        const PairRef nx1 = load_pair_ref(a_off, b_off, idx, 2 * wn + 1, n);
+        const bool has1 = 2 * w + 1 < n;
+        const uint8_t *pa0 = a + cur0.a0, *pb0 = b + cur0.b0, *pa1 = a + cur1.a0, *pb1 = b + cur1.b0;
+        uint64_t la0 = cur0.alen, lb0 = cur0.blen, la1 = cur1.alen, lb1 = cur1.blen;
+        uint32_t mk0 = 0, mk1 = 0, r0 = 0, r1 = 0;
+        const bool dp0 = bitpar::unit_costs_prepare(pa0, la0, pb0, lb0, k, mk0, &r0);
+        const bool dp1 = has1 && bitpar::unit_costs_prepare(pa1, la1, pb1, lb1, k, mk1, &r1);
+        if (dp0 && dp1 && (lb0 >> 4) == (lb1 >> 4)) {
+            bitpar::distance_duo(pa0, (int)la0, pb0, (int)lb0, mk0, pa1, (int)la1, pb1, (int)lb1, mk1, tab, pitch, r0, r1);
+            r0 = r0 <= mk0 ? r0 : 0xFFFFFFFFu;
+            r1 = r1 <= mk1 ? r1 : 0xFFFFFFFFu;
+        } else {
+            if (dp0) {
+                r0 = bitpar::distance_blk<false, 1, 16>(pa0, (int)la0, pb0, (int)lb0, mk0, tab, pitch);
+                r0 = r0 <= mk0 ? r0 : 0xFFFFFFFFu;
+            }
+            if (dp1) {
+                r1 = bitpar::distance_blk<false, 1, 16>(pa1, (int)la1, pb1, (int)lb1, mk1, tab, pitch);
+                r1 = r1 <= mk1 ? r1 : 0xFFFFFFFFu;
+            }
+        }
+        out[cur0.pair] = r0;
+        if (has1) out[cur1.pair] = r1;
+        cur0 = nx0;
+        cur1 = nx1;
+    }
+}
+
 typedef void (*lev_kern_t)(const uint8_t *, const uint64_t *, const uint8_t *, const uint64_t *, const uint32_t *,
                            size_t, uint32_t, uint32_t *);
 template <bool TRANS, int C>
@@ -157,6 +208,19 @@ int ta_launch_lev_bitpar(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, c
         const uint32_t kk = k < max_len ? k : max_len;
         const uint32_t wmax = kk + 1 + (costs.transpose ? 1u : 0u);  // widest band any pair of the batch can have
         const bool use_blk = !(variant && (variant[0] == 's' || variant[0] == 't')) && wmax <= 25;
+        // bands of <= 9 diagonals without transpositions: two pairs per thread (TA_BLK_DUO=0 disables)
+        static const int blk_duo = getenv("TA_BLK_DUO") ? atoi(getenv("TA_BLK_DUO")) : 1;
+        if (use_blk && blk_duo && !costs.transpose && wmax <= 9 && blk_planes == 1 && blk_c == 0) {
+            const int nt = 128;
+            const size_t smem = (size_t)128 * nt * 4;
+            const size_t items = (n + 1) / 2;
+            const unsigned blocks = (unsigned)std::min<size_t>((items + nt - 1) / nt, (size_t)ctx->sm_count * 3);
+            TA_CUDA(ctx, cudaFuncSetAttribute(lev_bitpar_duo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            lev_bitpar_duo_kernel<<<blocks, nt, smem, st>>>(a, a_off, b, b_off, idx, n, k, out);
+            ctx->launches++;
+            TA_CUDA(ctx, cudaGetLastError());
+            return TA_OK;
+        }
         if (use_blk) {
             const int C = (wmax <= 17 && blk_c != 8) ? 16 : 8;
             const int nt = env_threads ? env_threads : (blk_planes ? 128 : 224);

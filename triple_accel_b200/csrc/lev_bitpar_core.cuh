@@ -662,6 +662,230 @@ TA_HD uint32_t pair_unit_costs_blk(const uint8_t *a, uint64_t a_len, const uint8
     return d <= max_k ? d : 0xFFFFFFFFu;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// distance_duo: TWO pairs per thread for bands of W <= 9 diagonals (unit costs without transpositions, max_k <= 8).
+//
+// The block-table scheme of distance_blk with a 16-position frame (C = 8, L = 8) needs only 16 bits per pair, so two
+// pairs share every 32-bit word: pair P owns bits [16 P, 16 P + 16) of the table entries (each pair reads and writes
+// only its own half-word, so the two never interfere), of the A7 plane and of VP / VN / D0.  The recurrence, the
+// plane test, the rotation and the match counting are then issued ONCE for both pairs; only the byte extraction and
+// the table accesses stay per pair.  The packed recurrence is two exact, independent 16-bit recurrences:
+//   * bit 15 of each half is masked out of the addends ((Eq & VP & M) + (VP & M), M = 0x7fff7fff), so no carry leaves
+//     a half; bit 15 of the sum then holds the incoming carry c14 and D0 = ((S ^ VPm) | Eq | VN) still equals the
+//     16-bit result at that bit (if Eq15 = 0 the 16-bit word has (A + VP) ^ VP = c14 there as well; if Eq15 = 1, D0 = 1);
+//   * X = (D0 >> 1) & M shifts a zero into row 15 of each half, as a 16-bit shift would.
+// Both pairs must have the same number of full 16-column supersteps (n_A / 16 == n_B / 16); the last columns run in a
+// rolled loop that counts each pair's matches only inside its own length.  dP = exact distance if <= max_k.
+struct DuoSide {  // per-pair state of the duo kernel
+    Stream sa, sb;
+    uint32_t win[12];  // class bits of pattern-stream bytes [16 s - 16, 16 s + 32)
+    uint32_t bw[4], bc[4];
+    uint32_t g7prev, g7cur;
+    int n, diff, e, dhi;
+};
+
+TA_HD void distance_duo(const uint8_t *aA, int mA, const uint8_t *bA, int nA, uint32_t maxkA, const uint8_t *aB, int mB,
+                        const uint8_t *bB, int nB, uint32_t maxkB, uint8_t *tab, const uint32_t pitch, uint32_t &dA,
+                        uint32_t &dB) {
+    constexpr uint32_t CMASK = 0x7f7f7f7fu, M = 0x7fff7fffu;
+    DuoSide sd[2];
+    auto setup = [&](DuoSide &x, const uint8_t *a, int m, const uint8_t *b, int n, uint32_t max_k) {
+        x.n = n;
+        x.diff = n - m;
+        x.e = (int)((max_k - (uint32_t)x.diff) >> 1);
+        x.dhi = x.diff + x.e;
+        x.sa.init((intptr_t)a - x.dhi, (uintptr_t)a, (uintptr_t)a + m - 1);
+        x.sb.init((intptr_t)b, (uintptr_t)b, (uintptr_t)b + n - 1);
+#pragma unroll
+        for (int w = 0; w < 12; w++) x.win[w] = 0;
+        x.g7prev = x.g7cur = 0;
+    };
+    setup(sd[0], aA, mA, bA, nA, maxkA);
+    setup(sd[1], aB, mB, bB, nB, maxkB);
+    auto half_ptr = [&](int P, uint32_t w, int t) { return (uint16_t *)(tab + byte_of(w, t) * pitch + 2 * P); };
+
+    uint32_t A7 = 0, VP = 0, emask = 0;
+#pragma unroll
+    for (int P = 0; P < 2; P++) {
+        DuoSide &x = sd[P];
+        uint32_t t0[4];
+        x.sa.take(t0);  // T_0
+        x.g7cur = gather_bits16(t0, 7);
+        A7 |= (x.g7cur & 0xffu) << (16 * P);
+#pragma unroll
+        for (int w = 0; w < 4; w++) x.win[4 + w] = t0[w] & CMASK;
+#pragma unroll
+        for (int t = 0; t < 8; t++) *half_ptr(P, x.win[4 + (t >> 2)], t & 3) |= (uint16_t)(1u << t);
+        const uint32_t vp16 = x.dhi >= 16 ? 0u : ((0xffffu << x.dhi) & 0xffffu);
+        VP |= vp16 << (16 * P);
+        emask |= (1u << x.e) << (16 * P);
+    }
+    uint32_t VN = ~VP;
+    uint32_t acc = 0, matches[2] = {0, 0};
+
+    auto step = [&](const uint32_t Eq, const uint32_t cmask) {
+        const uint32_t VPm = VP & M;
+        const uint32_t S = (Eq & VPm) + VPm;
+        const uint32_t D0 = (S ^ VPm) | Eq | VN;
+        const uint32_t HP = VN | ~(D0 | VP);
+        const uint32_t Ds = D0 >> 1;
+        const uint32_t Y = ~((Ds & M) | HP);
+        VN = Ds & M & HP;
+        VP = (D0 & VP) | Y;
+        acc += D0 & cmask;
+    };
+    auto take_side = [&](DuoSide &x) {
+        uint32_t t[4];
+        x.sa.take(t);
+        x.g7prev = x.g7cur;
+        x.g7cur = gather_bits16(t, 7);
+#pragma unroll
+        for (int w = 0; w < 4; w++) x.win[8 + w] = t[w] & CMASK;
+        x.sb.take(x.bw);
+#pragma unroll
+        for (int w = 0; w < 4; w++) x.bc[w] = x.bw[w] & CMASK;
+    };
+
+    const int steps = nA >> 4;  // == nB >> 4
+    for (int s = 0; s < steps; s++) {
+        take_side(sd[0]);
+        take_side(sd[1]);
+        // start of chunk q (8 columns): planes of the entering block, dead block [g - 8, g) zeroed by value
+        auto begin_chunk = [&](const int q) {
+#pragma unroll
+            for (int P = 0; P < 2; P++) {
+                DuoSide &x = sd[P];
+                const uint32_t blk = (q == 0 ? 0xff00u : 0x00ffu) << (16 * P);
+                const uint32_t tops = (q == 0 ? x.g7prev : x.g7cur) << (16 * P);
+                A7 = (A7 & ~blk) | (tops & blk);
+#pragma unroll
+                for (int t = 0; t < 8; t++) {
+                    const int o = 8 + 8 * q + t;  // window offset of the dead byte; its block sits in byte (1 - q) of the half
+                    *((uint8_t *)half_ptr(P, x.win[o >> 2], o & 3) + (1 - q)) = 0;
+                }
+            }
+        };
+        auto enter_ptr = [&](const int P, const int u) {  // half-entry of stream byte j + 8 for column u
+            const int o = 24 + u;
+            return half_ptr(P, sd[P].win[o >> 2], o & 3);
+        };
+        begin_chunk(0);
+        uint16_t *pend[2] = {enter_ptr(0, 0), enter_ptr(1, 0)};
+        uint32_t pend_val[2] = {*pend[0], *pend[1]};
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            const uint32_t bit = 1u << ((u + 8) & 15);
+            *pend[0] = (uint16_t)(pend_val[0] | bit);
+            *pend[1] = (uint16_t)(pend_val[1] | bit);
+            const uint32_t rawA = *half_ptr(0, sd[0].bc[u >> 2], u & 3);
+            const uint32_t rawB = *half_ptr(1, sd[1].bc[u >> 2], u & 3);
+            uint32_t raw = prmt(rawA, rawB, 0x5410u);
+            const uint32_t i = (uint32_t)(u & 3);
+            raw &= ~(A7 ^ prmt(sd[0].bw[u >> 2], sd[1].bw[u >> 2], (0x8u | i) | ((0x8u | i) << 4) | ((0xcu | i) << 8) | ((0xcu | i) << 12)));
+            if (u + 1 < 16) {
+                if (u + 1 == 8) begin_chunk(1);
+                pend[0] = enter_ptr(0, u + 1);
+                pend[1] = enter_ptr(1, u + 1);
+                pend_val[0] = *pend[0];
+                pend_val[1] = *pend[1];
+            }
+            uint32_t Eq = raw;
+            if (u != 0) {
+                const uint32_t m1 = (0xffffu >> u) * 0x10001u;
+                Eq = ((raw >> u) & m1) | ((raw << (16 - u)) & ~m1);
+            }
+            step(Eq, emask);
+        }
+        matches[0] += (acc & 0xffffu) >> sd[0].e;
+        matches[1] += (acc >> 16) >> sd[1].e;
+        acc = 0;
+#pragma unroll
+        for (int P = 0; P < 2; P++)
+#pragma unroll
+            for (int w = 0; w < 8; w++) sd[P].win[w] = sd[P].win[w + 4];
+    }
+    // tables now hold stream bytes [j0 - 8, j0 + 8) of each pair = window bytes from offset 8
+    const int j0 = steps << 4;
+    const int rA = nA - j0, rB = nB - j0, r = rA > rB ? rA : rB;
+    uint32_t sw[2][10];
+    if (r > 0) {  // last columns: exact per-column sliding, rolled; each pair counts only its own columns
+        take_side(sd[0]);
+        take_side(sd[1]);
+        uint32_t tops = 0;
+#pragma unroll
+        for (int P = 0; P < 2; P++) {
+            tops |= ((sd[P].g7prev & 0xff00u) | (sd[P].g7cur & 0x00ffu)) << (16 * P);
+#pragma unroll
+            for (int w = 0; w < 10; w++) sw[P][w] = sd[P].win[2 + w];
+        }
+        for (int u = 0; u < r; u++) {
+            const uint32_t bit = 1u << ((u + 8) & 15);
+#pragma unroll
+            for (int P = 0; P < 2; P++) {
+                // byte j - 8 (sw byte 0) is dead and byte j + 8 (sw byte 16) takes over its position
+                *half_ptr(P, sw[P][0] & 0xffu, 0) &= (uint16_t)~bit;
+                *half_ptr(P, sw[P][4] & 0xffu, 0) |= (uint16_t)bit;
+            }
+            const uint32_t bit2 = bit * 0x10001u;
+            A7 = (A7 & ~bit2) | (tops & bit2);
+            const uint32_t chA = sd[0].bw[0] & 0xffu, chB = sd[1].bw[0] & 0xffu;
+            uint32_t raw = (uint32_t)*half_ptr(0, chA & 0x7fu, 0) | ((uint32_t)*half_ptr(1, chB & 0x7fu, 0) << 16);
+            raw &= ~(A7 ^ (((0u - (chA >> 7)) & 0xffffu) | ((0u - (chB >> 7)) << 16)));
+            const uint32_t m1 = (0xffffu >> u) * 0x10001u;
+            const uint32_t Eq = u ? (((raw >> u) & m1) | ((raw << (16 - u)) & ~m1)) : raw;
+            step(Eq, (u < rA ? (emask & 0xffffu) : 0u) | (u < rB ? (emask & 0xffff0000u) : 0u));
+#pragma unroll
+            for (int P = 0; P < 2; P++) {
+#pragma unroll
+                for (int w = 0; w < 3; w++) sd[P].bw[w] = funnel_r(sd[P].bw[w], sd[P].bw[w + 1], 8);
+                sd[P].bw[3] >>= 8;
+#pragma unroll
+                for (int w = 0; w < 9; w++) sw[P][w] = funnel_r(sw[P][w], sw[P][w + 1], 8);
+                sw[P][9] >>= 8;
+            }
+        }
+        matches[0] += (acc & 0xffffu) >> sd[0].e;
+        matches[1] += (acc >> 16) >> sd[1].e;
+    } else {
+#pragma unroll
+        for (int P = 0; P < 2; P++)
+#pragma unroll
+            for (int w = 0; w < 10; w++) sw[P][w] = sd[P].win[2 + w];
+    }
+    // leave the table clean: each half holds exactly the 16 stream bytes sw[P][0..3]
+#pragma unroll
+    for (int P = 0; P < 2; P++)
+#pragma unroll
+        for (int t = 0; t < 16; t++) *half_ptr(P, sw[P][t >> 2], t & 3) = 0;
+    dA = (uint32_t)sd[0].diff + (uint32_t)nA - matches[0];
+    dB = (uint32_t)sd[1].diff + (uint32_t)nB - matches[1];
+}
+
+// One pair's contract up to the point where the DP is needed (reference src/levenshtein.rs:386-430 with unit
+// costs): swaps so that a is the shorter string, clamps k; returns false when the answer is already known (*out).
+TA_HD bool unit_costs_prepare(const uint8_t *&a, uint64_t &a_len, const uint8_t *&b, uint64_t &b_len, uint32_t k,
+                              uint32_t &max_k, uint32_t *out) {
+    if (a_len > b_len) {
+        const uint8_t *tp = a;
+        a = b;
+        b = tp;
+        const uint64_t tl = a_len;
+        a_len = b_len;
+        b_len = tl;
+    }
+    const uint32_t diff = (uint32_t)(b_len - a_len);
+    max_k = k < (uint32_t)b_len ? k : (uint32_t)b_len;
+    if (diff > max_k) {
+        *out = 0xFFFFFFFFu;
+        return false;
+    }
+    if (a_len == 0) {
+        *out = (uint32_t)b_len;
+        return false;
+    }
+    return true;
+}
+
 template <bool TRANS, int PLANES, typename W>
 TA_HD uint32_t pair_unit_costs_tab(const uint8_t *a, uint64_t a_len, const uint8_t *b, uint64_t b_len, uint32_t k,
                                    uint8_t *tab, const uint32_t pitch) {
