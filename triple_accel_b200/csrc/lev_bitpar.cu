@@ -293,13 +293,17 @@ template <typename W, bool TRANS>
 __global__ void __launch_bounds__(128) search_filter_kernel(const uint8_t *__restrict__ needle, uint32_t N,
                                                             const uint8_t *__restrict__ hay,
                                                             const uint64_t *__restrict__ hay_off, size_t n, uint32_t k,
-                                                            uint32_t *__restrict__ idx_out,
+                                                            uint32_t subs, uint32_t *__restrict__ idx_out,
                                                             uint32_t *__restrict__ counter) {
     __shared__ W peq[256];
     for (int c = threadIdx.x; c < 256; c += blockDim.x) peq[c] = 0;
     __syncthreads();
-    if (threadIdx.x == 0)
-        for (uint32_t i = 0; i < N; i++) peq[needle[i]] |= (W)1 << i;
+    if (threadIdx.x < N) {
+        if (sizeof(W) == 4)
+            atomicOr((unsigned int *)&peq[needle[threadIdx.x]], 1u << threadIdx.x);
+        else
+            atomicOr((unsigned long long *)&peq[needle[threadIdx.x]], 1ull << threadIdx.x);
+    }
     __syncthreads();
 
     const size_t h = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -370,37 +374,181 @@ __global__ void __launch_bounds__(128) search_filter_kernel(const uint8_t *__res
             hit |= (x >= seg_begin) & (x < seg_end) & (score <= k);
         }
         if (hit) {
-            // segment (h, s) contains a match end: append its code (rare event, one atomic)
-            idx_out[atomicAdd(counter, 1u)] = (uint32_t)(h * gridDim.y + blockIdx.y);
+            // a match end in [x0, x0 + 16) (rare event): append the codes of the TA_SEARCH_SUB-byte sub-segments from
+            // there to the end of this thread's segment, which the exact kernel will re-run
+            const uint64_t first = (x0 > seg_begin ? x0 : seg_begin) / TA_SEARCH_SUB, last = (seg_end - 1) / TA_SEARCH_SUB;
+            for (uint64_t sub = first; sub <= last; sub++)
+                idx_out[atomicAdd(counter, 1u)] = (uint32_t)(h * subs + sub);
             return;
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// search_pigeon_kernel: the pre-filter for needles of <= 32 bytes when k + 1 (2k + 1 with transpositions) needle
+// pieces are at least PIGEON_MIN_PIECE bytes long.  An alignment with <= k unit-cost edits leaves at least one of
+// k + 1 consecutive needle pieces intact (a transposition can damage two, hence 2k + 1), so a haystack position can
+// only be a match end if one of the pieces occurs EXACTLY a bounded distance before it.  Exact occurrences of all
+// pieces are found with one shift-and recurrence over the needle's match masks -- the very table Myers' recurrence
+// uses: D = ((D << 1) | starts) & peq[byte], piece i ends here iff bit (its last needle index) of D is set -- which is
+// 2 ALU instructions per haystack byte instead of ~11.  The table is replicated per shared-memory bank ([byte][lane]),
+// so the data-dependent look-ups of a warp never conflict.  A candidate (rare: a piece of >= 4 random bytes) is
+// verified on the spot by the same thread with Myers' semi-global recurrence over the <= N + 2k bytes that can hold a
+// match through this piece occurrence; only confirmed end positions flag their TA_SEARCH_SUB-byte sub-segment, so
+// the flags are as precise as the Myers pre-filter's.  Thread (h, s) owns the END positions inside segment s of
+// haystack h and scans N + k + (longest piece) bytes before it so that every piece of such a match is seen.
+constexpr uint32_t PIGEON_MIN_PIECE = 4;
+
+template <bool TRANS>
+__global__ void __launch_bounds__(128) search_pigeon_kernel(const uint8_t *__restrict__ needle, uint32_t N,
+                                                            const uint8_t *__restrict__ hay,
+                                                            const uint64_t *__restrict__ hay_off, size_t n, uint32_t k,
+                                                            uint32_t pieces, uint32_t subs,
+                                                            uint32_t *__restrict__ idx_out,
+                                                            uint32_t *__restrict__ counter) {
+    extern __shared__ uint32_t peqr[];  // [256][32]: entry c of lane l at peqr[c * 32 + l]
+    for (uint32_t q = threadIdx.x; q < 256u * 32u; q += blockDim.x) peqr[q] = 0;
+    __syncthreads();
+    for (uint32_t q = threadIdx.x; q < N * 32u; q += blockDim.x)
+        atomicOr(&peqr[(uint32_t)needle[q >> 5] * 32u + (q & 31u)], 1u << (q >> 5));
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t *peq = peqr + lane;  // this lane's copy: entry c at peq[c * 32]
+
+    const size_t h = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= n) return;
+    const uint64_t h0 = hay_off[h], h1 = hay_off[h + 1];
+    const uint64_t H = h1 - h0;
+    const uint64_t seg_begin = (uint64_t)blockIdx.y * FILTER_SEG;
+    if (seg_begin >= H) return;
+    const uint64_t seg_end = seg_begin + FILTER_SEG < H ? seg_begin + FILTER_SEG : H;
+    const uint8_t *p = hay + h0;
+
+    // pieces: piece i = needle [s_i, s_i + l_i), l_i = N / pieces (+1 for the first N % pieces)
+    const uint32_t base_len = N / pieces, extra = N % pieces;
+    uint32_t starts = 0, finals = 0;
+    for (uint32_t i = 0, s = 0; i < pieces; i++) {
+        const uint32_t l = base_len + (i < extra ? 1u : 0u);
+        starts |= 1u << s;
+        finals |= 1u << (s + l - 1);
+        s += l;
+    }
+    const uint64_t back = (uint64_t)N + k + base_len + 1;
+    const uint64_t start = seg_begin > back ? seg_begin - back : 0;
+    uint32_t flagged = 0;  // sub-segments of this segment already appended (bit = sub index inside the segment)
+
+    // a piece whose last byte is haystack byte q (its last needle index = fin): confirm the match ends it allows
+    auto verify = [&](const uint64_t q, const uint32_t fin) {
+        const uint32_t r = N - 1 - fin;  // needle bytes after the piece
+        // end byte indices of matches through this occurrence: [q + r - k, q + r + k], inside this thread's segment
+        uint64_t lo = q + r > k ? q + r - k : 0, hi = q + r + k;
+        if (lo < seg_begin) lo = seg_begin;
+        if (hi > seg_end - 1) hi = seg_end - 1;
+        if (lo > hi) return;
+        // such a match starts at most (fin + 1) + k bytes before the piece's end
+        const uint64_t st = q + 1 > (uint64_t)fin + 1 + k ? q + 1 - (fin + 1 + k) : 0;
+        uint32_t VP = 0xffffffffu, VN = 0, D0prev = 0xffffffffu, Eqprev = 0, score = N;
+        const uint32_t top = 1u << (N - 1);
+        for (uint64_t t = st; t <= hi; t++) {
+            const uint32_t Eq = peq[(uint32_t)p[t] * 32u];
+            uint32_t D0 = (((Eq & VP) + VP) ^ VP) | Eq | VN;
+            if (TRANS) {
+                D0 |= ((~D0prev & Eq) << 1) & Eqprev;
+                D0prev = D0;
+                Eqprev = Eq;
+            }
+            uint32_t HP = VN | ~(D0 | VP);
+            uint32_t HN = D0 & VP;
+            score += (HP & top) ? 1u : 0u;
+            score -= (HN & top) ? 1u : 0u;
+            HP <<= 1;
+            HN <<= 1;
+            VP = HN | ~(D0 | HP);
+            VN = D0 & HP;
+            if (t >= lo && score <= k) {
+                const uint32_t sub_in = (uint32_t)((t - seg_begin) / TA_SEARCH_SUB);
+                if (!(flagged >> sub_in & 1u)) {
+                    flagged |= 1u << sub_in;
+                    idx_out[atomicAdd(counter, 1u)] = (uint32_t)(h * subs + t / TA_SEARCH_SUB);
+                }
+            }
+        }
+    };
+
+    bitpar::Stream hs;
+    hs.init((intptr_t)(p + start), (uintptr_t)p, (uintptr_t)(p + H - 1));
+    uint32_t D = 0;
+    for (uint64_t x0 = start; x0 < seg_end; x0 += 16) {
+        uint32_t wds[4];
+        hs.take(wds);
+        const uint32_t Dstart = D;
+        uint32_t seen = 0;
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            const uint32_t ch = bitpar::byte_of(wds[u >> 2], u & 3);
+            D = ((D << 1) | starts) & peq[ch * 32u];
+            seen |= D;
+        }
+        if (seen & finals) {  // some piece ends inside this chunk: replay it byte by byte
+            uint32_t Dr = Dstart;
+            for (int u = 0; u < 16; u++) {
+                const uint64_t q = x0 + (uint64_t)u;
+                if (q >= H) break;  // bytes past the haystack are don't-care padding of the last vector
+                const uint32_t ch = (wds[u >> 2] >> (8 * (u & 3))) & 0xffu;
+                Dr = ((Dr << 1) | starts) & peq[ch * 32u];
+                uint32_t f = Dr & finals;
+                while (f) {
+                    const uint32_t fin = (uint32_t)__ffs((int)f) - 1u;
+                    f &= f - 1u;
+                    verify(q, fin);
+                }
+            }
         }
     }
 }
 
 }  // namespace
 
-// appends the codes (haystack * segs + segment, unordered) of the 512-byte haystack segments that contain at least
-// one end position of unit-cost distance <= k to idx_out, counting them in *counter (must be zero on entry);
-// *segs_out = segments per haystack.  Needs needle_len in [1, 64], n * segs < 2^32; max_hay = longest haystack.
+// appends the codes (haystack * subs + sub-segment, unordered) of the TA_SEARCH_SUB-byte haystack sub-segments that
+// contain at least one end position of unit-cost distance <= k to idx_out, counting them in *counter (must be zero on
+// entry); *subs_out = sub-segments per haystack.  Needs needle_len in [1, 64], n * subs < 2^32; max_hay = longest
+// haystack.  Needles of <= 32 bytes whose k + 1 pieces are long enough use the exact-piece filter (search_pigeon_kernel),
+// the rest Myers' recurrence over the whole haystack (search_filter_kernel); TA_SEARCH_FILTER=myers|pigeon forces one.
 int ta_launch_search_filter(ta_ctx *ctx, const uint8_t *needle_dev, uint32_t needle_len, const uint8_t *hay,
                             const uint64_t *hay_off, size_t n, uint64_t max_hay, uint32_t k, bool transpose,
-                            uint32_t *idx_out, uint32_t *counter, uint32_t *segs_out, cudaStream_t st) {
+                            uint32_t *idx_out, uint32_t *counter, uint32_t *subs_out, cudaStream_t st) {
     if (needle_len == 0 || needle_len > 64) return TA_ERR_TOO_LARGE;
+    const uint64_t subs = max_hay ? (max_hay + TA_SEARCH_SUB - 1) / TA_SEARCH_SUB : 1;
     const uint64_t segs = max_hay ? (max_hay + FILTER_SEG - 1) / FILTER_SEG : 1;
-    *segs_out = (uint32_t)segs;
+    *subs_out = (uint32_t)subs;
     if (n == 0 || max_hay == 0) return TA_OK;
-    if (segs > 65535 || (uint64_t)n * segs > 0xFFFFFFF0ull) return TA_ERR_TOO_LARGE;
+    if (segs > 65535 || (uint64_t)n * subs > 0xFFFFFFF0ull) return TA_ERR_TOO_LARGE;
     const dim3 grid((unsigned)((n + 127) / 128), (unsigned)segs);
-    if (needle_len <= 32) {
+    static const char *force = getenv("TA_SEARCH_FILTER");
+    const uint32_t pieces = transpose ? 2 * k + 1 : k + 1;
+    bool pigeon = needle_len <= 32 && pieces <= needle_len && needle_len / pieces >= PIGEON_MIN_PIECE;
+    if (force && force[0] == 'm') pigeon = false;
+    if (force && force[0] == 'p' && needle_len <= 32 && pieces <= needle_len) pigeon = true;
+    if (pigeon) {
+        const size_t smem = 256 * 32 * sizeof(uint32_t);
+        if (transpose) {
+            TA_CUDA(ctx, cudaFuncSetAttribute(search_pigeon_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            search_pigeon_kernel<true><<<grid, 128, smem, st>>>(needle_dev, needle_len, hay, hay_off, n, k, pieces, (uint32_t)subs, idx_out, counter);
+        } else {
+            TA_CUDA(ctx, cudaFuncSetAttribute(search_pigeon_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            search_pigeon_kernel<false><<<grid, 128, smem, st>>>(needle_dev, needle_len, hay, hay_off, n, k, pieces, (uint32_t)subs, idx_out, counter);
+        }
+    } else if (needle_len <= 32) {
         if (transpose)
-            search_filter_kernel<uint32_t, true><<<grid, 128, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, k, idx_out, counter);
+            search_filter_kernel<uint32_t, true><<<grid, 128, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, k, (uint32_t)subs, idx_out, counter);
         else
-            search_filter_kernel<uint32_t, false><<<grid, 128, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, k, idx_out, counter);
+            search_filter_kernel<uint32_t, false><<<grid, 128, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, k, (uint32_t)subs, idx_out, counter);
     } else {
         if (transpose)
-            search_filter_kernel<uint64_t, true><<<grid, 128, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, k, idx_out, counter);
+            search_filter_kernel<uint64_t, true><<<grid, 128, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, k, (uint32_t)subs, idx_out, counter);
         else
-            search_filter_kernel<uint64_t, false><<<grid, 128, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, k, idx_out, counter);
+            search_filter_kernel<uint64_t, false><<<grid, 128, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, k, (uint32_t)subs, idx_out, counter);
     }
     ctx->launches++;
     TA_CUDA(ctx, cudaGetLastError());

@@ -29,9 +29,8 @@ int ta_launch_search_filter(ta_ctx *ctx, const uint8_t *needle_dev, uint32_t nee
 
 namespace {
 
-struct Hit {  // one reported end position
-    uint32_t hay, cost;
-    uint64_t end, len;
+struct Hit {  // one reported end position (string lengths are < 2^22, TA_MAX_STRING_LEN)
+    uint32_t hay, end, len, cost;
 };
 
 struct SearchArgs {
@@ -40,7 +39,7 @@ struct SearchArgs {
     const uint64_t *hay_off;
     const uint32_t *idx;  // optional: work item w -> haystack idx[w] (or a segment code, see segs)
     uint32_t segs;        // 0: idx holds haystack indices.  > 0: idx holds haystack * segs + segment codes and the
-                          // item covers only that TA_SEARCH_SEG-byte segment after a warm-up of `warm` bytes
+                          // item covers only that TA_SEARCH_SUB-byte segment after a warm-up of `warm` bytes
     uint32_t warm;
     size_t n;
     const uint32_t *n_dev;  // optional: the number of work items lives on the device (written by the pre-filter)
@@ -197,8 +196,8 @@ __global__ void __launch_bounds__(64) search_exact_kernel(const SearchArgs args)
                 Hit h;
                 h.hay = hidx;
                 h.cost = left_dp;
-                h.end = x;
-                h.len = left_len;
+                h.end = (uint32_t)x;
+                h.len = (uint32_t)left_len;
                 args.hits[slot] = h;
             }
         }
@@ -237,8 +236,8 @@ __global__ void __launch_bounds__(128) search_wave_kernel(const SearchArgs args)
     uint64_t col0 = 0, emit_from = 0;  // columns are numbered from col0; hits are reported for x > emit_from
     if (args.segs) {
         const uint64_t seg = code % args.segs;
-        emit_from = seg * TA_SEARCH_SEG;
-        const uint64_t seg_end = emit_from + TA_SEARCH_SEG < H ? emit_from + TA_SEARCH_SEG : H;
+        emit_from = seg * TA_SEARCH_SUB;
+        const uint64_t seg_end = emit_from + TA_SEARCH_SUB < H ? emit_from + TA_SEARCH_SUB : H;
         col0 = emit_from > args.warm ? emit_from - args.warm : 0;
         hay += col0;
         H = seg_end - col0;
@@ -378,8 +377,8 @@ __global__ void __launch_bounds__(128) search_wave_kernel(const SearchArgs args)
                         Hit h;
                         h.hay = hidx;
                         h.cost = dp;
-                        h.end = (uint64_t)x + col0;
-                        h.len = len;
+                        h.end = (uint32_t)((uint64_t)x + col0);
+                        h.len = (uint32_t)len;
                         args.hits[slot] = h;
                     }
                 }
@@ -435,7 +434,7 @@ static int search_device(ta_ctx *ctx, cudaStream_t st, const uint8_t *d_needle, 
     unsigned long long *d_count = (unsigned long long *)(ctx->d_flags + 4);
     TA_CUDA(ctx, cudaMemsetAsync(counter, 0, 4 * sizeof(uint32_t), st));  // item counter, pad, 64-bit hit counter
     if (!no_filter && unit && needle_len <= 64 && !anchored && k < needle_len) {
-        const uint64_t nseg = max_hay ? (max_hay + TA_SEARCH_SEG - 1) / TA_SEARCH_SEG : 1;
+        const uint64_t nseg = max_hay ? (max_hay + TA_SEARCH_SUB - 1) / TA_SEARCH_SUB : 1;
         if ((uint64_t)n * nseg <= 0xFFFFFFF0ull && nseg <= 65535) {
             if ((rc = ta_dev_reserve(ctx, ctx->d_work[0], n * nseg * sizeof(uint32_t))) != TA_OK) return rc;
             rc = ta_launch_search_filter(ctx, d_needle, (uint32_t)needle_len, d_hay, d_off, n, max_hay, k,
@@ -525,13 +524,51 @@ static int search_device(ta_ctx *ctx, cudaStream_t st, const uint8_t *d_needle, 
     return TA_ERR_TOO_LARGE;
 }
 
+// orders the hits by (haystack, end): LSD radix sort on the 64-bit key, 11 bits per pass, only over the bits in use
+// (a comparison sort of a few thousand 16-byte records costs more than the exact kernel that produced them)
+static void sort_hits(std::vector<Hit> &hits) {
+    const size_t n = hits.size();
+    if (n < 2) return;
+    if (n < 64) {
+        std::sort(hits.begin(), hits.end(), [](const Hit &x, const Hit &y) {
+            return x.hay != y.hay ? x.hay < y.hay : x.end < y.end;
+        });
+        return;
+    }
+    uint32_t max_hay = 0, max_end = 0;
+    for (const Hit &h : hits) {
+        max_hay = std::max(max_hay, h.hay);
+        max_end = std::max(max_end, h.end);
+    }
+    int end_bits = 1, hay_bits = 1;
+    while (end_bits < 32 && (max_end >> end_bits)) end_bits++;
+    while (hay_bits < 32 && (max_hay >> hay_bits)) hay_bits++;
+    const int key_bits = end_bits + hay_bits;
+    auto key = [&](const Hit &h) { return ((uint64_t)h.hay << end_bits) | h.end; };
+    std::vector<Hit> tmp(n);
+    Hit *src = hits.data(), *dst = tmp.data();
+    constexpr int RB = 11;
+    size_t count[1 << RB];
+    for (int shift = 0; shift < key_bits; shift += RB) {
+        memset(count, 0, sizeof count);
+        for (size_t i = 0; i < n; i++) count[(key(src[i]) >> shift) & ((1u << RB) - 1)]++;
+        size_t sum = 0;
+        for (int b = 0; b < (1 << RB); b++) {
+            const size_t c = count[b];
+            count[b] = sum;
+            sum += c;
+        }
+        for (size_t i = 0; i < n; i++) dst[count[(key(src[i]) >> shift) & ((1u << RB) - 1)]++] = src[i];
+        std::swap(src, dst);
+    }
+    if (src != hits.data()) memcpy(hits.data(), src, n * sizeof(Hit));
+}
+
 // Host phase: order the hits by (haystack, end) and apply the reference's emission rules -- the row-0 match
 // (src/levenshtein.rs:1686-1707), the running Best threshold (:1792-1806) and the Best post-pass (:1812-1835).
 static void emit_matches(size_t n, size_t needle_len, uint32_t k, bool best, ta_costs costs, std::vector<Hit> &hits,
                          uint64_t *moff, std::vector<ta_match> &result) {
-    std::sort(hits.begin(), hits.end(), [](const Hit &x, const Hit &y) {
-        return x.hay != y.hay ? x.hay < y.hay : x.end < y.end;
-    });
+    sort_hits(hits);
     const uint32_t row0 = (uint32_t)needle_len * costs.gap + costs.start_gap;
     size_t hp = 0;
     std::vector<ta_match> cur;

@@ -9,7 +9,8 @@
 
 #include "../../include/triple_accel_b200.h"
 
-#define TA_SEARCH_SEG 512  // haystack bytes per pre-filter segment (lev_bitpar.cu, search.cu)
+#define TA_SEARCH_SEG 512  // haystack bytes scanned per pre-filter thread (lev_bitpar.cu)
+#define TA_SEARCH_SUB 128  // granularity at which the pre-filter flags match ends = work item of the exact kernel
 #define TA_INF 0x3FFFFFFFu  // "out of band" cell value; real costs stay below 2^30 (TA_MAX_STRING_LEN)
 
 struct DevBuf {
