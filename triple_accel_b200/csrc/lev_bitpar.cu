@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(128) search_filter_kernel(const uint8_t *__res
 constexpr uint32_t PIGEON_MIN_PIECE = 4;
 
 template <bool TRANS>
-__global__ void __launch_bounds__(128) search_pigeon_kernel(const uint8_t *__restrict__ needle, uint32_t N,
+__global__ void __launch_bounds__(256) search_pigeon_kernel(const uint8_t *__restrict__ needle, uint32_t N,
                                                             const uint8_t *__restrict__ hay,
                                                             const uint64_t *__restrict__ hay_off, size_t n, uint32_t k,
                                                             uint32_t pieces, uint32_t subs,
@@ -435,7 +435,11 @@ __global__ void __launch_bounds__(128) search_pigeon_kernel(const uint8_t *__res
         s += l;
     }
     const uint64_t back = (uint64_t)N + k + base_len + 1;
-    const uint64_t start = seg_begin > back ? seg_begin - back : 0;
+    uint64_t start = seg_begin > back ? seg_begin - back : 0;
+    {  // start on a 16-byte boundary of the haystack's memory when possible: the stream then needs no re-alignment
+        const uint64_t mis = (uint64_t)((uintptr_t)(p + start) & 15u);
+        if (start >= mis) start -= mis;
+    }
     uint32_t flagged = 0;  // sub-segments of this segment already appended (bit = sub index inside the segment)
 
     // a piece whose last byte is haystack byte q (its last needle index = fin): confirm the match ends it allows
@@ -495,7 +499,10 @@ __global__ void __launch_bounds__(128) search_pigeon_kernel(const uint8_t *__res
             for (int u = 0; u < 16; u++) {
                 const uint64_t q = x0 + (uint64_t)u;
                 if (q >= H) break;  // bytes past the haystack are don't-care padding of the last vector
-                const uint32_t ch = (wds[u >> 2] >> (8 * (u & 3))) & 0xffu;
+                const uint32_t ch = wds[0] & 0xffu;  // (the words are shifted along: no dynamic register indexing)
+#pragma unroll
+                for (int w = 0; w < 3; w++) wds[w] = bitpar::funnel_r(wds[w], wds[w + 1], 8);
+                wds[3] >>= 8;
                 Dr = ((Dr << 1) | starts) & peq[ch * 32u];
                 uint32_t f = Dr & finals;
                 while (f) {
@@ -531,13 +538,17 @@ int ta_launch_search_filter(ta_ctx *ctx, const uint8_t *needle_dev, uint32_t nee
     if (force && force[0] == 'm') pigeon = false;
     if (force && force[0] == 'p' && needle_len <= 32 && pieces <= needle_len) pigeon = true;
     if (pigeon) {
+        // 256-thread blocks: the 32 KB bank-replicated table is shared by 8 warps (TA_PIGEON_THREADS overrides)
+        static const int env_pt = getenv("TA_PIGEON_THREADS") ? atoi(getenv("TA_PIGEON_THREADS")) : 0;
+        const int pt = env_pt ? env_pt : 256;
+        const dim3 pgrid((unsigned)((n + pt - 1) / pt), (unsigned)segs);
         const size_t smem = 256 * 32 * sizeof(uint32_t);
         if (transpose) {
             TA_CUDA(ctx, cudaFuncSetAttribute(search_pigeon_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            search_pigeon_kernel<true><<<grid, 128, smem, st>>>(needle_dev, needle_len, hay, hay_off, n, k, pieces, (uint32_t)subs, idx_out, counter);
+            search_pigeon_kernel<true><<<pgrid, pt, smem, st>>>(needle_dev, needle_len, hay, hay_off, n, k, pieces, (uint32_t)subs, idx_out, counter);
         } else {
             TA_CUDA(ctx, cudaFuncSetAttribute(search_pigeon_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            search_pigeon_kernel<false><<<grid, 128, smem, st>>>(needle_dev, needle_len, hay, hay_off, n, k, pieces, (uint32_t)subs, idx_out, counter);
+            search_pigeon_kernel<false><<<pgrid, pt, smem, st>>>(needle_dev, needle_len, hay, hay_off, n, k, pieces, (uint32_t)subs, idx_out, counter);
         }
     } else if (needle_len <= 32) {
         if (transpose)
