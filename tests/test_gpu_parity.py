@@ -607,7 +607,7 @@ SEARCH_TESTS = ("test_search_random or test_search_planted or test_kat_search or
     ({"TA_BITPAR": "simd"}, LEV_TESTS),
     ({"TA_BITPAR": "tab"}, LEV_TESTS),
     ({"TA_BITPAR": "tab", "TA_BITPAR_BITS": "32"}, LEV_TESTS),
-    ({"TA_BLK_DUO": "0"}, LEV_TESTS),
+    ({"TA_BLK_DUO": "0", "TA_EXP_FIRST_K": "30"}, LEV_TESTS),
     ({"TA_BLK_PLANES": "0"}, LEV_TESTS),
     ({"TA_BLK_PLANES": "1", "TA_BLK_C": "8"}, LEV_TESTS),
     ({"TA_BLK_PLANES": "0", "TA_BLK_C": "8", "TA_BITPAR_THREADS": "64"}, LEV_TESTS),

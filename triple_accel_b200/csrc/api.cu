@@ -280,12 +280,19 @@ __global__ void collect_none_kernel(const uint32_t *__restrict__ out, const uint
 
 int check_costs(ta_costs c) { return ta_costs_valid(c) ? TA_OK : TA_ERR_BAD_COSTS; }
 
-// exponential search on device-resident data: k = 30, 60, ... over the pairs that are still TA_NONE
+// exponential search on device-resident data: k = (16,) 30, 60, ... over the pairs that are still TA_NONE
 // (reference src/levenshtein.rs:1445-1454, 1480-1494, 1516-1526)
 int exp_rounds_dev(ta_ctx *ctx, const uint8_t *da, const uint64_t *da_off, const uint8_t *db, const uint64_t *db_off,
                    size_t n, ta_costs costs, uint32_t max_len, uint32_t *d_out, cudaStream_t st) {
     int rc;
-    uint32_t k = 30;
+    // The result is the exact distance whatever thresholds are tried, so the schedule is free.  With unit costs a
+    // first round at the widest band the block-table kernel takes (k = 16, 15 with transpositions: 30 instructions per
+    // column instead of 42 for the 32-row sliding table that k = 30 needs) answers every pair within that distance
+    // 1.4x faster; the rest continue with the reference's 30, 60, 120, ... (TA_EXP_FIRST_K overrides, 30 = reference).
+    static const int env_first = getenv("TA_EXP_FIRST_K") ? atoi(getenv("TA_EXP_FIRST_K")) : 0;
+    const bool unit = costs.mismatch == 1 && costs.gap == 1 && costs.start_gap == 0 && costs.transpose <= 1;
+    uint32_t k = env_first > 0 ? (uint32_t)env_first : (unit ? (costs.transpose ? 15u : 16u) : 30u);
+    if (k > 30) k = 30;
     if ((rc = ta_launch_lev(ctx, da, da_off, db, db_off, n, nullptr, k, costs, max_len, d_out, st)) != TA_OK) return rc;
     if ((rc = ta_dev_reserve(ctx, ctx->d_work[0], n * sizeof(uint32_t))) != TA_OK) return rc;
     if ((rc = ta_dev_reserve(ctx, ctx->d_work[1], n * sizeof(uint32_t))) != TA_OK) return rc;
@@ -305,7 +312,7 @@ int exp_rounds_dev(ta_ctx *ctx, const uint8_t *da, const uint64_t *da_off, const
         const uint32_t remaining = ctx->h_flags[1];
         if (remaining == 0) break;
         if (k > 0x7FFFFFFFu) return TA_ERR_TOO_LARGE;  // cannot happen: k exceeds every cost bound long before
-        k *= 2;
+        k = k < 30 ? 30 : k * 2;
         cur = idx[flip];
         cur_n = remaining;
         flip ^= 1;
