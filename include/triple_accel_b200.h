@@ -89,7 +89,9 @@ uint64_t ta_launch_count(ta_ctx *ctx);
 /* Pinned host memory for fast H2D/D2H of batch buffers (optional: any host pointer is accepted). */
 void *ta_host_alloc(size_t bytes);
 void ta_host_free(void *p);
-/* Free arrays returned by ta_levenshtein_search_batch. */
+/* Releases an output array this library returned (match lists, per-unit offsets, edit lists).  Pass only such
+ * pointers (NULL is ignored): the blocks carry a small header and large ones are parked for reuse by the next call
+ * instead of going back to the system allocator. */
 void ta_free(void *p);
 
 /* EditCosts::new validity (src/levenshtein.rs:38-60) / check_search (src/levenshtein.rs:67-71): 1 = valid */
