@@ -617,11 +617,13 @@ SEARCH_TESTS = ("test_search_random or test_search_planted or test_kat_search or
     ({"TA_SEARCH_KERNEL": "thread"}, SEARCH_TESTS),
     ({"TA_SEARCH_FILTER": "myers"}, SEARCH_TESTS),
     ({"TA_SEARCH_FILTER": "pigeon"}, SEARCH_TESTS),
+    ({"TA_SEARCH_FILTER": "pigeon", "TA_PIGEON_STAGED": "0"}, SEARCH_TESTS),
 ], ids=["general-band-kernel", "bitpar-simd-kernel", "bitpar-sliding-table-kernel",
         "bitpar-sliding-table-32bit-on-narrow-bands", "bitpar-block-table-one-pair-per-thread", "bitpar-block-table-256-entries",
         "bitpar-block-table-8-blocks", "bitpar-block-table-256-entries-8-blocks",
         "bitpar-table-2plane-kernel", "search-thread-kernel-nofilter", "search-wave-kernel-nofilter",
-        "search-thread-kernel-filter", "search-myers-filter-forced", "search-pigeonhole-filter-forced"])
+        "search-thread-kernel-filter", "search-myers-filter-forced", "search-pigeonhole-filter-forced",
+        "search-pigeonhole-filter-lane-per-segment-loads"])
 def test_every_kernel_variant_forced(env, select):
     """The dispatchers pick a kernel from the cost model, band width and batch size (bit-parallel vs general banded
     kernel; pre-filter + warp-wavefront vs thread-per-haystack exact search).  These switches force the variants

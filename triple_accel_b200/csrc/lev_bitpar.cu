@@ -515,6 +515,177 @@ __global__ void __launch_bounds__(256) search_pigeon_kernel(const uint8_t *__res
     }
 }
 
+
+// search_pigeon_staged_kernel: the same filter with the haystack STAGED THROUGH SHARED MEMORY.  In the kernel above
+// every lane streams its own segment, so one warp-wide 16-byte load touches 32 different 128-byte lines and the LSU
+// data pipe, not arithmetic, bounds the kernel.  Here a warp owns 32 consecutive (haystack, segment) items and moves
+// them in steps of 64 bytes per item: the 32 x 64-byte rows of a step are fetched by coalesced 16-byte cp.async
+// (LDGSTS, four lanes per row, no register staging) into a padded per-warp tile, double-buffered so that the copy
+// of step t + 1 overlaps the arithmetic of step t, and every lane then reads its own row back with four
+// conflict-free LDS.128.  Rows start on the 16-byte boundary at or below the item's first byte; vectors past the
+// haystack's last one are clamped like bitpar::Stream does (don't-care bytes, never flagged: see verify()).
+constexpr int PIGEON_ROW = 80;  // 64 data bytes + 16 of padding: rows of a quarter-warp fall into distinct banks
+
+template <bool TRANS>
+__global__ void __launch_bounds__(256) search_pigeon_staged_kernel(const uint8_t *__restrict__ needle, uint32_t N,
+                                                                   const uint8_t *__restrict__ hay,
+                                                                   const uint64_t *__restrict__ hay_off, size_t n,
+                                                                   uint32_t k, uint32_t pieces, uint32_t subs,
+                                                                   uint32_t segs, uint32_t *__restrict__ idx_out,
+                                                                   uint32_t *__restrict__ counter) {
+    extern __shared__ __align__(16) uint8_t pg_smem[];
+    uint32_t *peqr = (uint32_t *)pg_smem;  // [256][32]
+    for (uint32_t q = threadIdx.x; q < 256u * 32u; q += blockDim.x) peqr[q] = 0;
+    __syncthreads();
+    for (uint32_t q = threadIdx.x; q < N * 32u; q += blockDim.x)
+        atomicOr(&peqr[(uint32_t)needle[q >> 5] * 32u + (q & 31u)], 1u << (q >> 5));
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t *peq = peqr + lane;
+    uint8_t *tile = pg_smem + 256 * 32 * 4 + (size_t)warp * (2 * 32 * PIGEON_ROW);
+
+    const size_t item = ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * 32 + lane;
+    bool active = item < n * (size_t)segs;
+    const size_t h = active ? item / segs : 0;
+    const uint32_t sidx = active ? (uint32_t)(item % segs) : 0;
+    const uint64_t h0 = hay_off[h], h1 = hay_off[h + 1];
+    const uint64_t H = h1 - h0;
+    const uint64_t seg_begin = (uint64_t)sidx * FILTER_SEG;
+    if (seg_begin >= H) active = false;
+    const uint64_t seg_end = seg_begin + FILTER_SEG < H ? seg_begin + FILTER_SEG : H;
+    const uint8_t *p = hay + h0;
+
+    const uint32_t base_len = N / pieces, extra = N % pieces;
+    uint32_t starts = 0, finals = 0;
+    for (uint32_t i = 0, s = 0; i < pieces; i++) {
+        const uint32_t l = base_len + (i < extra ? 1u : 0u);
+        starts |= 1u << s;
+        finals |= 1u << (s + l - 1);
+        s += l;
+    }
+    const uint64_t back = (uint64_t)N + k + base_len + 1;
+    const uint64_t start = seg_begin > back ? seg_begin - back : 0;
+    // row geometry: a0 = 16-byte boundary at or below the first scanned byte, x0 = its byte index in the haystack
+    const uintptr_t a0 = active ? ((uintptr_t)(p + start) & ~(uintptr_t)15) : 0;
+    const int64_t x0 = (int64_t)a0 - (int64_t)(uintptr_t)p;
+    const int vlast = active ? (int)((((uintptr_t)(p + H - 1) & ~(uintptr_t)15) - a0) >> 4) : -1;
+    const int own_steps = active ? (int)(((int64_t)seg_end - x0 + 63) >> 6) : 0;
+    int nsteps = own_steps;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nsteps = max(nsteps, __shfl_xor_sync(0xffffffffu, nsteps, o));
+
+    // loader duty: this lane fetches vector slot (lane & 3) of rows (lane >> 2) + 8 r, r = 0..3, of every step
+    const uint32_t slot = lane & 3u;
+    unsigned long long lbase[4];
+    int lvlast[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int jr = (int)(lane >> 2) + 8 * r;
+        lbase[r] = __shfl_sync(0xffffffffu, (unsigned long long)a0, jr);
+        lvlast[r] = __shfl_sync(0xffffffffu, vlast, jr);
+    }
+    const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
+    auto issue = [&](const int t, const int buf) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            if (lvlast[r] >= 0) {
+                const int jr = (int)(lane >> 2) + 8 * r;
+                int v = 4 * t + (int)slot;
+                v = v < lvlast[r] ? v : lvlast[r];
+                const unsigned long long src = lbase[r] + 16ull * (unsigned long long)v;
+                const uint32_t dst = tile_s + (uint32_t)(buf * 32 * PIGEON_ROW + jr * PIGEON_ROW) + 16u * slot;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    uint32_t flagged = 0;
+    auto verify = [&](const uint64_t q, const uint32_t fin) {
+        const uint32_t r = N - 1 - fin;
+        uint64_t lo = q + r > k ? q + r - k : 0, hi = q + r + k;
+        if (lo < seg_begin) lo = seg_begin;
+        if (hi > seg_end - 1) hi = seg_end - 1;
+        if (lo > hi) return;
+        const uint64_t st = q + 1 > (uint64_t)fin + 1 + k ? q + 1 - (fin + 1 + k) : 0;
+        uint32_t VP = 0xffffffffu, VN = 0, D0prev = 0xffffffffu, Eqprev = 0, score = N;
+        const uint32_t top = 1u << (N - 1);
+        for (uint64_t t = st; t <= hi; t++) {
+            const uint32_t Eq = peq[(uint32_t)p[t] * 32u];
+            uint32_t D0 = (((Eq & VP) + VP) ^ VP) | Eq | VN;
+            if (TRANS) {
+                D0 |= ((~D0prev & Eq) << 1) & Eqprev;
+                D0prev = D0;
+                Eqprev = Eq;
+            }
+            uint32_t HP = VN | ~(D0 | VP);
+            uint32_t HN = D0 & VP;
+            score += (HP & top) ? 1u : 0u;
+            score -= (HN & top) ? 1u : 0u;
+            HP <<= 1;
+            HN <<= 1;
+            VP = HN | ~(D0 | HP);
+            VN = D0 & HP;
+            if (t >= lo && score <= k) {
+                const uint32_t sub_in = (uint32_t)((t - seg_begin) / TA_SEARCH_SUB);
+                if (!(flagged >> sub_in & 1u)) {
+                    flagged |= 1u << sub_in;
+                    idx_out[atomicAdd(counter, 1u)] = (uint32_t)(h * subs + t / TA_SEARCH_SUB);
+                }
+            }
+        }
+    };
+
+    uint32_t D = 0;
+    if (nsteps > 0) issue(0, 0);
+    for (int t = 0; t < nsteps; t++) {
+        if (t + 1 < nsteps) {
+            issue(t + 1, (t + 1) & 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncwarp();
+        if (t < own_steps) {
+            const uint4 *row = (const uint4 *)(tile + (t & 1) * 32 * PIGEON_ROW + lane * PIGEON_ROW);
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int64_t xc = x0 + 64 * (int64_t)t + 16 * c;  // haystack index of the chunk's first byte
+                if (xc >= (int64_t)seg_end) break;
+                const uint4 v4 = row[c];
+                uint32_t wds[4] = {v4.x, v4.y, v4.z, v4.w};
+                const uint32_t Dstart = D;
+                uint32_t seen = 0;
+#pragma unroll
+                for (int u = 0; u < 16; u++) {
+                    const uint32_t ch = bitpar::byte_of(wds[u >> 2], u & 3);
+                    D = ((D << 1) | starts) & peq[ch * 32u];
+                    seen |= D;
+                }
+                if (seen & finals) {  // some piece ends inside this chunk: replay it byte by byte
+                    uint32_t Dr = Dstart;
+                    for (int u = 0; u < 16; u++) {
+                        const int64_t q = xc + u;
+                        if (q >= (int64_t)H) break;  // don't-care padding of the last vector
+                        const uint32_t ch = wds[0] & 0xffu;
+#pragma unroll
+                        for (int w = 0; w < 3; w++) wds[w] = bitpar::funnel_r(wds[w], wds[w + 1], 8);
+                        wds[3] >>= 8;
+                        Dr = ((Dr << 1) | starts) & peq[ch * 32u];
+                        uint32_t f = q >= 0 ? (Dr & finals) : 0u;  // bytes below the haystack's first are padding too
+                        while (f) {
+                            const uint32_t fin = (uint32_t)__ffs((int)f) - 1u;
+                            f &= f - 1u;
+                            verify((uint64_t)q, fin);
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();  // everyone is done with buffer t & 1 before step t + 2 overwrites it
+    }
+}
+
 }  // namespace
 
 // appends the codes (haystack * subs + sub-segment, unordered) of the TA_SEARCH_SUB-byte haystack sub-segments that
@@ -541,6 +712,23 @@ int ta_launch_search_filter(ta_ctx *ctx, const uint8_t *needle_dev, uint32_t nee
         // 256-thread blocks: the 32 KB bank-replicated table is shared by 8 warps (TA_PIGEON_THREADS overrides)
         static const int env_pt = getenv("TA_PIGEON_THREADS") ? atoi(getenv("TA_PIGEON_THREADS")) : 0;
         const int pt = env_pt ? env_pt : 256;
+        static const int staged = getenv("TA_PIGEON_STAGED") ? atoi(getenv("TA_PIGEON_STAGED")) : 1;
+        if (staged) {  // coalesced cp.async rows through shared memory (default); TA_PIGEON_STAGED=0 = lane-per-segment loads
+            const size_t items = n * (size_t)segs;
+            const size_t warps = (items + 31) / 32;
+            const unsigned blocks = (unsigned)((warps + (pt / 32) - 1) / (pt / 32));
+            const size_t smem = 256 * 32 * sizeof(uint32_t) + (size_t)(pt / 32) * 2 * 32 * PIGEON_ROW;
+            if (transpose) {
+                TA_CUDA(ctx, cudaFuncSetAttribute(search_pigeon_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                search_pigeon_staged_kernel<true><<<blocks, pt, smem, st>>>(needle_dev, needle_len, hay, hay_off, n, k, pieces, (uint32_t)subs, (uint32_t)segs, idx_out, counter);
+            } else {
+                TA_CUDA(ctx, cudaFuncSetAttribute(search_pigeon_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                search_pigeon_staged_kernel<false><<<blocks, pt, smem, st>>>(needle_dev, needle_len, hay, hay_off, n, k, pieces, (uint32_t)subs, (uint32_t)segs, idx_out, counter);
+            }
+            ctx->launches++;
+            TA_CUDA(ctx, cudaGetLastError());
+            return TA_OK;
+        }
         const dim3 pgrid((unsigned)((n + pt - 1) / pt), (unsigned)segs);
         const size_t smem = 256 * 32 * sizeof(uint32_t);
         if (transpose) {
