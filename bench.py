@@ -33,6 +33,11 @@ WORKLOADS = {
                       "levenshtein_simd_k k=8, 1M pairs len=128, unit costs, set M (b = a after U[0,8] edits)"),
     "lev_k16_len128": ("lev_k", 1_000_000, 128, 16, (1, 1, 0, 0),
                        "levenshtein_simd_k k=16, 1M pairs len=128, unit costs, set M (b = a after U[0,16] edits)"),
+    "lev_k8_len128_R": ("lev_k_R", 1_000_000, 128, 8, (1, 1, 0, 0),
+                        "levenshtein_simd_k k=8, 1M pairs len=128, unit costs, set R (b independent of a: every pair is "
+                        "None; the kernel leaves a pair once its final-diagonal value exceeds k)"),
+    "lev_k16_len128_R": ("lev_k_R", 1_000_000, 128, 16, (1, 1, 0, 0),
+                         "levenshtein_simd_k k=16, 1M pairs len=128, unit costs, set R (b independent of a)"),
     "rdamerau_k16_len512": ("lev_k", 1_000_000, 512, 16, (1, 1, 0, 1),
                             "RDAMERAU_COSTS k=16, 1M pairs len=512, set M (U[0,16] edits incl. swaps)"),
     "lev_k16_len4096": ("lev_k", 262_144, 4096, 16, (1, 1, 0, 0),
@@ -56,8 +61,13 @@ def nominal_cells(length, k):
     return (2 * u + 1) * length - u * u
 
 
+RANDOM_SET = [False]  # set by main(): the workload's pairs are unrelated (set R)
+
+
 def make_inputs(op, n, length, k, costs, seed):
     from triple_accel_b200 import synth
+    if op == "lev_k" and RANDOM_SET[0]:
+        return synth.random_pairs(n, length, seed=seed)
     if op == "hamming":
         return synth.hamming_pairs(n, length, seed=seed)
     if op == "exp":
@@ -172,6 +182,8 @@ def run_reference(args, wl):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import _oracle as orc
     op, n, length, k, costs, desc = wl
+    if op == "lev_k_R":
+        op, RANDOM_SET[0] = "lev_k", True
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -226,11 +238,12 @@ def main():
     wl = list(WORKLOADS[args.workload])
     if args.pairs:
         wl[1] = args.pairs
-    op, n, length, k, costs, desc = wl
-
     if args.impl == "reference":
         run_reference(args, wl)
         return
+    op, n, length, k, costs, desc = wl
+    if op == "lev_k_R":
+        op, RANDOM_SET[0] = "lev_k", True
 
     import torch
     import triple_accel_b200 as ta
@@ -323,6 +336,12 @@ def main():
     value = total_pairs * cells_pair / (ms_step * 1e-3) / 1e9
     # algorithmic bytes: |a| + |b| + 4 per pair (CSR offsets, +16 B/pair, not counted); search: |haystack|
     alg_bytes = int(b.nbytes) if op == "search" else int(a.nbytes + b.nbytes + 4 * n)
+    if RANDOM_SET[0]:
+        # set R: a pair is decided at the first 16-column boundary past k + 1 columns; count only the bytes needed to
+        # get there ("if the kernel early-exits, only count bytes of strings it actually streamed" --
+        # the kernel's prefetches read somewhat more, so this is the conservative figure)
+        need = min(length, 16 * ((k + 1 + 15) // 16))
+        alg_bytes = int(n * (2 * need + 4))
 
     # ---- end to end through the host-buffer C ABI (pinned host inputs; H2D + kernel + D2H timed) --------------
     e2e = None

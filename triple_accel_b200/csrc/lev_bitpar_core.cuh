@@ -588,13 +588,25 @@ TA_HD uint32_t distance_blk(const uint8_t *a, int m, const uint8_t *b, int n, ui
         slide_window();
     };
 
+    // Early exit: the value on the final diagonal, diff + j - matches(j), never decreases from column to column (its
+    // delta is the D0 bit: 0 or +1) and ends as the result, so once it exceeds max_k the answer is "> max_k" whatever
+    // follows.  Checked once per 16 columns; unrelated pairs leave after the first superstep or two.
+    bool dead = false;
     int j0 = 0;
     for (; j0 + 32 <= n; j0 += 32) {
         superstep(IntC<0>());
+        if ((uint32_t)diff + (uint32_t)(j0 + 16) - matches > max_k) {
+            dead = true;
+            break;
+        }
         superstep(IntC<16>());
+        if ((uint32_t)diff + (uint32_t)(j0 + 32) - matches > max_k) {
+            dead = true;
+            break;
+        }
     }
     uint32_t phase = 0;
-    if (j0 + 16 <= n) {
+    if (!dead && j0 + 16 <= n) {
         superstep(IntC<0>());
         j0 += 16;
         phase = 16;
@@ -602,7 +614,7 @@ TA_HD uint32_t distance_blk(const uint8_t *a, int m, const uint8_t *b, int n, ui
     // the table now holds stream bytes [j0 - C, j0 + L) = window bytes from offset 16 - C
     constexpr int SW0 = (16 - C) / 4;
     uint32_t sw[NW - SW0];
-    if (j0 < n) {  // last n % 16 columns: slide the table column by column (exact clear + set), rolled
+    if (!dead && j0 < n) {  // last n % 16 columns: slide the table column by column (exact clear + set), rolled
         take_pattern();
         sb.take(bw);
 #pragma unroll
@@ -639,7 +651,7 @@ TA_HD uint32_t distance_blk(const uint8_t *a, int m, const uint8_t *b, int n, ui
     // leave the table clean: it holds exactly the 32 stream bytes sw[0..7]
 #pragma unroll
     for (int t = 0; t < 32; t++) *(W *)blk_entry(tab, sw[t >> 2], t & 3, pitch) = 0;
-    return (uint32_t)diff + (uint32_t)n - matches;
+    return dead ? 0xFFFFFFFFu : (uint32_t)diff + (uint32_t)n - matches;
 }
 
 template <bool TRANS, int PLANES, int C>
@@ -747,6 +759,8 @@ TA_HD void distance_duo(const uint8_t *aA, int mA, const uint8_t *bA, int nA, ui
     };
 
     const int steps = nA >> 4;  // == nB >> 4
+    bool dead[2] = {false, false};
+    int s_done = steps;
     for (int s = 0; s < steps; s++) {
         take_side(sd[0]);
         take_side(sd[1]);
@@ -803,10 +817,19 @@ TA_HD void distance_duo(const uint8_t *aA, int mA, const uint8_t *bA, int nA, ui
         for (int P = 0; P < 2; P++)
 #pragma unroll
             for (int w = 0; w < 8; w++) sd[P].win[w] = sd[P].win[w + 4];
+        // early exit (see distance_blk): a pair whose final-diagonal value passed max_k is decided; leave when both are
+        const uint32_t cols = (uint32_t)(s + 1) << 4;
+        dead[0] = dead[0] || (uint32_t)sd[0].diff + cols - matches[0] > maxkA;
+        dead[1] = dead[1] || (uint32_t)sd[1].diff + cols - matches[1] > maxkB;
+        if (dead[0] && dead[1]) {
+            s_done = s + 1;
+            break;
+        }
     }
     // tables now hold stream bytes [j0 - 8, j0 + 8) of each pair = window bytes from offset 8
-    const int j0 = steps << 4;
-    const int rA = nA - j0, rB = nB - j0, r = rA > rB ? rA : rB;
+    const int j0 = s_done << 4;
+    const bool both_dead = dead[0] && dead[1];
+    const int rA = nA - j0, rB = nB - j0, r = both_dead ? 0 : (rA > rB ? rA : rB);
     uint32_t sw[2][10];
     if (r > 0) {  // last columns: exact per-column sliding, rolled; each pair counts only its own columns
         take_side(sd[0]);
@@ -857,8 +880,8 @@ TA_HD void distance_duo(const uint8_t *aA, int mA, const uint8_t *bA, int nA, ui
     for (int P = 0; P < 2; P++)
 #pragma unroll
         for (int t = 0; t < 16; t++) *half_ptr(P, sw[P][t >> 2], t & 3) = 0;
-    dA = (uint32_t)sd[0].diff + (uint32_t)nA - matches[0];
-    dB = (uint32_t)sd[1].diff + (uint32_t)nB - matches[1];
+    dA = dead[0] ? 0xFFFFFFFFu : (uint32_t)sd[0].diff + (uint32_t)nA - matches[0];
+    dB = dead[1] ? 0xFFFFFFFFu : (uint32_t)sd[1].diff + (uint32_t)nB - matches[1];
 }
 
 // One pair's contract up to the point where the DP is needed (reference src/levenshtein.rs:386-430 with unit
