@@ -354,6 +354,7 @@ TA_HD uint32_t distance_tab(const uint8_t *a, int m, const uint8_t *b, int n, ui
     };
 
     uint32_t aw[4] = {0, 0, 0, 0}, bw[4], bc[4];
+    bool dead = false;
     int j0 = 0;
     for (; j0 + 16 <= n; j0 += 16) {  // full 16-column chunks: every selector and shift below is a constant
         sa.take(aw);                  // the bytes that enter during this chunk
@@ -393,8 +394,13 @@ TA_HD uint32_t distance_tab(const uint8_t *a, int m, const uint8_t *b, int n, ui
         for (int w = 0; w < 4; w++) ring[RING - 4 + w] = aw[w];
         phase = (phase + 16u) & (uint32_t)(BITS - 1);
         bit0 = (W)((W)1 << phase);
+        // early exit: the final-diagonal value diff + j - matches(j) never decreases and ends as the result
+        if ((uint32_t)diff + (uint32_t)(j0 + 16) - matches > max_k) {
+            dead = true;
+            break;
+        }
     }
-    if (j0 < n) {  // last n % 16 columns: the same column step, rolled, bytes shifted out of the chunk's words
+    if (!dead && j0 < n) {  // last n % 16 columns: the same column step, rolled, bytes shifted out of the chunk's words
         sa.take(aw);
         sb.take(bw);
         tops7 = (W)((W)gather_bits16(aw, 7) * bit0);
@@ -424,7 +430,7 @@ TA_HD uint32_t distance_tab(const uint8_t *a, int m, const uint8_t *b, int n, ui
     for (int t = 0; t < BITS; t++) tab_at<W>(tab, byte_of(ring[t >> 2], t & 3), pitch) = 0;
 #pragma unroll
     for (int t = 0; t < 16; t++) tab_at<W>(tab, byte_of(aw[t >> 2], t & 3), pitch) = 0;
-    return (uint32_t)diff + (uint32_t)n - matches;
+    return dead ? 0xFFFFFFFFu : (uint32_t)diff + (uint32_t)n - matches;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -590,15 +596,12 @@ TA_HD uint32_t distance_blk(const uint8_t *a, int m, const uint8_t *b, int n, ui
 
     // Early exit: the value on the final diagonal, diff + j - matches(j), never decreases from column to column (its
     // delta is the D0 bit: 0 or +1) and ends as the result, so once it exceeds max_k the answer is "> max_k" whatever
-    // follows.  Checked once per 16 columns; unrelated pairs leave after the first superstep or two.
+    // follows.  Checked once per 32 columns, at the loop's own back edge (a test between the two unrolled supersteps
+    // would split the straight-line body and cost the matching pairs 3-9 %); unrelated pairs leave after one pass.
     bool dead = false;
     int j0 = 0;
     for (; j0 + 32 <= n; j0 += 32) {
         superstep(IntC<0>());
-        if ((uint32_t)diff + (uint32_t)(j0 + 16) - matches > max_k) {
-            dead = true;
-            break;
-        }
         superstep(IntC<16>());
         if ((uint32_t)diff + (uint32_t)(j0 + 32) - matches > max_k) {
             dead = true;
