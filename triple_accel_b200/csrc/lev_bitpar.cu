@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(128, 3) lev_bitpar_duo_kernel(const uint8_t *_
         uint32_t mk0 = 0, mk1 = 0, r0 = 0, r1 = 0;
         const bool dp0 = bitpar::unit_costs_prepare(pa0, la0, pb0, lb0, k, mk0, &r0);
         const bool dp1 = has1 && bitpar::unit_costs_prepare(pa1, la1, pb1, lb1, k, mk1, &r1);
-        if (dp0 && dp1 && (lb0 >> 4) == (lb1 >> 4)) {
+        if (dp0 && dp1 && ((lb0 + 15) >> 4) == ((lb1 + 15) >> 4)) {
             bitpar::distance_duo(pa0, (int)la0, pb0, (int)lb0, mk0, pa1, (int)la1, pb1, (int)lb1, mk1, tab, pitch, r0, r1);
             r0 = r0 <= mk0 ? r0 : 0xFFFFFFFFu;
             r1 = r1 <= mk1 ? r1 : 0xFFFFFFFFu;
