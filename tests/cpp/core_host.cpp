@@ -159,7 +159,7 @@ int main(int argc, char **argv) {
             uint32_t mk1, mk2, o1 = 0, o2 = 0;
             const bool dp1 = bitpar::unit_costs_prepare(x1, lx1, y1, ly1, k, mk1, &o1);
             const bool dp2 = bitpar::unit_costs_prepare(x2, lx2, y2, ly2, k, mk2, &o2);
-            if (dp1 && dp2 && ((ly1 + 15) >> 4) == ((ly2 + 15) >> 4)) {
+            if (dp1 && dp2 && (ly1 >> 4) == (ly2 >> 4)) {
                 static uint32_t tab[128];
                 uint32_t d1, d2;
                 bitpar::distance_duo(x1, (int)lx1, y1, (int)ly1, mk1, x2, (int)lx2, y2, (int)ly2, mk2, (uint8_t *)tab, 4u, d1, d2);

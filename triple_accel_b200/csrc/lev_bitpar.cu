@@ -145,18 +145,25 @@ __global__ void __launch_bounds__(128, 3) lev_bitpar_duo_kernel(const uint8_t *_
         uint32_t mk0 = 0, mk1 = 0, r0 = 0, r1 = 0;
         const bool dp0 = bitpar::unit_costs_prepare(pa0, la0, pb0, lb0, k, mk0, &r0);
         const bool dp1 = has1 && bitpar::unit_costs_prepare(pa1, la1, pb1, lb1, k, mk1, &r1);
-        if (dp0 && dp1 && ((lb0 + 15) >> 4) == ((lb1 + 15) >> 4)) {
+        if (dp0 && dp1 && (lb0 >> 4) == (lb1 >> 4)) {
             bitpar::distance_duo(pa0, (int)la0, pb0, (int)lb0, mk0, pa1, (int)la1, pb1, (int)lb1, mk1, tab, pitch, r0, r1);
             r0 = r0 <= mk0 ? r0 : 0xFFFFFFFFu;
             r1 = r1 <= mk1 ? r1 : 0xFFFFFFFFu;
         } else {
-            if (dp0) {
-                r0 = bitpar::distance_blk<false, 1, 16>(pa0, (int)la0, pb0, (int)lb0, mk0, tab, pitch);
-                r0 = r0 <= mk0 ? r0 : 0xFFFFFFFFu;
-            }
-            if (dp1) {
-                r1 = bitpar::distance_blk<false, 1, 16>(pa1, (int)la1, pb1, (int)lb1, mk1, tab, pitch);
-                r1 = r1 <= mk1 ? r1 : 0xFFFFFFFFu;
+            // one pair after the other through ONE inlined copy of the single-pair routine: the kernel's hot code has
+            // to stay within the 32 KB L1.5 instruction cache (two copies made every warp on an SM thrash it)
+#pragma unroll 1
+            for (int q = 0; q < 2; q++) {
+                if (q == 0 ? dp0 : dp1) {
+                    const uint32_t mk = q == 0 ? mk0 : mk1;
+                    uint32_t r = bitpar::distance_blk<false, 1, 16>(q == 0 ? pa0 : pa1, (int)(q == 0 ? la0 : la1),
+                                                                    q == 0 ? pb0 : pb1, (int)(q == 0 ? lb0 : lb1), mk, tab, pitch);
+                    r = r <= mk ? r : 0xFFFFFFFFu;
+                    if (q == 0)
+                        r0 = r;
+                    else
+                        r1 = r;
+                }
             }
         }
         out[cur0.pair] = r0;

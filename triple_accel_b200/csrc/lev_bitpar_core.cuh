@@ -357,6 +357,7 @@ TA_HD uint32_t distance_tab(const uint8_t *a, int m, const uint8_t *b, int n, ui
     bool dead = false;
     int j0 = 0;
     for (; j0 + 16 <= n; j0 += 16) {  // full 16-column chunks: every selector and shift below is a constant
+        const uint32_t m_old = matches;
         sa.take(aw);                  // the bytes that enter during this chunk
         sb.take(bw);
         tops7 = (W)((W)gather_bits16(aw, 7) * bit0);
@@ -394,8 +395,9 @@ TA_HD uint32_t distance_tab(const uint8_t *a, int m, const uint8_t *b, int n, ui
         for (int w = 0; w < 4; w++) ring[RING - 4 + w] = aw[w];
         phase = (phase + 16u) & (uint32_t)(BITS - 1);
         bit0 = (W)((W)1 << phase);
-        // early exit: the final-diagonal value diff + j - matches(j) never decreases and ends as the result
-        if ((uint32_t)diff + (uint32_t)(j0 + 16) - matches > max_k) {
+        // early exit: the final-diagonal value diff + j - matches(j) never decreases and ends as the result (tested
+        // on the count as of the start of this chunk, which is long computed: the branch never waits for the chain)
+        if ((uint32_t)diff + (uint32_t)j0 - m_old > max_k) {
             dead = true;
             break;
         }
@@ -450,8 +452,8 @@ TA_HD uint32_t distance_tab(const uint8_t *a, int m, const uint8_t *b, int n, ui
 // unit costs every change of diagonal costs 1, the path starts on row dhi and ends on row e, so a path through such
 // a cell costs at least (p - dhi) + (p - e) >= 66 - 2C - (W - 1) >= 34 - C > max_k (max_k <= W <= 33 - C); it can
 // neither lower a distance that is <= max_k nor pull one that is > max_k below the threshold.
-// Columns are unrolled 32 deep so that every rotation, bit and sub-word offset is an immediate; ragged lengths are
-// rounded up with virtual all-match columns in front of the matrix (see `pad` below), so there is no rolled tail.
+// Columns are unrolled 32 deep so that every rotation, bit and sub-word offset is an immediate.  The last n mod 16
+// columns slide the table column by column with an exact clear (rolled code).
 //   PLANES = 1: 128 entries (7-bit classes) + the A7 plane;  PLANES = 0: 256 entries, no plane.
 //   `tab` = the thread's entry 0, `pitch` = bytes between entries; the table is all-zero on entry and on exit.
 TA_HD uint8_t *blk_entry(uint8_t *tab, uint32_t w, int t, uint32_t pitch) { return tab + byte_of(w, t) * pitch; }
@@ -473,19 +475,10 @@ TA_HD uint32_t distance_blk(const uint8_t *a, int m, const uint8_t *b, int n, ui
     const int diff = n - m;
     const int e = (int)((max_k - (uint32_t)diff) >> 1) + ((TRANS && ((max_k - (uint32_t)diff) & 1u)) ? 1 : 0);
     const int dhi = diff + e;  // window row p of column j is matrix row i = j - dhi + p
-    // The column count is rounded up to a multiple of 16 with `pad` VIRTUAL columns in front of the matrix whose match
-    // word is forced to all-ones: every cell then equals its diagonal predecessor, so the window's vertical deltas
-    // (the whole state) pass through unchanged, each virtual column is counted as a match on the final diagonal, and
-    // diff + (n + pad) - matches is still the distance.  No ragged tail is left: every column runs in unrolled code.
-    // When pad != 0 the frame is rotated by 16 positions so that the lone first superstep is the PH = 16 body and
-    // the (PH = 0, PH = 16) loop follows it unchanged.
-    const int pad = (16 - (n & 15)) & 15;
-    const int np = n + pad;
-    const uint32_t base = pad ? 16u : 0u;  // stream byte t sits at circular position (t + base) mod 32
 
     Stream sa, sb;
-    sa.init((intptr_t)a - dhi - pad, (uintptr_t)a, (uintptr_t)a + m - 1);
-    sb.init((intptr_t)b - pad, (uintptr_t)b, (uintptr_t)b + n - 1);
+    sa.init((intptr_t)a - dhi, (uintptr_t)a, (uintptr_t)a + m - 1);
+    sb.init((intptr_t)b, (uintptr_t)b, (uintptr_t)b + n - 1);
 
     // win = class bits of pattern-stream bytes [16 s - 16, ...) at superstep s; g7 = top bits of the last takes
     uint32_t win[NW];
@@ -501,13 +494,11 @@ TA_HD uint32_t distance_blk(const uint8_t *a, int m, const uint8_t *b, int n, ui
             g7cur = gather_bits16(x + 4 * (NT - 1), 7);
             if (NT == 2) g7prev = gather_bits16(x, 7);
             A7 = NT == 1 ? g7cur : (g7prev | ((g7cur & 0xffu) << 16));
-            A7 = funnel_r(A7, A7, (32u - base) & 31u);  // rotate left by base
         }
 #pragma unroll
         for (int w = 0; w < 4 * NT; w++) win[4 + w] = x[w] & CMASK;
 #pragma unroll
-        for (int t = 0; t < L; t++)
-            *(W *)blk_entry(tab, win[4 + (t >> 2)], t & 3, pitch) |= 1u << (((uint32_t)t + base) & 31u);
+        for (int t = 0; t < L; t++) *(W *)blk_entry(tab, win[4 + (t >> 2)], t & 3, pitch) |= 1u << t;
     }
 
     W VP = dhi >= 32 ? 0u : (0xffffffffu << dhi);
@@ -553,10 +544,8 @@ TA_HD uint32_t distance_blk(const uint8_t *a, int m, const uint8_t *b, int n, ui
     // j + L in is software-pipelined by hand: its load is issued one column early (right after the previous store,
     // which it must follow because two entering bytes may share an entry), so neither the store nor the look-up that
     // follows it waits for shared-memory latency.
-    const uint32_t padbits = (1u << pad) - 1u;  // bit u set: column u of the first superstep is virtual
-    auto superstep = [&](auto phc, auto firstc) {
+    auto superstep = [&](auto phc) {
         constexpr uint32_t PH = (uint32_t)decltype(phc)::value;
-        constexpr bool FIRST = decltype(firstc)::value != 0;  // the superstep that holds the virtual columns
         take_pattern();
         sb.take(bw);
 #pragma unroll
@@ -600,9 +589,7 @@ TA_HD uint32_t distance_blk(const uint8_t *a, int m, const uint8_t *b, int n, ui
                 pend = enter_addr(u + 1);
                 pend_val = *pend;
             }
-            W Eq = funnel_r(raw, raw, (PH + (uint32_t)u) & 31u);
-            if (FIRST) Eq |= (W)((int32_t)(padbits << (31 - u)) >> 31);  // all-ones in a virtual column
-            step(Eq);
+            step(funnel_r(raw, raw, (PH + (uint32_t)u) & 31u));
         }
         matches += acc >> e;
         acc = 0;
@@ -611,38 +598,69 @@ TA_HD uint32_t distance_blk(const uint8_t *a, int m, const uint8_t *b, int n, ui
 
     // Early exit: the value on the final diagonal, diff + j - matches(j), never decreases from column to column (its
     // delta is the D0 bit: 0 or +1) and ends as the result, so once it exceeds max_k the answer is "> max_k" whatever
-    // follows.  Tested once per 32 columns against the count as of the START of the pass: that value is long computed,
-    // so the branch never waits for the recurrence's dependency chain (testing the fresh count drained the pipeline at
-    // every back edge and cost the matching pairs 3 %).  Unrelated pairs leave after two passes.
+    // follows.  Tested once per 32 columns, at the loop's own back edge, against the count as of the START of the pass:
+    // that value is long computed, so the branch never waits for the recurrence's dependency chain (testing the fresh
+    // count drained the pipeline at every back edge, a test between the two unrolled supersteps split the
+    // straight-line body: 3-9 % on the matching pairs).  Unrelated pairs leave after two passes.
     bool dead = false;
-    int j0 = 0;  // (padded) columns done
-    if (pad) {
-        superstep(IntC<16>(), IntC<1>());
-        j0 = 16;
-    }
-    for (; j0 + 32 <= np; j0 += 32) {
+    int j0 = 0;
+    for (; j0 + 32 <= n; j0 += 32) {
         const uint32_t m_old = matches;
-        superstep(IntC<0>(), IntC<0>());
-        superstep(IntC<16>(), IntC<0>());
+        superstep(IntC<0>());
+        superstep(IntC<16>());
         if ((uint32_t)diff + (uint32_t)j0 - m_old > max_k) {
             dead = true;
             j0 += 32;
             break;
         }
     }
-    if (!dead && j0 + 16 <= np) {
-        superstep(IntC<0>(), IntC<0>());
+    uint32_t phase = 0;
+    if (!dead && j0 + 16 <= n) {
+        superstep(IntC<0>());
         j0 += 16;
+        phase = 16;
     }
     // the table now holds stream bytes [j0 - C, j0 + L) = window bytes from offset 16 - C
     constexpr int SW0 = (16 - C) / 4;
-    uint32_t sw[8];
+    uint32_t sw[NW - SW0];
+    if (!dead && j0 < n) {  // last n % 16 columns: slide the table column by column (exact clear + set), rolled
+        take_pattern();
+        sb.take(bw);
 #pragma unroll
-    for (int w = 0; w < 8; w++) sw[w] = win[SW0 + w];
+        for (int w = 0; w < NW - SW0; w++) sw[w] = win[SW0 + w];
+        W tops = 0;
+        if (PLANES) {
+            if (C == 16)
+                tops = g7cur << ((phase + 16u) & 31u);
+            else
+                tops = ((g7prev >> 8) << ((phase + 24u) & 31u)) | ((g7cur & 0xffu) << phase);
+        }
+        for (int u = 0; u < n - j0; u++) {
+            // byte j - C (sw byte 0) is dead and byte j + L (sw byte 32) takes over its position
+            const W bit = 1u << ((phase + (uint32_t)(u + L)) & 31u);
+            *(W *)blk_entry(tab, sw[0] & 0xffu, 0, pitch) &= ~bit;
+            *(W *)blk_entry(tab, sw[8] & 0xffu, 0, pitch) |= bit;
+            if (PLANES) A7 = (A7 & ~bit) | (tops & bit);
+            const uint32_t bch = bw[0] & 0xffu;
+            W raw = *(const W *)blk_entry(tab, bch & (CMASK & 0xffu), 0, pitch);
+            if (PLANES) raw &= ~(A7 ^ (0u - (bch >> 7)));
+            step(funnel_r(raw, raw, (phase + (uint32_t)u) & 31u));
+#pragma unroll
+            for (int w = 0; w < 3; w++) bw[w] = funnel_r(bw[w], bw[w + 1], 8);
+            bw[3] >>= 8;
+#pragma unroll
+            for (int w = 0; w + 1 < NW - SW0; w++) sw[w] = funnel_r(sw[w], sw[w + 1], 8);
+            sw[NW - 1 - SW0] >>= 8;
+        }
+        matches += acc >> e;
+    } else {
+#pragma unroll
+        for (int w = 0; w < NW - SW0; w++) sw[w] = win[SW0 + w];
+    }
     // leave the table clean: it holds exactly the 32 stream bytes sw[0..7]
 #pragma unroll
     for (int t = 0; t < 32; t++) *(W *)blk_entry(tab, sw[t >> 2], t & 3, pitch) = 0;
-    return dead ? 0xFFFFFFFFu : (uint32_t)diff + (uint32_t)np - matches;
+    return dead ? 0xFFFFFFFFu : (uint32_t)diff + (uint32_t)n - matches;
 }
 
 template <bool TRANS, int PLANES, int C>
@@ -677,15 +695,14 @@ TA_HD uint32_t pair_unit_costs_blk(const uint8_t *a, uint64_t a_len, const uint8
 //     a half; bit 15 of the sum then holds the incoming carry c14 and D0 = ((S ^ VPm) | Eq | VN) still equals the
 //     16-bit result at that bit (if Eq15 = 0 the 16-bit word has (A + VP) ^ VP = c14 there as well; if Eq15 = 1, D0 = 1);
 //   * X = (D0 >> 1) & M shifts a zero into row 15 of each half, as a 16-bit shift would.
-// Both pairs must have the same number of 16-column supersteps once their lengths are rounded up
-// ((n_A + 15) / 16 == (n_B + 15) / 16); each is padded with its own virtual all-match columns in front (see
-// distance_blk), so there is no rolled tail.  dP = exact distance if <= max_k.
+// Both pairs must have the same number of full 16-column supersteps (n_A / 16 == n_B / 16); the last columns run in a
+// rolled loop that counts each pair's matches only inside its own length.  dP = exact distance if <= max_k.
 struct DuoSide {  // per-pair state of the duo kernel
     Stream sa, sb;
     uint32_t win[12];  // class bits of pattern-stream bytes [16 s - 16, 16 s + 32)
     uint32_t bw[4], bc[4];
     uint32_t g7prev, g7cur;
-    int n, diff, e, dhi, pad;
+    int n, diff, e, dhi;
 };
 
 TA_HD void distance_duo(const uint8_t *aA, int mA, const uint8_t *bA, int nA, uint32_t maxkA, const uint8_t *aB, int mB,
@@ -698,9 +715,8 @@ TA_HD void distance_duo(const uint8_t *aA, int mA, const uint8_t *bA, int nA, ui
         x.diff = n - m;
         x.e = (int)((max_k - (uint32_t)x.diff) >> 1);
         x.dhi = x.diff + x.e;
-        x.pad = (16 - (n & 15)) & 15;  // virtual all-match columns in front of the matrix (see distance_blk)
-        x.sa.init((intptr_t)a - x.dhi - x.pad, (uintptr_t)a, (uintptr_t)a + m - 1);
-        x.sb.init((intptr_t)b - x.pad, (uintptr_t)b, (uintptr_t)b + n - 1);
+        x.sa.init((intptr_t)a - x.dhi, (uintptr_t)a, (uintptr_t)a + m - 1);
+        x.sb.init((intptr_t)b, (uintptr_t)b, (uintptr_t)b + n - 1);
 #pragma unroll
         for (int w = 0; w < 12; w++) x.win[w] = 0;
         x.g7prev = x.g7cur = 0;
@@ -751,11 +767,11 @@ TA_HD void distance_duo(const uint8_t *aA, int mA, const uint8_t *bA, int nA, ui
         for (int w = 0; w < 4; w++) x.bc[w] = x.bw[w] & CMASK;
     };
 
-    // both pairs have the same number of 16-column supersteps once their lengths are rounded up
-    const int steps = (nA + 15) >> 4;  // == (nB + 15) >> 4
-    const uint32_t padbits = ((1u << sd[0].pad) - 1u) | (((1u << sd[1].pad) - 1u) << 16);
-    auto superstep = [&](auto firstc) {
-        constexpr bool FIRST = decltype(firstc)::value != 0;  // the superstep that holds the virtual columns
+    const int steps = nA >> 4;  // == nB >> 4
+    bool dead[2] = {false, false};
+    int s_done = steps;
+    for (int s = 0; s < steps; s++) {
+        const uint32_t m_old0 = matches[0], m_old1 = matches[1];
         take_side(sd[0]);
         take_side(sd[1]);
         // start of chunk q (8 columns): planes of the entering block, dead block [g - 8, g) zeroed by value
@@ -802,7 +818,6 @@ TA_HD void distance_duo(const uint8_t *aA, int mA, const uint8_t *bA, int nA, ui
                 const uint32_t m1 = (0xffffu >> u) * 0x10001u;
                 Eq = ((raw >> u) & m1) | ((raw << (16 - u)) & ~m1);
             }
-            if (FIRST) Eq |= ((padbits >> u) & 0x10001u) * 0xffffu;  // all-ones in a pair's virtual column
             step(Eq, emask);
         }
         matches[0] += (acc & 0xffffu) >> sd[0].e;
@@ -812,35 +827,72 @@ TA_HD void distance_duo(const uint8_t *aA, int mA, const uint8_t *bA, int nA, ui
         for (int P = 0; P < 2; P++)
 #pragma unroll
             for (int w = 0; w < 8; w++) sd[P].win[w] = sd[P].win[w + 4];
-    };
-    // early exit (see distance_blk): a pair whose final-diagonal value passed max_k is decided; leave when both are.
-    // The test uses the counts as of the start of the superstep, which are long computed.
-    bool dead[2] = {false, false};
-    int s = 0;
-    if (padbits) {
-        superstep(IntC<1>());
-        s = 1;
-    }
-    for (; s < steps; s++) {
-        const uint32_t cols = (uint32_t)s << 4, m0 = matches[0], m1 = matches[1];
-        superstep(IntC<0>());
-        dead[0] = dead[0] || (uint32_t)sd[0].diff + cols - m0 > maxkA;
-        dead[1] = dead[1] || (uint32_t)sd[1].diff + cols - m1 > maxkB;
-        if (dead[0] && dead[1]) break;
+        // early exit (see distance_blk): a pair whose final-diagonal value passed max_k is decided; leave when both
+        // are.  The test uses the counts as of the start of this superstep, which are long computed.
+        const uint32_t cols = (uint32_t)s << 4;
+        dead[0] = dead[0] || (uint32_t)sd[0].diff + cols - m_old0 > maxkA;
+        dead[1] = dead[1] || (uint32_t)sd[1].diff + cols - m_old1 > maxkB;
+        if (dead[0] && dead[1]) {
+            s_done = s + 1;
+            break;
+        }
     }
     // tables now hold stream bytes [j0 - 8, j0 + 8) of each pair = window bytes from offset 8
-    uint32_t sw[2][4];
+    const int j0 = s_done << 4;
+    const bool both_dead = dead[0] && dead[1];
+    const int rA = nA - j0, rB = nB - j0, r = both_dead ? 0 : (rA > rB ? rA : rB);
+    uint32_t sw[2][10];
+    if (r > 0) {  // last columns: exact per-column sliding, rolled; each pair counts only its own columns
+        take_side(sd[0]);
+        take_side(sd[1]);
+        uint32_t tops = 0;
 #pragma unroll
-    for (int P = 0; P < 2; P++)
+        for (int P = 0; P < 2; P++) {
+            tops |= ((sd[P].g7prev & 0xff00u) | (sd[P].g7cur & 0x00ffu)) << (16 * P);
 #pragma unroll
-        for (int w = 0; w < 4; w++) sw[P][w] = sd[P].win[2 + w];
+            for (int w = 0; w < 10; w++) sw[P][w] = sd[P].win[2 + w];
+        }
+        for (int u = 0; u < r; u++) {
+            const uint32_t bit = 1u << ((u + 8) & 15);
+#pragma unroll
+            for (int P = 0; P < 2; P++) {
+                // byte j - 8 (sw byte 0) is dead and byte j + 8 (sw byte 16) takes over its position
+                *half_ptr(P, sw[P][0] & 0xffu, 0) &= (uint16_t)~bit;
+                *half_ptr(P, sw[P][4] & 0xffu, 0) |= (uint16_t)bit;
+            }
+            const uint32_t bit2 = bit * 0x10001u;
+            A7 = (A7 & ~bit2) | (tops & bit2);
+            const uint32_t chA = sd[0].bw[0] & 0xffu, chB = sd[1].bw[0] & 0xffu;
+            uint32_t raw = (uint32_t)*half_ptr(0, chA & 0x7fu, 0) | ((uint32_t)*half_ptr(1, chB & 0x7fu, 0) << 16);
+            raw &= ~(A7 ^ (((0u - (chA >> 7)) & 0xffffu) | ((0u - (chB >> 7)) << 16)));
+            const uint32_t m1 = (0xffffu >> u) * 0x10001u;
+            const uint32_t Eq = u ? (((raw >> u) & m1) | ((raw << (16 - u)) & ~m1)) : raw;
+            step(Eq, (u < rA ? (emask & 0xffffu) : 0u) | (u < rB ? (emask & 0xffff0000u) : 0u));
+#pragma unroll
+            for (int P = 0; P < 2; P++) {
+#pragma unroll
+                for (int w = 0; w < 3; w++) sd[P].bw[w] = funnel_r(sd[P].bw[w], sd[P].bw[w + 1], 8);
+                sd[P].bw[3] >>= 8;
+#pragma unroll
+                for (int w = 0; w < 9; w++) sw[P][w] = funnel_r(sw[P][w], sw[P][w + 1], 8);
+                sw[P][9] >>= 8;
+            }
+        }
+        matches[0] += (acc & 0xffffu) >> sd[0].e;
+        matches[1] += (acc >> 16) >> sd[1].e;
+    } else {
+#pragma unroll
+        for (int P = 0; P < 2; P++)
+#pragma unroll
+            for (int w = 0; w < 10; w++) sw[P][w] = sd[P].win[2 + w];
+    }
     // leave the table clean: each half holds exactly the 16 stream bytes sw[P][0..3]
 #pragma unroll
     for (int P = 0; P < 2; P++)
 #pragma unroll
         for (int t = 0; t < 16; t++) *half_ptr(P, sw[P][t >> 2], t & 3) = 0;
-    dA = dead[0] ? 0xFFFFFFFFu : (uint32_t)sd[0].diff + (uint32_t)(nA + sd[0].pad) - matches[0];
-    dB = dead[1] ? 0xFFFFFFFFu : (uint32_t)sd[1].diff + (uint32_t)(nB + sd[1].pad) - matches[1];
+    dA = dead[0] ? 0xFFFFFFFFu : (uint32_t)sd[0].diff + (uint32_t)nA - matches[0];
+    dB = dead[1] ? 0xFFFFFFFFu : (uint32_t)sd[1].diff + (uint32_t)nB - matches[1];
 }
 
 // One pair's contract up to the point where the DP is needed (reference src/levenshtein.rs:386-430 with unit
