@@ -354,9 +354,9 @@ TA_HD uint32_t distance_tab(const uint8_t *a, int m, const uint8_t *b, int n, ui
     };
 
     uint32_t aw[4] = {0, 0, 0, 0}, bw[4], bc[4];
-    bool dead = false;
+    int lim = n;
     int j0 = 0;
-    for (; j0 + 16 <= n; j0 += 16) {  // full 16-column chunks: every selector and shift below is a constant
+    for (; j0 + 16 <= lim; j0 += 16) {  // full 16-column chunks: every selector and shift below is a constant
         const uint32_t m_old = matches;
         sa.take(aw);                  // the bytes that enter during this chunk
         sb.take(bw);
@@ -397,11 +397,9 @@ TA_HD uint32_t distance_tab(const uint8_t *a, int m, const uint8_t *b, int n, ui
         bit0 = (W)((W)1 << phase);
         // early exit: the final-diagonal value diff + j - matches(j) never decreases and ends as the result (tested
         // on the count as of the start of this chunk, which is long computed: the branch never waits for the chain)
-        if ((uint32_t)diff + (uint32_t)j0 - m_old > max_k) {
-            dead = true;
-            break;
-        }
+        lim = (uint32_t)diff + (uint32_t)j0 - m_old > max_k ? 0 : lim;  // folded into the loop bound: single exit
     }
+    const bool dead = lim == 0;  // (n >= 1 here)
     if (!dead && j0 < n) {  // last n % 16 columns: the same column step, rolled, bytes shifted out of the chunk's words
         sa.take(aw);
         sb.take(bw);
@@ -602,18 +600,16 @@ TA_HD uint32_t distance_blk(const uint8_t *a, int m, const uint8_t *b, int n, ui
     // that value is long computed, so the branch never waits for the recurrence's dependency chain (testing the fresh
     // count drained the pipeline at every back edge, a test between the two unrolled supersteps split the
     // straight-line body: 3-9 % on the matching pairs).  Unrelated pairs leave after two passes.
-    bool dead = false;
+    // The exit is folded into the loop bound (lim drops to 0) so that the loop keeps a single exit.
+    int lim = n;
     int j0 = 0;
-    for (; j0 + 32 <= n; j0 += 32) {
+    for (; j0 + 32 <= lim; j0 += 32) {
         const uint32_t m_old = matches;
         superstep(IntC<0>());
         superstep(IntC<16>());
-        if ((uint32_t)diff + (uint32_t)j0 - m_old > max_k) {
-            dead = true;
-            j0 += 32;
-            break;
-        }
+        lim = (uint32_t)diff + (uint32_t)j0 - m_old > max_k ? 0 : lim;
     }
+    const bool dead = lim == 0;  // (n >= 1 here)
     uint32_t phase = 0;
     if (!dead && j0 + 16 <= n) {
         superstep(IntC<0>());
@@ -770,7 +766,8 @@ TA_HD void distance_duo(const uint8_t *aA, int mA, const uint8_t *bA, int nA, ui
     const int steps = nA >> 4;  // == nB >> 4
     bool dead[2] = {false, false};
     int s_done = steps;
-    for (int s = 0; s < steps; s++) {
+    int slim = steps;
+    for (int s = 0; s < slim; s++) {
         const uint32_t m_old0 = matches[0], m_old1 = matches[1];
         take_side(sd[0]);
         take_side(sd[1]);
@@ -832,9 +829,9 @@ TA_HD void distance_duo(const uint8_t *aA, int mA, const uint8_t *bA, int nA, ui
         const uint32_t cols = (uint32_t)s << 4;
         dead[0] = dead[0] || (uint32_t)sd[0].diff + cols - m_old0 > maxkA;
         dead[1] = dead[1] || (uint32_t)sd[1].diff + cols - m_old1 > maxkB;
-        if (dead[0] && dead[1]) {
+        if (dead[0] && dead[1]) {  // folded into the loop bound: the loop keeps a single exit
             s_done = s + 1;
-            break;
+            slim = 0;
         }
     }
     // tables now hold stream bytes [j0 - 8, j0 + 8) of each pair = window bytes from offset 8
