@@ -89,6 +89,25 @@ class Engine {
                                                  SearchType::Best, LEVENSHTEIN_COSTS, false);
     }
 
+    // The crate's scalar / word-wise / movemask variants are CPU micro-variants of the same contracts: names for the
+    // same entry points, so that every public name of the crate resolves.
+    uint32_t hamming_naive(bytes a, bytes b) { return hamming(a, b); }          // src/hamming.rs:36-47
+    uint32_t hamming_words_64(bytes a, bytes b) { return hamming(a, b); }       // src/hamming.rs:176
+    uint32_t hamming_words_128(bytes a, bytes b) { return hamming(a, b); }      // src/hamming.rs:249
+    uint32_t hamming_simd_parallel(bytes a, bytes b) { return hamming(a, b); }  // src/hamming.rs:317-330
+    uint32_t hamming_simd_movemask(bytes a, bytes b) { return hamming(a, b); }  // src/hamming.rs:354
+    uint32_t levenshtein_naive(bytes a, bytes b) { return levenshtein(a, b); }  // src/levenshtein.rs:105
+    std::optional<uint32_t> levenshtein_naive_k(bytes a, bytes b, uint32_t k) { return levenshtein_simd_k(a, b, k); }
+    std::optional<uint32_t> levenshtein_naive_k_with_opts(bytes a, bytes b, uint32_t k, const EditCosts &costs) {
+        return levenshtein_simd_k_with_opts(a, b, k, costs);  // src/levenshtein.rs:376-607: the contract itself
+    }
+    std::vector<Match> levenshtein_search_naive_with_opts(bytes needle, bytes haystack, uint32_t k, SearchType st,
+                                                          const EditCosts &costs, bool anchored) {  // :1589-1838
+        return levenshtein_search_simd_with_opts(needle, haystack, k, st, costs, anchored);
+    }
+    std::vector<Match> levenshtein_search_naive(bytes needle, bytes haystack) { return levenshtein_search(needle, haystack); }
+    std::vector<Match> levenshtein_search_simd(bytes needle, bytes haystack) { return levenshtein_search(needle, haystack); }
+
    private:
     void check(int rc) {
         if (rc == TA_OK) return;

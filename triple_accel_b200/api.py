@@ -369,6 +369,38 @@ class Engine:
 
     levenshtein_search = levenshtein_search_simd  # src/levenshtein.rs:2508-2513
 
+    # ---- the crate's remaining public names: same contracts, so the same kernels -------------
+    # The reference's scalar ("naive"), word-wise and movemask variants are CPU micro-variants of functions that
+    # return identical values; here they are names for the one GPU path, so that every `pub fn` of the crate resolves.
+    hamming_naive = hamming              # src/hamming.rs:36-47
+    hamming_words_64 = hamming           # src/hamming.rs:176 (the reference additionally wants alloc_str'd inputs)
+    hamming_words_128 = hamming          # src/hamming.rs:249
+    hamming_simd_parallel = hamming      # src/hamming.rs:317-330
+    hamming_simd_movemask = hamming      # src/hamming.rs:354
+    levenshtein_naive = levenshtein      # src/levenshtein.rs:105 (u8 slices)
+    levenshtein_naive_k = levenshtein_simd_k                      # src/levenshtein.rs:342-349
+    levenshtein_naive_k_with_opts = levenshtein_simd_k_with_opts  # src/levenshtein.rs:376-607 (the contract itself)
+    levenshtein_search_naive = levenshtein_search_simd                        # src/levenshtein.rs:1549-1556
+    levenshtein_search_naive_with_opts = levenshtein_search_simd_with_opts    # src/levenshtein.rs:1589-1838
+    # (the scalar Hamming search does not reject NUL bytes in the haystack; the public entry, and this path, do:
+    #  src/hamming.rs:463, src/lib.rs:237-243)
+    hamming_search_naive = hamming_search_simd                      # src/hamming.rs:70-72
+    hamming_search_naive_with_opts = hamming_search_simd_with_opts  # src/hamming.rs:96-146
+
+    def levenshtein_naive_with_opts(self, a, b, trace_on=False, costs=LEVENSHTEIN_COSTS):
+        """src/levenshtein.rs:148-319: (distance, None).  The distance is the k = u32::MAX case of the bounded routine;
+        the unbounded routine's traceback has its own tie order and is not on the offloaded path."""
+        if trace_on:
+            raise NotImplementedError("levenshtein_naive_with_opts(trace_on=true): use levenshtein_simd_k_with_opts")
+        return self.levenshtein_simd_k_with_opts(a, b, 0xFFFFFFFF, False, costs)
+
+    def levenstein_naive_str(self, a: str, b: str):
+        """src/levenshtein.rs:123-127 (sic): distance between two `str`s counted in chars."""
+        r = self.levenshtein_simd_k_str(a, b, 0xFFFFFFFF)
+        if r is None:
+            raise OverflowError("more than 256 distinct chars: not representable on the u8 path")
+        return r
+
 
 _default = None
 
@@ -408,3 +440,20 @@ hamming_batch = _forward("hamming_batch")
 levenshtein_k_batch = _forward("levenshtein_k_batch")
 levenshtein_exp_batch = _forward("levenshtein_exp_batch")
 levenshtein_search_batch = _forward("levenshtein_search_batch")
+for _n in ("hamming_naive", "hamming_words_64", "hamming_words_128", "hamming_simd_parallel", "hamming_simd_movemask",
+           "levenshtein_naive", "levenshtein_naive_k", "levenshtein_naive_k_with_opts", "levenshtein_naive_with_opts",
+           "levenstein_naive_str", "levenshtein_search_naive", "levenshtein_search_naive_with_opts",
+           "hamming_search_naive", "hamming_search_naive_with_opts"):
+    globals()[_n] = _forward(_n)
+
+
+def alloc_str(length):
+    """src/lib.rs:196-206: a zeroed, 16-byte-aligned byte string of `length` bytes.  (Alignment only mattered to the
+    reference's word-wise CPU loops; the GPU path takes any alignment.)"""
+    return bytearray(length)
+
+
+def fill_str(dest, src):
+    """src/lib.rs:228-235: copies src into the front of dest; panics (asserts) if dest is shorter."""
+    assert len(dest) >= len(src)
+    dest[:len(src)] = src
