@@ -116,6 +116,25 @@ def reference_cpu_run(orc, op, a, ao, b, bo, k, costs, cnt, threads, length):
     return oracle_run(orc, op, a, ao, b, bo, k, costs, cnt, threads), "scalar oracle (port of the reference's scalar routine)"
 
 
+def dominant_kernel(op, k, costs, length):
+    """name of the kernel the dispatcher picks for this workload (triple_accel_b200/csrc/lev_bitpar.cu, search.cu)"""
+    if op == "hamming":
+        return "hamming_kernel"
+    if op == "search":
+        return "search_pigeon_staged_kernel (+ search_wave_kernel on the flagged 128-byte sub-segments)"
+    unit = tuple(costs[:3]) == (1, 1, 0) and costs[3] <= 1
+    if op == "exp":
+        k = 15 if costs[3] else 16  # first round of the exponential search
+    band = min(k, length) + 1 + (1 if costs[3] else 0)
+    if not unit or band > 64:
+        return "lev_band_kernel"
+    if band <= 9 and not costs[3]:
+        return "lev_bitpar_duo_kernel"
+    if band <= 25:
+        return "lev_bitpar_blk_kernel<C=%d>" % (16 if band <= 17 else 8)
+    return "lev_bitpar_tab_kernel<%s>" % ("u32" if band <= 32 else "u64")
+
+
 class ClockSampler:
     """samples nvidia-smi SM clocks / throttle reasons during the timed region"""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -398,8 +417,7 @@ def main():
         traffic = json.load(open(tpath)).get(args.workload)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                "kernel": {"hamming": "hamming_kernel", "search": "search_filter_kernel (+ search_wave_kernel on hits)"}
-                .get(op, "lev_bitpar_blk_kernel / lev_bitpar_tab_kernel (unit costs) or lev_band_kernel")}
+                "kernel": dominant_kernel(op, k, costs, length)}
 
     cpu_baseline = None
     if not args.no_cpu_baseline:
@@ -413,9 +431,14 @@ def main():
         t0 = time.perf_counter()
         oracle_run(orc, op, a, ao, b, bo, k, costs, sample, threads)
         dt_scalar = time.perf_counter() - t0
+        one = max(1, sample // threads)  # the same reference path on ONE thread (the crate itself is single-threaded)
+        t0 = time.perf_counter()
+        reference_cpu_run(orc, op, a, ao, b, bo, k, costs, one, 1, length)
+        dt_one = time.perf_counter() - t0
         cpu_baseline = {"value": sample * cells_pair / dt / 1e9, "unit": "GCUPS", "cores": threads, "kind": "port",
                         "sample": "first %d units of the same batch; %s on %d threads" % (sample, what, threads),
-                        "pairs_per_s": sample / dt, "scalar_port_pairs_per_s": sample / dt_scalar}
+                        "pairs_per_s": sample / dt, "scalar_port_pairs_per_s": sample / dt_scalar,
+                        "one_thread_pairs_per_s": one / dt_one}
 
     line = {
         "metric": "dp_cell_updates_per_s", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
