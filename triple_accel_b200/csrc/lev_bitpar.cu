@@ -109,7 +109,11 @@ __global__ void __launch_bounds__(256) lev_bitpar_blk_kernel(const uint8_t *__re
         const PairRef nn = load_pair_ref(a_off, b_off, idx, w + 2 * total, n);  // in flight during this pair
         prefetch_l2(a + nxt.a0, nxt.alen);
         prefetch_l2(b + nxt.b0, nxt.blen);
-        out[cur.pair] = bitpar::pair_unit_costs_blk<TRANS, PLANES, C>(a + cur.a0, cur.alen, b + cur.b0, cur.blen, k, tab, pitch);
+        bitpar::NextHint hint;  // first bytes of the next pair: into L1 when this pair leaves its main loop
+        hint.p[0] = nxt.alen ? a + nxt.a0 : nullptr;
+        hint.p[1] = nxt.blen ? b + nxt.b0 : nullptr;
+        hint.p[2] = hint.p[3] = nullptr;
+        out[cur.pair] = bitpar::pair_unit_costs_blk<TRANS, PLANES, C>(a + cur.a0, cur.alen, b + cur.b0, cur.blen, k, tab, pitch, &hint);
         cur = nxt;
         nxt = nn;
     }
@@ -146,7 +150,13 @@ __global__ void __launch_bounds__(128, 3) lev_bitpar_duo_kernel(const uint8_t *_
         const bool dp0 = bitpar::unit_costs_prepare(pa0, la0, pb0, lb0, k, mk0, &r0);
         const bool dp1 = has1 && bitpar::unit_costs_prepare(pa1, la1, pb1, lb1, k, mk1, &r1);
         if (dp0 && dp1 && (lb0 >> 4) == (lb1 >> 4)) {
-            bitpar::distance_duo(pa0, (int)la0, pb0, (int)lb0, mk0, pa1, (int)la1, pb1, (int)lb1, mk1, tab, pitch, r0, r1);
+            bitpar::NextHint hint;  // first bytes of the next item's four strings: into L1 at the end of the main loop
+            hint.p[0] = nx0.alen ? a + nx0.a0 : nullptr;
+            hint.p[1] = nx0.blen ? b + nx0.b0 : nullptr;
+            hint.p[2] = nx1.alen ? a + nx1.a0 : nullptr;
+            hint.p[3] = nx1.blen ? b + nx1.b0 : nullptr;
+            bitpar::distance_duo(pa0, (int)la0, pb0, (int)lb0, mk0, pa1, (int)la1, pb1, (int)lb1, mk1, tab, pitch, r0, r1,
+                                 &hint);
             r0 = r0 <= mk0 ? r0 : 0xFFFFFFFFu;
             r1 = r1 <= mk1 ? r1 : 0xFFFFFFFFu;
         } else {

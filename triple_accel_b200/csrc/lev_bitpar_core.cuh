@@ -454,6 +454,22 @@ TA_HD uint32_t distance_tab(const uint8_t *a, int m, const uint8_t *b, int n, ui
 // columns slide the table column by column with an exact clear (rolled code).
 //   PLANES = 1: 128 entries (7-bit classes) + the A7 plane;  PLANES = 0: 256 entries, no plane.
 //   `tab` = the thread's entry 0, `pitch` = bytes between entries; the table is all-zero on entry and on exit.
+// The bytes a thread will want first when it starts its NEXT work item: pulled into L1 when the current item leaves
+// its main loop (the tail and the table clean-up that follow hide the L2 latency); device only.
+struct NextHint {
+    const uint8_t *p[4];
+};
+TA_HD void prefetch_next(const NextHint *h) {
+#if defined(__CUDA_ARCH__)
+    if (h) {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (h->p[i]) asm volatile("prefetch.global.L1 [%0];" ::"l"(h->p[i]));
+    }
+#else
+    (void)h;
+#endif
+}
 TA_HD uint8_t *blk_entry(uint8_t *tab, uint32_t w, int t, uint32_t pitch) { return tab + byte_of(w, t) * pitch; }
 template <int V>
 struct IntC {
@@ -462,7 +478,7 @@ struct IntC {
 
 template <bool TRANS, int PLANES, int C>
 TA_HD uint32_t distance_blk(const uint8_t *a, int m, const uint8_t *b, int n, uint32_t max_k, uint8_t *tab,
-                            const uint32_t pitch) {
+                            const uint32_t pitch, const NextHint *next = nullptr) {
     static_assert(C == 8 || C == 16, "block = a byte or a half of the entry");
     static_assert(PLANES == 0 || PLANES == 1, "");
     typedef uint32_t W;
@@ -610,6 +626,7 @@ TA_HD uint32_t distance_blk(const uint8_t *a, int m, const uint8_t *b, int n, ui
         lim = (uint32_t)diff + (uint32_t)j0 - m_old > max_k ? 0 : lim;
     }
     const bool dead = lim == 0;  // (n >= 1 here)
+    prefetch_next(next);
     uint32_t phase = 0;
     if (!dead && j0 + 16 <= n) {
         superstep(IntC<0>());
@@ -661,7 +678,7 @@ TA_HD uint32_t distance_blk(const uint8_t *a, int m, const uint8_t *b, int n, ui
 
 template <bool TRANS, int PLANES, int C>
 TA_HD uint32_t pair_unit_costs_blk(const uint8_t *a, uint64_t a_len, const uint8_t *b, uint64_t b_len, uint32_t k,
-                                   uint8_t *tab, const uint32_t pitch) {
+                                   uint8_t *tab, const uint32_t pitch, const NextHint *next = nullptr) {
     if (a_len > b_len) {
         const uint8_t *tp = a;
         a = b;
@@ -675,7 +692,7 @@ TA_HD uint32_t pair_unit_costs_blk(const uint8_t *a, uint64_t a_len, const uint8
     const uint32_t max_k = k < (uint32_t)n ? k : (uint32_t)n;
     if (diff > max_k) return 0xFFFFFFFFu;
     if (m == 0) return (uint32_t)n;
-    const uint32_t d = distance_blk<TRANS, PLANES, C>(a, m, b, n, max_k, tab, pitch);
+    const uint32_t d = distance_blk<TRANS, PLANES, C>(a, m, b, n, max_k, tab, pitch, next);
     return d <= max_k ? d : 0xFFFFFFFFu;
 }
 
@@ -703,7 +720,7 @@ struct DuoSide {  // per-pair state of the duo kernel
 
 TA_HD void distance_duo(const uint8_t *aA, int mA, const uint8_t *bA, int nA, uint32_t maxkA, const uint8_t *aB, int mB,
                         const uint8_t *bB, int nB, uint32_t maxkB, uint8_t *tab, const uint32_t pitch, uint32_t &dA,
-                        uint32_t &dB) {
+                        uint32_t &dB, const NextHint *next = nullptr) {
     constexpr uint32_t CMASK = 0x7f7f7f7fu, M = 0x7fff7fffu;
     DuoSide sd[2];
     auto setup = [&](DuoSide &x, const uint8_t *a, int m, const uint8_t *b, int n, uint32_t max_k) {
@@ -834,6 +851,7 @@ TA_HD void distance_duo(const uint8_t *aA, int mA, const uint8_t *bA, int nA, ui
             slim = 0;
         }
     }
+    prefetch_next(next);
     // tables now hold stream bytes [j0 - 8, j0 + 8) of each pair = window bytes from offset 8
     const int j0 = s_done << 4;
     const bool both_dead = dead[0] && dead[1];
