@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(256) lev_bitpar_blk_kernel(const uint8_t *__re
         hint.p[0] = nxt.alen ? a + nxt.a0 : nullptr;
         hint.p[1] = nxt.blen ? b + nxt.b0 : nullptr;
         hint.p[2] = hint.p[3] = nullptr;
+        hint.len[0] = nxt.alen, hint.len[1] = nxt.blen, hint.len[2] = hint.len[3] = 0;
         out[cur.pair] = bitpar::pair_unit_costs_blk<TRANS, PLANES, C>(a + cur.a0, cur.alen, b + cur.b0, cur.blen, k, tab, pitch, &hint);
         cur = nxt;
         nxt = nn;
@@ -155,6 +156,7 @@ __global__ void __launch_bounds__(128, 3) lev_bitpar_duo_kernel(const uint8_t *_
             hint.p[1] = nx0.blen ? b + nx0.b0 : nullptr;
             hint.p[2] = nx1.alen ? a + nx1.a0 : nullptr;
             hint.p[3] = nx1.blen ? b + nx1.b0 : nullptr;
+            hint.len[0] = nx0.alen, hint.len[1] = nx0.blen, hint.len[2] = nx1.alen, hint.len[3] = nx1.blen;
             bitpar::distance_duo(pa0, (int)la0, pb0, (int)lb0, mk0, pa1, (int)la1, pb1, (int)lb1, mk1, tab, pitch, r0, r1,
                                  &hint);
             r0 = r0 <= mk0 ? r0 : 0xFFFFFFFFu;

@@ -457,14 +457,18 @@ TA_HD uint32_t distance_tab(const uint8_t *a, int m, const uint8_t *b, int n, ui
 // The bytes a thread will want first when it starts its NEXT work item: pulled into L1 when the current item leaves
 // its main loop (the tail and the table clean-up that follow hide the L2 latency); device only.
 struct NextHint {
-    const uint8_t *p[4];
+    const uint8_t *p[4];  // first byte of each string (nullptr: none)
+    uint32_t len[4];
 };
 TA_HD void prefetch_next(const NextHint *h) {
 #if defined(__CUDA_ARCH__)
     if (h) {
 #pragma unroll
         for (int i = 0; i < 4; i++)
-            if (h->p[i]) asm volatile("prefetch.global.L1 [%0];" ::"l"(h->p[i]));
+            if (h->p[i]) {  // the line of the first byte and the line 127 bytes on (a ragged string straddles two)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(h->p[i]));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(h->p[i] + (h->len[i] < 128u ? h->len[i] - 1u : 127u)));
+            }
     }
 #else
     (void)h;
