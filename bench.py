@@ -38,6 +38,9 @@ WORKLOADS = {
                         "None; the kernel leaves a pair once its final-diagonal value exceeds k)"),
     "lev_k16_len128_R": ("lev_k_R", 1_000_000, 128, 16, (1, 1, 0, 0),
                          "levenshtein_simd_k k=16, 1M pairs len=128, unit costs, set R (b independent of a)"),
+    "lev_k8_ragged96_160": ("lev_k_ragged", 1_000_000, 128, 8, (1, 1, 0, 0),
+                            "levenshtein_simd_k k=8, 1M pairs, |a| ~ U[96,160] (mean 128), unit costs, set M: neighbouring "
+                            "pairs have unrelated lengths (arbitrary alignment, ragged tails, few pairs can share a thread)"),
     "rdamerau_k16_len512": ("lev_k", 1_000_000, 512, 16, (1, 1, 0, 1),
                             "RDAMERAU_COSTS k=16, 1M pairs len=512, set M (U[0,16] edits incl. swaps)"),
     "lev_k16_len4096": ("lev_k", 262_144, 4096, 16, (1, 1, 0, 0),
@@ -62,12 +65,15 @@ def nominal_cells(length, k):
 
 
 RANDOM_SET = [False]  # set by main(): the workload's pairs are unrelated (set R)
+RAGGED_SET = [False]  # set by main(): |a| ~ U[0.75 len, 1.25 len]
 
 
 def make_inputs(op, n, length, k, costs, seed):
     from triple_accel_b200 import synth
     if op == "lev_k" and RANDOM_SET[0]:
         return synth.random_pairs(n, length, seed=seed)
+    if op == "lev_k" and RAGGED_SET[0]:
+        return synth.ragged_mutated_pairs(n, length * 3 // 4, length * 5 // 4, k, seed=seed)
     if op == "hamming":
         return synth.hamming_pairs(n, length, seed=seed)
     if op == "exp":
@@ -203,6 +209,8 @@ def run_reference(args, wl):
     op, n, length, k, costs, desc = wl
     if op == "lev_k_R":
         op, RANDOM_SET[0] = "lev_k", True
+    if op == "lev_k_ragged":
+        op, RAGGED_SET[0] = "lev_k", True
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -263,6 +271,8 @@ def main():
     op, n, length, k, costs, desc = wl
     if op == "lev_k_R":
         op, RANDOM_SET[0] = "lev_k", True
+    if op == "lev_k_ragged":
+        op, RAGGED_SET[0] = "lev_k", True
 
     import torch
     import triple_accel_b200 as ta

@@ -2,7 +2,7 @@
 # every bench workload once (kernel-only, e2e, CPU baseline) -> gpurun_out/bench_all.jsonl
 mkdir -p gpurun_out
 : > gpurun_out/bench_all.jsonl
-for w in lev_k8_len128 lev_k16_len128 lev_k8_len128_R lev_k16_len128_R rdamerau_k16_len512 exp_len1024 search_n32_h4096 lev_k16_len4096 lev_k60_len1024 affine_k16_len128 hamming_len64 hamming_len4096; do
+for w in lev_k8_len128 lev_k16_len128 lev_k8_len128_R lev_k16_len128_R lev_k8_ragged96_160 rdamerau_k16_len512 exp_len1024 search_n32_h4096 lev_k16_len4096 lev_k60_len1024 affine_k16_len128 hamming_len64 hamming_len4096; do
   python bench.py --workload $w --steps ${STEPS:-50} --warmup 5 2>/dev/null | tail -1 >> gpurun_out/bench_all.jsonl
 done
 TA_FORCE_BAND=1 python bench.py --workload lev_k8_len128 --steps 20 --warmup 5 --no-e2e --no-cpu-baseline 2>/dev/null | tail -1 | sed 's/"name": "lev_k8_len128"/"name": "lev_k8_len128 (general lev_band_kernel forced)"/' >> gpurun_out/bench_all.jsonl

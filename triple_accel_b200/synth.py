@@ -81,6 +81,36 @@ def mutated_pairs(n, length, max_edits, seed=1234, exact_edits=False, allow_swap
     return a, fixed_offsets(n, length), b, b_off
 
 
+def ragged_mutated_pairs(n, min_len, max_len, max_edits, seed=1234, templates=4096):
+    """set M with ragged lengths: |a| ~ U[min_len, max_len], b = a after e ~ U[0, max_edits] random edits.
+    Same template + XOR-mask construction as mutated_pairs; consecutive pairs have unrelated lengths."""
+    g = _rng(seed)
+    t = min(templates, n)
+    a_t, b_t = [], []
+    for r in range(t):
+        la = int(g.integers(min_len, max_len + 1))
+        row = g.integers(0, 256, size=la, dtype=np.uint8)
+        a_t.append(row)
+        b_t.append(np.frombuffer(_apply_edits(row, int(g.integers(0, max_edits + 1)), g, False), np.uint8))
+    reps = (n + t - 1) // t
+    masks = g.integers(0, 256, size=reps, dtype=np.uint8)
+    a_cat, b_cat = np.concatenate(a_t), np.concatenate(b_t)
+    a_len = np.array([len(x) for x in a_t], np.uint64)
+    b_len = np.array([len(x) for x in b_t], np.uint64)
+    a_parts, b_parts, al, bl = [], [], [], []
+    for r in range(reps):
+        cnt = min(t, n - r * t)
+        a_parts.append(a_cat[:int(a_len[:cnt].sum())] ^ masks[r])
+        b_parts.append(b_cat[:int(b_len[:cnt].sum())] ^ masks[r])
+        al.append(a_len[:cnt])
+        bl.append(b_len[:cnt])
+    a_off = np.zeros(n + 1, np.uint64)
+    b_off = np.zeros(n + 1, np.uint64)
+    a_off[1:] = np.cumsum(np.concatenate(al))
+    b_off[1:] = np.cumsum(np.concatenate(bl))
+    return np.concatenate(a_parts), a_off, np.concatenate(b_parts), b_off
+
+
 def random_pairs(n, length, seed=1234):
     """set R: independent uniform byte strings of equal length (almost every pair is farther apart than k)."""
     g = _rng(seed)
