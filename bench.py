@@ -119,6 +119,10 @@ def reference_cpu_run(orc, op, a, ao, b, bo, k, costs, cnt, threads, length):
     if simd and op == "lev_k" and orc.lib().orc_simd_covers(length, length, k, orc.Costs(*costs)):
         return orc.levenshtein_simd_k_batch(a, ao[:cnt + 1], b, bo[:cnt + 1], k, costs, threads=threads), \
             "AVX2 restatement of levenshtein_simd_k_with_opts (Avx1x32x8 core)"
+    if simd and op == "search" and len(a) <= 32 and max(len(a) + k, k + 1) <= 255:
+        m, off = orc.levenshtein_search_simd_batch(a, b, bo[:cnt + 1], k, 1, costs, False, threads=threads)
+        return np.concatenate([off.astype(np.uint64), m.reshape(-1)]), \
+            "AVX2 restatement of levenshtein_search_simd_with_opts (Avx1x32x8 search core)"
     return oracle_run(orc, op, a, ao, b, bo, k, costs, cnt, threads), "scalar oracle (port of the reference's scalar routine)"
 
 

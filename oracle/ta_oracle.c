@@ -584,7 +584,7 @@ typedef struct {
     /* search */
     const uint8_t *needle;
     size_t needle_len;
-    int search_type, anchored;
+    int search_type, anchored, simd;
     orc_match **per;
     int64_t *cnt;
 } batch_ctx;
@@ -619,9 +619,12 @@ static void hsearch_range(void *p, size_t lo, size_t hi) {
 static void search_range(void *p, size_t lo, size_t hi) {
     batch_ctx *x = (batch_ctx *)p;
     for (size_t i = lo; i < hi; i++)
-        x->cnt[i] = orc_levenshtein_search_naive_with_opts(x->needle, x->needle_len, x->a + x->a_off[i],
-                                                           x->a_off[i + 1] - x->a_off[i], x->k, x->search_type,
-                                                           x->c, x->anchored, &x->per[i]);
+        x->cnt[i] = x->simd ? orc_levenshtein_search_simd_with_opts(x->needle, x->needle_len, x->a + x->a_off[i],
+                                                                    x->a_off[i + 1] - x->a_off[i], x->k, x->search_type,
+                                                                    x->c, x->anchored, &x->per[i], NULL)
+                            : orc_levenshtein_search_naive_with_opts(x->needle, x->needle_len, x->a + x->a_off[i],
+                                                                     x->a_off[i + 1] - x->a_off[i], x->k,
+                                                                     x->search_type, x->c, x->anchored, &x->per[i]);
 }
 
 /* ---- batch drivers over the AVX2 restatement of the reference's SIMD path (ta_ref_avx2.c): CPU baseline only ---- */
@@ -685,12 +688,26 @@ void orc_levenshtein_exp_batch(const uint8_t *a, const uint64_t *a_off, const ui
     parallel_for(n, 64, n_threads, lev_exp_range, &x);
 }
 
+static int64_t search_batch_impl(const uint8_t *needle, size_t needle_len, const uint8_t *hay, const uint64_t *hay_off,
+                                 size_t n, uint32_t k, int search_type, orc_costs c, int anchored, orc_match **out,
+                                 uint64_t *match_off, int n_threads, int simd);
 int64_t orc_levenshtein_search_batch(const uint8_t *needle, size_t needle_len, const uint8_t *hay,
                                      const uint64_t *hay_off, size_t n, uint32_t k, int search_type, orc_costs c,
                                      int anchored, orc_match **out, uint64_t *match_off, int n_threads) {
+    return search_batch_impl(needle, needle_len, hay, hay_off, n, k, search_type, c, anchored, out, match_off, n_threads, 0);
+}
+/* the same loop over the AVX2 restatement of the reference's SIMD search (ta_ref_avx2.c): CPU baseline only */
+int64_t orc_levenshtein_search_simd_batch(const uint8_t *needle, size_t needle_len, const uint8_t *hay,
+                                          const uint64_t *hay_off, size_t n, uint32_t k, int search_type, orc_costs c,
+                                          int anchored, orc_match **out, uint64_t *match_off, int n_threads) {
+    return search_batch_impl(needle, needle_len, hay, hay_off, n, k, search_type, c, anchored, out, match_off, n_threads, 1);
+}
+static int64_t search_batch_impl(const uint8_t *needle, size_t needle_len, const uint8_t *hay, const uint64_t *hay_off,
+                                 size_t n, uint32_t k, int search_type, orc_costs c, int anchored, orc_match **out,
+                                 uint64_t *match_off, int n_threads, int simd) {
     batch_ctx x = {0};
     x.a = hay, x.a_off = hay_off, x.k = k, x.c = c, x.needle = needle, x.needle_len = needle_len;
-    x.search_type = search_type, x.anchored = anchored;
+    x.search_type = search_type, x.anchored = anchored, x.simd = simd;
     x.per = (orc_match **)calloc(n ? n : 1, sizeof(orc_match *));
     x.cnt = (int64_t *)calloc(n ? n : 1, sizeof(int64_t));
     parallel_for(n, 16, n_threads, search_range, &x);

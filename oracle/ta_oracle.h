@@ -105,6 +105,13 @@ uint32_t orc_levenshtein_simd_k_with_opts(const uint8_t *a, size_t a_len, const 
 uint32_t orc_levenshtein_simd_exp_with_opts(const uint8_t *a, size_t a_len, const uint8_t *b, size_t b_len,
                                             orc_costs c);
 int64_t orc_hamming_simd(const uint8_t *a, size_t a_len, const uint8_t *b, size_t b_len);
+/* levenshtein_search_simd_with_opts -> the Avx1x32x8 search core (needle <= 32 bytes, u8 cells), else the scalar oracle */
+int64_t orc_levenshtein_search_simd_with_opts(const uint8_t *needle, size_t needle_len, const uint8_t *haystack,
+                                              size_t haystack_len, uint32_t k, int search_type, orc_costs c,
+                                              int anchored, orc_match **out, int *covered);
+int64_t orc_levenshtein_search_simd_batch(const uint8_t *needle, size_t needle_len, const uint8_t *hay,
+                                          const uint64_t *hay_off, size_t n, uint32_t k, int search_type, orc_costs c,
+                                          int anchored, orc_match **out, uint64_t *match_off, int n_threads);
 void orc_levenshtein_simd_k_batch(const uint8_t *a, const uint64_t *a_off, const uint8_t *b, const uint64_t *b_off,
                                   size_t n, uint32_t k, orc_costs c, uint32_t *out, int n_threads);
 void orc_levenshtein_simd_exp_batch(const uint8_t *a, const uint64_t *a_off, const uint8_t *b, const uint64_t *b_off,

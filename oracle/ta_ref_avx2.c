@@ -23,6 +23,7 @@
 #include <immintrin.h>
 #include <stddef.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "ta_oracle.h"
@@ -262,4 +263,178 @@ int64_t orc_hamming_simd(const uint8_t *a, size_t a_len, const uint8_t *b, size_
     if (a_len != b_len) return -1;
     if (orc_simd_available()) return (int64_t)count_mismatches_avx2(a, b, a_len);
     return orc_hamming_naive(a, a_len, b, b_len);
+}
+
+/* ------------------------------------------------------------------------------------------------------------ */
+/* levenshtein_search_simd_with_opts -> levenshtein_search_simd_core_avx_1x32x8, src/levenshtein.rs:1911-2155,  */
+/* 2161-2449, with Jewel's double_min_length / triple_min_length (src/jewel.rs:362-417).  Restated for the      */
+/* single-register u8 type only (needle <= 32 bytes and max(needle_len + unit_k, k + 1) <= 255: every search    */
+/* configuration in BASELINE.json); anything else falls back to the scalar oracle (*covered = 0).  The SIMD     */
+/* path's length tie-break differs from the scalar routine's in rare cases: this is a timing  */
+/* baseline, not the parity oracle.                                                                             */
+
+TGT static inline __m256i shl2(__m256i v) { /* lane i <- lane i + 2, zeros into lanes 30, 31 */
+    return _mm256_alignr_epi8(_mm256_permute2x128_si256(v, v, 0x81), v, 2);
+}
+TGT static inline void double_min_length(__m256i new_gap, __m256i *cont_gap, __m256i new_len, __m256i *cont_len) {
+    const __m256i res_min = _mm256_min_epu8(new_gap, *cont_gap);
+    const __m256i new_mask = _mm256_cmpeq_epi8(new_gap, res_min);
+    __m256i res_len = _mm256_blendv_epi8(*cont_len, new_len, new_mask);
+    const __m256i eq_mask = _mm256_cmpeq_epi8(new_gap, *cont_gap);
+    res_len = _mm256_blendv_epi8(res_len, _mm256_max_epu8(new_len, *cont_len), eq_mask);
+    *cont_gap = res_min;
+    *cont_len = res_len;
+}
+TGT static inline void triple_min_length(__m256i sub, __m256i a_gap, __m256i b_gap, __m256i sub_len, __m256i a_len,
+                                         __m256i b_len, __m256i *res_min, __m256i *res_len) {
+    const __m256i min1 = _mm256_min_epu8(a_gap, b_gap);
+    const __m256i a_mask = _mm256_cmpeq_epi8(a_gap, min1);
+    __m256i len1 = _mm256_blendv_epi8(b_len, a_len, a_mask);
+    len1 = _mm256_blendv_epi8(len1, _mm256_max_epu8(a_len, b_len), _mm256_cmpeq_epi8(a_gap, b_gap));
+    const __m256i min2 = _mm256_min_epu8(sub, min1);
+    __m256i len2 = _mm256_blendv_epi8(len1, sub_len, _mm256_cmpeq_epi8(sub, min2));
+    len2 = _mm256_blendv_epi8(len2, _mm256_max_epu8(sub_len, len1), _mm256_cmpeq_epi8(sub, min1));
+    *res_min = min2;
+    *res_len = len2;
+}
+
+typedef struct {
+    orc_match *v;
+    size_t n, cap;
+} match_vec;
+static void mv_push(match_vec *m, uint64_t start, uint64_t end, uint32_t k) {
+    if (m->n == m->cap) {
+        m->cap = m->cap ? 2 * m->cap : 16;
+        m->v = (orc_match *)realloc(m->v, m->cap * sizeof(orc_match));
+    }
+    m->v[m->n].start = start, m->v[m->n].end = end, m->v[m->n].k = k, m->v[m->n]._pad = 0;
+    m->n++;
+}
+
+TGT static int64_t search_core_1x32x8(const uint8_t *needle, size_t needle_len, const uint8_t *haystack,
+                                      size_t haystack_len, uint32_t k, int best, orc_costs costs, int anchored,
+                                      orc_match **out) {
+    const __m256i ones8 = _mm256_set1_epi8(-1), zeros = _mm256_setzero_si256();
+    __m256i dp0 = ones8, dp_temp = ones8, dp1 = ones8, dp2 = ones8, needle_gap_dp = ones8, haystack_gap_dp = ones8;
+    const uint32_t open = (uint32_t)costs.start_gap + costs.gap;
+    dp2 = slow_insert(dp2, 31, open); /* :2185-2192 */
+    haystack_gap_dp = slow_insert(haystack_gap_dp, 31, open);
+    __m256i length0 = zeros, length_temp = zeros, length1 = zeros, length2 = zeros, needle_gap_length = zeros,
+            haystack_gap_length = zeros;
+    const __m256i ones = _mm256_set1_epi8(1), twos = _mm256_set1_epi8(2);
+    size_t len; /* :2206-2218 */
+    if (anchored) {
+        size_t extra = (size_t)((k > costs.start_gap ? k - costs.start_gap : 0u) / costs.gap);
+        size_t lim = needle_len + extra < needle_len ? (size_t)-1 : needle_len + extra;
+        len = needle_len + (haystack_len < lim ? haystack_len : lim);
+    } else {
+        len = needle_len + haystack_len;
+    }
+    const int final_idx = 32 - (int)needle_len;
+    __m256i needle_window = slow_loadu(zeros, 31, needle, needle_len, 1); /* :2223-2229 */
+    __m256i haystack_window = zeros;
+    size_t haystack_idx = 0;
+    uint32_t curr_k = k;
+    __m256i match_mask0 = zeros, match_mask1, match_mask_cost, sub, sub_length, needle_gap, haystack_gap,
+            transpose = zeros, transpose_length = zeros;
+    const __m256i mismatch_cost = _mm256_set1_epi8((char)costs.mismatch), gap_cost = _mm256_set1_epi8((char)costs.gap),
+                  start_gap_cost = _mm256_set1_epi8((char)costs.start_gap),
+                  transpose_cost = _mm256_set1_epi8((char)costs.transpose);
+    const int allow_transpose = costs.transpose != 0;
+    match_vec res = {0, 0, 0};
+#define CAPK(x) ((x) < k + 1 ? (x) : k + 1)
+    for (size_t i = 1; i < len;) { /* :2283 */
+        haystack_window = shl1(haystack_window);
+        if (haystack_idx < haystack_len) {
+            haystack_window = _mm256_insert_epi8(haystack_window, (char)haystack[haystack_idx], 31); /* insert_last_0 */
+            haystack_idx++;
+        }
+        match_mask1 = _mm256_cmpeq_epi8(needle_window, haystack_window);
+        match_mask_cost = _mm256_andnot_si256(match_mask1, mismatch_cost);
+        sub = shl1(dp1); /* match/mismatch, :2297-2311 */
+        if (anchored && i > 1) sub = _mm256_insert_epi8(sub, (char)CAPK((uint32_t)(i - 1) * costs.gap + costs.start_gap), 31);
+        sub = _mm256_adds_epu8(sub, match_mask_cost);
+        sub_length = _mm256_add_epi8(shl1(length1), ones);
+        needle_gap = _mm256_adds_epu8(dp2, start_gap_cost); /* gap in needle, :2314-2322 */
+        double_min_length(needle_gap, &needle_gap_dp, length2, &needle_gap_length);
+        needle_gap_dp = _mm256_adds_epu8(needle_gap_dp, gap_cost);
+        needle_gap_length = _mm256_add_epi8(needle_gap_length, ones);
+        haystack_gap = _mm256_adds_epu8(dp2, start_gap_cost); /* gap in haystack, :2325-2346 */
+        double_min_length(haystack_gap, &haystack_gap_dp, length2, &haystack_gap_length);
+        haystack_gap_dp = shl1(haystack_gap_dp);
+        if (anchored)
+            haystack_gap_dp = _mm256_insert_epi8(haystack_gap_dp, (char)CAPK((uint32_t)i * costs.gap + costs.start_gap), 31);
+        else
+            haystack_gap_dp = _mm256_insert_epi8(haystack_gap_dp, (char)costs.start_gap, 31);
+        haystack_gap_dp = _mm256_adds_epu8(haystack_gap_dp, gap_cost);
+        haystack_gap_length = shl1(haystack_gap_length);
+        if (allow_transpose) { /* :2348-2367 */
+            transpose = _mm256_and_si256(shl1(match_mask0), match_mask0);
+            match_mask0 = _mm256_andnot_si256(match_mask1, transpose);
+            dp0 = shl2(dp0);
+            if (anchored && i > 3) dp0 = _mm256_insert_epi8(dp0, (char)CAPK((uint32_t)(i - 3) * costs.gap + costs.start_gap), 30);
+            length0 = shl2(length0);
+            transpose = _mm256_adds_epu8(dp0, transpose_cost);
+            transpose_length = _mm256_add_epi8(length0, twos);
+        }
+        triple_min_length(sub, needle_gap_dp, haystack_gap_dp, sub_length, needle_gap_length, haystack_gap_length, &dp0,
+                          &length0);
+        if (allow_transpose) {
+            dp0 = _mm256_blendv_epi8(dp0, transpose, match_mask0);
+            length0 = _mm256_blendv_epi8(length0, transpose_length, match_mask0);
+            __m256i t = match_mask0;
+            match_mask0 = match_mask1;
+            match_mask1 = t;
+        }
+        { /* :2388-2393 */
+            __m256i t = dp0;
+            dp0 = dp_temp, dp_temp = dp1, dp1 = dp2, dp2 = t;
+            t = length0;
+            length0 = length_temp, length_temp = length1, length1 = length2, length2 = t;
+        }
+        i++;
+        if (i >= needle_len) { /* :2397-2420 */
+            uint8_t a1[32], a2[32];
+            _mm256_storeu_si256((__m256i *)a1, dp2);
+            _mm256_storeu_si256((__m256i *)a2, length2);
+            const uint32_t final_res = a1[final_idx];
+            const size_t final_length = a2[final_idx];
+            if (final_res <= curr_k) {
+                const size_t end_idx = i - needle_len;
+                if (best) curr_k = final_res;
+                if (!best || res.n == 0 || end_idx - final_length > res.v[res.n - 1].start)
+                    mv_push(&res, end_idx - final_length, end_idx, final_res); /* :2429-2441 folded in */
+                else
+                    res.v[res.n - 1].start = end_idx - final_length, res.v[res.n - 1].end = end_idx,
+                                   res.v[res.n - 1].k = final_res;
+            }
+        }
+    }
+#undef CAPK
+    if (best) { /* only retain matches with the lowest k, :2447 */
+        size_t w = 0;
+        for (size_t r = 0; r < res.n; r++)
+            if (res.v[r].k == curr_k) res.v[w++] = res.v[r];
+        res.n = w;
+    }
+    *out = res.v;
+    return (int64_t)res.n;
+}
+
+/* public entry; *covered = 0 when the scalar oracle answered instead */
+int64_t orc_levenshtein_search_simd_with_opts(const uint8_t *needle, size_t needle_len, const uint8_t *haystack,
+                                              size_t haystack_len, uint32_t k, int search_type, orc_costs c,
+                                              int anchored, orc_match **out, int *covered) {
+    if (covered) *covered = 0;
+    if (needle_len != 0 && orc_costs_valid_search(c) && orc_simd_available()) {
+        const uint32_t unit_k = (k > c.start_gap ? k - c.start_gap : 0u) / c.gap;
+        uint64_t ub1 = (uint64_t)needle_len + unit_k, ub2 = (uint64_t)k + 1;
+        const uint64_t upper = ub1 > ub2 ? ub1 : ub2;
+        if (needle_len <= 32 && upper <= 255) {
+            if (covered) *covered = 1;
+            return search_core_1x32x8(needle, needle_len, haystack, haystack_len, k, search_type == 1, c, anchored, out);
+        }
+    }
+    return orc_levenshtein_search_naive_with_opts(needle, needle_len, haystack, haystack_len, k, search_type, c,
+                                                  anchored, out);
 }

@@ -101,6 +101,12 @@ def lib():
         L.orc_levenshtein_simd_exp_batch.argtypes = L.orc_levenshtein_exp_batch.argtypes
         L.orc_hamming_simd_batch.restype = None
         L.orc_hamming_simd_batch.argtypes = L.orc_hamming_batch.argtypes
+        L.orc_levenshtein_search_simd_with_opts.restype = C.c_int64
+        L.orc_levenshtein_search_simd_with_opts.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_uint32,
+                                                            C.c_int, Costs, C.c_int, C.POINTER(C.POINTER(Match)),
+                                                            C.POINTER(C.c_int)]
+        L.orc_levenshtein_search_simd_batch.restype = C.c_int64
+        L.orc_levenshtein_search_simd_batch.argtypes = L.orc_levenshtein_search_batch.argtypes
         _lib = L
     return _lib
 
@@ -254,6 +260,38 @@ def levenshtein_simd_k_with_opts(a, b, k, costs=LEVENSHTEIN_COSTS):
 
 def hamming_simd(a, b):
     return lib().orc_hamming_simd(a, len(a), b, len(b))
+
+
+def levenshtein_search_simd_with_opts(needle, haystack, k, search_type=0, costs=LEVENSHTEIN_COSTS, anchored=False):
+    """([(start, end, k), ...], covered) from the restatement of the reference's AVX2 search core"""
+    mp, cov = C.POINTER(Match)(), C.c_int(0)
+    n = lib().orc_levenshtein_search_simd_with_opts(needle, len(needle), haystack, len(haystack), k, search_type,
+                                                    Costs(*costs), int(anchored), C.byref(mp), C.byref(cov))
+    if n < 0:
+        raise AssertionError("check_search failed (reference panics, src/levenshtein.rs:69)")
+    out = [(mp[i].start, mp[i].end, mp[i].k) for i in range(n)]
+    if mp:
+        lib().orc_free(mp)
+    return out, bool(cov.value)
+
+
+def levenshtein_search_simd_batch(needle, hay, hay_off, k, search_type=0, costs=LEVENSHTEIN_COSTS, anchored=False,
+                                  threads=1):
+    n = len(hay_off) - 1
+    mp = C.POINTER(Match)()
+    moff = np.zeros(n + 1, np.uint64)
+    total = lib().orc_levenshtein_search_simd_batch(bytes(needle), len(needle), _p(hay), _p(hay_off), n, k, search_type,
+                                                    Costs(*costs), int(anchored), C.byref(mp), _p(moff), threads)
+    if total < 0:
+        raise AssertionError("check_search failed")
+    arr = np.zeros((total, 3), np.uint64)
+    if total:
+        raw = np.ctypeslib.as_array(C.cast(mp, C.POINTER(C.c_uint64)), shape=(total, 3)).copy()
+        arr[:, 0], arr[:, 1] = raw[:, 0], raw[:, 1]
+        arr[:, 2] = raw[:, 2] & 0xFFFFFFFF
+    if mp:
+        lib().orc_free(mp)
+    return arr, moff
 
 
 def levenshtein_simd_k_batch(a, a_off, b, b_off, k, costs=LEVENSHTEIN_COSTS, threads=1):

@@ -99,3 +99,50 @@ def test_simd_equals_scalar_without_transpositions(costs):
     got = orc.levenshtein_simd_exp_batch(a, ao, b, bo, costs, threads=4)
     want = orc.levenshtein_exp_batch(a, ao, b, bo, costs, threads=4)
     assert np.array_equal(got, want)
+
+
+def test_search_simd_kats():
+    """every SIMD-named search KAT of the reference (tests/basic_tests.rs:683-815 and the doc-tests)"""
+    n = 0
+    for r in KAT:
+        if r["fn"] not in ("levenshtein_search_simd_with_opts", "levenshtein_search_simd", "levenshtein_search"):
+            continue
+        needle, hay = _b(r["a"]), _b(r["b"])
+        if "k" in r:
+            got, covered = orc.levenshtein_search_simd_with_opts(needle, hay, r["k"], r["search_type"],
+                                                                 tuple(r["costs"]), r["anchored"])
+        else:
+            got, covered = orc.levenshtein_search_simd_with_opts(needle, hay, orc.search_default_k(len(needle)), 1)
+        if r["expect"].get("first_only"):
+            got = got[:1]
+        assert got == [(m["start"], m["end"], m["k"]) for m in r["expect"]["matches"]], r["src"]
+        assert covered or len(needle) == 0 or len(needle) > 32
+        n += 1
+    assert n >= 24
+
+
+@pytest.mark.parametrize("costs", [(1, 1, 0, 0), (2, 1, 1, 0)], ids=str)
+def test_search_simd_agrees_with_scalar_on_ends_and_costs(costs):
+    """On random inputs the SIMD search must report the same (end, k) pairs as the scalar routine (All mode); the
+    `start` of a match may differ in rare length ties, which is why this is a baseline and not the
+    parity oracle -- the share of differing starts is bounded here."""
+    rng = random.Random(11)
+    total = diff_start = 0
+    for _ in range(300):
+        alpha = rng.choice([3, 4, 20, 255])
+        nlen = rng.randrange(1, 33)
+        needle = bytes(1 + rng.randrange(alpha) for _ in range(nlen))
+        hay = bytearray(1 + rng.randrange(alpha) for _ in range(rng.randrange(0, 300)))
+        if len(hay) > nlen and rng.random() < 0.7:
+            p = rng.randrange(len(hay) - nlen)
+            hay[p:p + nlen] = needle
+        k = rng.randrange(0, max(1, nlen // 2) + 1)
+        got, covered = orc.levenshtein_search_simd_with_opts(needle, bytes(hay), k, 0, costs)
+        # (the scalar routine also reports the empty match at end 0 when needle_len * gap + start_gap <= k,
+        #  src/levenshtein.rs:1686-1707; the SIMD core never looks at end 0)
+        want = [m for m in orc.levenshtein_search_naive_with_opts(needle, bytes(hay), k, 0, costs) if m[1] > 0]
+        assert covered
+        assert [(e, c) for _, e, c in got] == [(e, c) for _, e, c in want], (needle, bytes(hay), k)
+        total += len(want)
+        diff_start += sum(1 for g, w in zip(got, want) if g[0] != w[0])
+    assert total > 500 and diff_start <= total * 0.05, (total, diff_start)
