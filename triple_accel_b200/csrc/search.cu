@@ -423,6 +423,7 @@ static int search_device(ta_ctx *ctx, cudaStream_t st, const uint8_t *d_needle, 
                          const uint8_t *d_hay, const uint64_t *d_off, size_t n, uint64_t max_hay, uint32_t k,
                          ta_costs costs, int anchored, std::vector<Hit> &hits) {
     int rc;
+    if (max_hay > 0xFFFFFFF0ull) return TA_ERR_TOO_LARGE;  // hit records carry 32-bit end positions and lengths
     constexpr size_t SPEC_HITS = 16384;  // hits copied back speculatively with the counters (384 KB, pinned)
     const bool unit = costs.mismatch == 1 && costs.gap == 1 && costs.start_gap == 0 && costs.transpose <= 1;
     const uint32_t *d_idx = nullptr;
