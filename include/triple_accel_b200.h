@@ -133,7 +133,8 @@ int ta_levenshtein_exp_batch(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_of
  * (src/levenshtein.rs:1911-2155), bit-exact with levenshtein_search_naive_with_opts (src/levenshtein.rs:1589-1838)
  * for every haystack of the batch.  *out_matches receives all matches, haystack by haystack, in the order the
  * reference iterator yields them; matches of haystack i are (*out_matches)[(*out_match_off)[i] ..
- * (*out_match_off)[i+1]).  Both arrays are malloc'd by the library: release with ta_free.
+ * (*out_match_off)[i+1]).  Both arrays are allocated by the library: release with ta_free.  The needle is limited
+ * to TA_MAX_STRING_LEN bytes, a haystack to 2^32 - 16 bytes (TA_ERR_TOO_LARGE beyond).
  * levenshtein_search(needle, haystack) (src/levenshtein.rs:2508-2513) is k = ta_search_default_k(needle_len),
  * TA_SEARCH_BEST, unit costs, anchored = 0. */
 int ta_levenshtein_search_batch(ta_ctx *ctx, const uint8_t *needle, size_t needle_len, const uint8_t *hay,
