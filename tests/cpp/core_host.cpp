@@ -1,6 +1,6 @@
 // Host-side differential test of the per-pair bit-parallel cores (triple_accel_b200/csrc/lev_bitpar_core.cuh is
 // host/device code) against the scalar oracle.  Test infrastructure: built and run by tests/test_core_host.py.
-// usage: core_host <iterations> <seed>
+// usage: core_host <iterations> <seed> [longest string, default 300]
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -39,13 +39,14 @@ static uint32_t run_blk(const uint8_t *a, int la, const uint8_t *b, int lb, uint
 int main(int argc, char **argv) {
     const int iters = argc > 1 ? atoi(argv[1]) : 100000;
     std::mt19937_64 rng(argc > 2 ? atoll(argv[2]) : 12345);
+    const int long_len = argc > 3 ? atoi(argv[3]) : 300;
     std::vector<uint8_t> arena(1 << 16);  // strings live at base + {0, 1024, 4096, 6144} + small offsets
     uint8_t *base = (uint8_t *)(((uintptr_t)arena.data() + 4096) & ~(uintptr_t)15);
     long tests = 0, duo_tests = 0;
     for (int it = 0; it < iters; it++) {
         const int alphas[5] = {2, 3, 4, 26, 256};
         const int alpha = alphas[rng() % 5];
-        const int maxlen = it % 3 == 0 ? 300 : 40;
+        const int maxlen = it % 3 == 0 ? long_len : 40;
         int la = (int)(rng() % maxlen), lb;
         const int mode = (int)(rng() % 3);
         const size_t offa = rng() % 64, offb = 1024 + rng() % 64;
