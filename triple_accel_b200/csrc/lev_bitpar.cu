@@ -190,6 +190,58 @@ __global__ void __launch_bounds__(128, 3) lev_bitpar_duo_kernel(const uint8_t *_
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Length bucketing (experimental, TA_LEN_BUCKETS=1): a counting sort of the pair indices by (longer length) / 16, so
+// that neighbouring work items have the same number of 16-column supersteps -- pairs can then share a thread in the
+// duo kernel and the lanes of a warp finish together -- handed to the distance kernels as the index indirection they
+// already take for the exponential rounds.  Three small launches; off by default until measured.
+__device__ __forceinline__ uint32_t len_class(const uint64_t *__restrict__ a_off, const uint64_t *__restrict__ b_off, size_t i) {
+    const uint64_t la = a_off[i + 1] - a_off[i], lb = b_off[i + 1] - b_off[i];
+    const uint64_t c = (la > lb ? la : lb) >> 4;
+    return c < 255 ? (uint32_t)c : 255u;
+}
+__global__ void __launch_bounds__(256) len_hist_kernel(const uint64_t *__restrict__ a_off, const uint64_t *__restrict__ b_off,
+                                                       size_t n, uint32_t *__restrict__ hist) {
+    __shared__ uint32_t sh[256];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        atomicAdd(&sh[len_class(a_off, b_off, i)], 1u);
+    __syncthreads();
+    if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+__global__ void len_scan_kernel(const uint32_t *__restrict__ hist, uint32_t *__restrict__ pos) {
+    if (threadIdx.x == 0) {
+        uint32_t sum = 0;
+        for (int c = 0; c < 256; c++) {
+            pos[c] = sum;
+            sum += hist[c];
+        }
+    }
+}
+__global__ void __launch_bounds__(256) len_scatter_kernel(const uint64_t *__restrict__ a_off,
+                                                          const uint64_t *__restrict__ b_off, size_t n,
+                                                          uint32_t *__restrict__ pos, uint32_t *__restrict__ idx) {
+    __shared__ uint32_t cnt[256], base[256];
+    // each pass of the block places blockDim.x pairs: count per class, reserve a global range per class, then place
+    for (size_t i0 = (size_t)blockIdx.x * blockDim.x; i0 < n; i0 += (size_t)gridDim.x * blockDim.x) {
+        cnt[threadIdx.x] = 0;
+        __syncthreads();
+        const size_t i = i0 + threadIdx.x;
+        uint32_t c = 0, rank = 0;
+        if (i < n) {
+            c = len_class(a_off, b_off, i);
+            rank = atomicAdd(&cnt[c], 1u);
+        }
+        __syncthreads();
+        if (cnt[threadIdx.x]) base[threadIdx.x] = atomicAdd(&pos[threadIdx.x], cnt[threadIdx.x]);
+        __syncthreads();
+        if (i < n) idx[base[c] + rank] = (uint32_t)i;
+        __syncthreads();
+    }
+}
+
 typedef void (*lev_kern_t)(const uint8_t *, const uint64_t *, const uint8_t *, const uint64_t *, const uint32_t *,
                            size_t, uint32_t, uint32_t *);
 template <bool TRANS, int C>
@@ -217,6 +269,21 @@ int ta_launch_lev_bitpar(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, c
                          const uint64_t *b_off, size_t n, const uint32_t *idx, uint32_t k, ta_costs costs,
                          uint32_t max_len, uint32_t *out, cudaStream_t st) {
     if (n == 0) return TA_OK;
+    static const int len_buckets = getenv("TA_LEN_BUCKETS") ? atoi(getenv("TA_LEN_BUCKETS")) : 0;
+    if (len_buckets && idx == nullptr && n >= 4096 && n < 0xFFFFFFF0ull) {
+        int rc;
+        if ((rc = ta_dev_reserve(ctx, ctx->d_work[2], n * sizeof(uint32_t))) != TA_OK) return rc;
+        if ((rc = ta_dev_reserve(ctx, ctx->d_work[3], 512 * sizeof(uint32_t))) != TA_OK) return rc;
+        uint32_t *hist = (uint32_t *)ctx->d_work[3].p, *pos = hist + 256, *perm = (uint32_t *)ctx->d_work[2].p;
+        TA_CUDA(ctx, cudaMemsetAsync(hist, 0, 256 * sizeof(uint32_t), st));
+        const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 8);
+        len_hist_kernel<<<blocks, 256, 0, st>>>(a_off, b_off, n, hist);
+        len_scan_kernel<<<1, 32, 0, st>>>(hist, pos);
+        len_scatter_kernel<<<blocks, 256, 0, st>>>(a_off, b_off, n, pos, perm);
+        ctx->launches += 3;
+        TA_CUDA(ctx, cudaGetLastError());
+        idx = perm;
+    }
     // Implementations of the same per-pair contract: the match-table kernel (default; 32-row window, or 64-row window
     // for 32 <= k <= 63) and the register-only SWAR-compare kernel (32 rows).  TA_BITPAR=simd|tab, TA_BITPAR_PLANES and
     // TA_BITPAR_THREADS force variants (the tests pin every one of them to the oracle).
