@@ -611,6 +611,7 @@ SEARCH_TESTS = ("test_search_random or test_search_planted or test_kat_search or
     ({"TA_BITPAR": "tab"}, LEV_TESTS),
     ({"TA_BITPAR": "tab", "TA_BITPAR_BITS": "32"}, LEV_TESTS),
     ({"TA_BLK_DUO": "0", "TA_EXP_FIRST_K": "30"}, LEV_TESTS),
+    ({"TA_LEN_BUCKETS": "1"}, LEV_TESTS + " or test_full_size"),
     ({"TA_BLK_PLANES": "0"}, LEV_TESTS),
     ({"TA_BLK_PLANES": "1", "TA_BLK_C": "8"}, LEV_TESTS),
     ({"TA_BLK_PLANES": "0", "TA_BLK_C": "8", "TA_BITPAR_THREADS": "64"}, LEV_TESTS),
@@ -622,7 +623,7 @@ SEARCH_TESTS = ("test_search_random or test_search_planted or test_kat_search or
     ({"TA_SEARCH_FILTER": "pigeon"}, SEARCH_TESTS),
     ({"TA_SEARCH_FILTER": "pigeon", "TA_PIGEON_STAGED": "0"}, SEARCH_TESTS),
 ], ids=["general-band-kernel", "bitpar-simd-kernel", "bitpar-sliding-table-kernel",
-        "bitpar-sliding-table-32bit-on-narrow-bands", "bitpar-block-table-one-pair-per-thread", "bitpar-block-table-256-entries",
+        "bitpar-sliding-table-32bit-on-narrow-bands", "bitpar-block-table-one-pair-per-thread", "length-bucketing-pre-pass", "bitpar-block-table-256-entries",
         "bitpar-block-table-8-blocks", "bitpar-block-table-256-entries-8-blocks",
         "bitpar-table-2plane-kernel", "search-thread-kernel-nofilter", "search-wave-kernel-nofilter",
         "search-thread-kernel-filter", "search-myers-filter-forced", "search-pigeonhole-filter-forced",
