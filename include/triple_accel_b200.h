@@ -10,8 +10,9 @@
  * Batch layout ("CSR"): a batch of n byte strings is one contiguous byte buffer plus n+1 u64 offsets;
  * string i is bytes[off[i] .. off[i+1]).  Pair i is (a_i, b_i).
  *
- * Threading: a ta_ctx owns one CUDA device, its streams and staging buffers; calls on one ctx are serialised by
- * an internal mutex.  Use one ctx per thread (or per process, one process per GPU) for concurrency.
+ * Threading: a ta_ctx owns one CUDA device (ta_init) or several (ta_init_multi), their streams and staging buffers;
+ * calls on one ctx are serialised by an internal mutex, any number of threads may share a ctx, and distinct contexts
+ * run concurrently (also on the same device).  The reference's functions are pure and re-entrant; so are these.
  *
  * Errors: 0 = success; negative = error (ta_strerror).  Contract violations that the reference turns into
  * panics are reported as error codes (the Rust shim panics on them):  TA_ERR_LEN_MISMATCH <-> assert at
@@ -29,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TA_ABI_VERSION 1
+#define TA_ABI_VERSION 2
 
 /* Option::None for a distance (Option<u32> in src/levenshtein.rs:342, 677, 714-720) */
 #define TA_NONE 0xFFFFFFFFu
@@ -79,6 +80,18 @@ typedef struct ta_ctx ta_ctx;
 int ta_abi_version(void);
 /* Create a context on CUDA device `device` (one context per GPU; one process per GPU in multi-GPU runs). */
 int ta_init(int device, ta_ctx **out);
+/* Create ONE context over `n_devices` distinct CUDA devices of this box.  Every host-buffer batch entry
+ * point below then splits its batch into contiguous ranges of pairs / haystacks balanced by bytes, runs each range on
+ * its own device (own streams, staging buffers and host thread) and writes the results into the caller's arrays in
+ * batch order: same results as a single-device context, no data-path collective.  The needle of
+ * ta_levenshtein_search_batch is uploaded to the first device and sent to the others with ncclBroadcast over a
+ * single-process communicator (libnccl.so.2 is loaded at run time; without it the needle is copied per device, see
+ * ta_multi_uses_nccl).  Batches below ~4 MB per device use fewer devices.  The *_dev entry points take pointers that
+ * live on one device and therefore return TA_ERR_BAD_ARG on a multi-device context.  n_devices == 1 is ta_init. */
+int ta_init_multi(const int *devices, int n_devices, ta_ctx **out);
+int ta_device_count(ta_ctx *ctx);               /* devices this ctx spans */
+int ta_multi_uses_nccl(ta_ctx *ctx);            /* 1 = needle travels by ncclBroadcast */
+uint64_t ta_multi_needle_broadcasts(ta_ctx *ctx); /* ncclBroadcast calls issued so far */
 void ta_shutdown(ta_ctx *ctx);
 const char *ta_strerror(int code);
 const char *ta_last_error(ta_ctx *ctx); /* text of the last CUDA error seen by this ctx */
@@ -93,6 +106,8 @@ void ta_host_free(void *p);
  * pointers (NULL is ignored): the blocks carry a small header and large ones are parked for reuse by the next call
  * instead of going back to the system allocator. */
 void ta_free(void *p);
+/* Returns the parked blocks of ta_free to the system allocator (at most six blocks of <= 64 MB are ever parked). */
+void ta_trim(void);
 
 /* EditCosts::new validity (src/levenshtein.rs:38-60) / check_search (src/levenshtein.rs:67-71): 1 = valid */
 int ta_costs_valid(ta_costs c);

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_strerror():
     lib = _ffi.load()
-    assert lib.ta_abi_version() == 1
+    assert lib.ta_abi_version() == 2
     assert lib.ta_strerror(0) == b"ok"
     assert b"length" in lib.ta_strerror(_ffi.TA_ERR_LEN_MISMATCH)
 

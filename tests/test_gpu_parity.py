@@ -274,6 +274,43 @@ def test_lev_k_mutated(eng, length, k, costs):
     assert np.array_equal(got2, want)
 
 
+@pytest.mark.parametrize("costs", [(1, 1, 0, 0), (1, 1, 0, 1)], ids=str)
+@pytest.mark.parametrize("alpha", [2, 4, 256])
+def test_lev_fr_long_strings(eng, costs, alpha):
+    """long strings, small k: the dispatcher's diagonal-extension kernel (lev_fr.cu).  Small alphabets and periodic
+    strings make many diagonals slide far (every lane of an octet queues a cooperative slide); ragged lengths and
+    offsets exercise every 16-byte re-alignment of the two streams; swapped arguments, None and length-difference
+    exits included."""
+    rng = random.Random(alpha * 7 + costs[3])
+    A, B = [], []
+    for i in range(260):
+        la = rng.choice((1024, 1500, 2048, 4096)) + rng.randrange(0, 40)
+        if i % 5 == 4:  # periodic: every diagonal that is a multiple of the period matches for ever
+            unit = bytes(rng.randrange(alpha) for _ in range(rng.choice((1, 2, 3, 7, 16))))
+            s = (unit * (la // len(unit) + 1))[:la]
+        else:
+            s = bytes(rng.randrange(alpha) for _ in range(la))
+        r = rng.random()
+        if r < 0.75:
+            t = _mutate(rng, s, rng.randrange(0, 20), alpha)
+        elif r < 0.85:
+            t = s
+        else:
+            t = bytes(rng.randrange(alpha) for _ in range(la + rng.randrange(-5, 6)))
+        A.append(s)
+        B.append(t)
+    a, ao = _pack(A)
+    b, bo = _pack(B)
+    for k in (0, 3, 8, 16):
+        want = orc.levenshtein_k_batch(a, ao, b, bo, k, costs, threads=8)
+        got = eng.levenshtein_k_batch(a, ao, b, bo, k, costs)
+        bad = np.nonzero(got != want)[0]
+        assert len(bad) == 0, (k, len(bad), int(bad[0]), int(got[bad[0]]), int(want[bad[0]]))
+        assert np.array_equal(eng.levenshtein_k_batch(b, bo, a, ao, k, costs), want)
+    assert np.array_equal(eng.levenshtein_exp_batch(a, ao, b, bo, costs),
+                          orc.levenshtein_exp_batch(a, ao, b, bo, costs, threads=8))
+
+
 @pytest.mark.parametrize("costs", [(1, 1, 0, 0), (1, 1, 0, 1), (1, 1, 2, 0), (3, 2, 0, 2)], ids=str)
 def test_lev_full_matrix(eng, costs):
     """levenshtein() / rdamerau(): k = u32::MAX, the band is the whole matrix"""
@@ -601,12 +638,15 @@ def test_cpp_header_mirror(tmp_path):
 
 
 LEV_TESTS = "test_lev_k_mutated or test_lev_k_random_short or test_nul_bytes or test_lev_exp"
+FR_TESTS = LEV_TESTS + " or test_lev_fr_long_strings or test_lev_full_matrix"
 SEARCH_TESTS = ("test_search_random or test_search_planted or test_kat_search or "
                 "test_search_filter_long_needles_and_transpositions or test_search_segment_warmup")
 
 
 @pytest.mark.parametrize("env,select", [
     ({"TA_FORCE_BAND": "1"}, LEV_TESTS),
+    ({"TA_FR": "1"}, FR_TESTS),
+    ({"TA_FR": "0"}, "test_lev_fr_long_strings"),
     ({"TA_BITPAR": "simd"}, LEV_TESTS),
     ({"TA_BITPAR": "tab"}, LEV_TESTS),
     ({"TA_BITPAR": "tab", "TA_BITPAR_BITS": "32"}, LEV_TESTS),
@@ -622,7 +662,7 @@ SEARCH_TESTS = ("test_search_random or test_search_planted or test_kat_search or
     ({"TA_SEARCH_FILTER": "myers"}, SEARCH_TESTS),
     ({"TA_SEARCH_FILTER": "pigeon"}, SEARCH_TESTS),
     ({"TA_SEARCH_FILTER": "pigeon", "TA_PIGEON_STAGED": "0"}, SEARCH_TESTS),
-], ids=["general-band-kernel", "bitpar-simd-kernel", "bitpar-sliding-table-kernel",
+], ids=["general-band-kernel", "diagonal-extension-kernel-forced", "diagonal-extension-kernel-off", "bitpar-simd-kernel", "bitpar-sliding-table-kernel",
         "bitpar-sliding-table-32bit-on-narrow-bands", "bitpar-block-table-one-pair-per-thread", "length-bucketing-pre-pass", "bitpar-block-table-256-entries",
         "bitpar-block-table-8-blocks", "bitpar-block-table-256-entries-8-blocks",
         "bitpar-table-2plane-kernel", "search-thread-kernel-nofilter", "search-wave-kernel-nofilter",

@@ -39,6 +39,11 @@ _vp, _sz, _u32, _int = C.c_void_p, C.c_size_t, C.c_uint32, C.c_int
 SIGNATURES = {
     "ta_abi_version": (_int, []),
     "ta_init": (_int, [_int, C.POINTER(_vp)]),
+    "ta_init_multi": (_int, [C.POINTER(_int), _int, C.POINTER(_vp)]),
+    "ta_device_count": (_int, [_vp]),
+    "ta_multi_uses_nccl": (_int, [_vp]),
+    "ta_multi_needle_broadcasts": (C.c_uint64, [_vp]),
+    "ta_trim": (None, []),
     "ta_shutdown": (None, [_vp]),
     "ta_strerror": (C.c_char_p, [_int]),
     "ta_last_error": (C.c_char_p, [_vp]),

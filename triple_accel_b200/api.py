@@ -105,19 +105,48 @@ def _ptr(x):
     return x.ctypes.data_as(C.c_void_p)
 
 
-class Engine:
-    """One ta_ctx: one CUDA device, its streams and staging buffers."""
+def _k32(k):
+    """k is a u32 in the crate; larger Python ints saturate (they mean "unbounded"), negatives are an error"""
+    k = int(k)
+    if k < 0:
+        raise OverflowError("k is a u32")
+    return min(k, 0xFFFFFFFF)
 
-    def __init__(self, device=None):
+
+class Engine:
+    """One ta_ctx: one CUDA device (Engine(0)) or several (Engine(devices=[0, 1, ...]): every host-buffer batch call
+    is split across them inside the library, see ta_init_multi), its streams and staging buffers."""
+
+    def __init__(self, device=None, devices=None):
         self._lib = _ffi.load()
+        h = C.c_void_p()
+        if devices is not None and len(devices) != 1:
+            devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+            rc = self._lib.ta_init_multi(devs, len(devices), C.byref(h))
+            if rc != 0:
+                raise TripleAccelError(rc, "ta_init_multi(%r) failed; this library has no CPU fallback" % (list(devices),))
+            self._h = h
+            self.device = int(devices[0])
+            self.devices = [int(d) for d in devices]
+            return
+        if devices is not None:
+            device = devices[0]
         if device is None:
             device = int(os.environ.get("LOCAL_RANK", "0"))
-        h = C.c_void_p()
         rc = self._lib.ta_init(int(device), C.byref(h))
         if rc != 0:
             raise TripleAccelError(rc, "ta_init(device=%d) failed; this library has no CPU fallback" % device)
         self._h = h
         self.device = int(device)
+        self.devices = [int(device)]
+
+    @property
+    def uses_nccl(self):
+        return bool(self._lib.ta_multi_uses_nccl(self._h))
+
+    @property
+    def needle_broadcasts(self):
+        return int(self._lib.ta_multi_needle_broadcasts(self._h))
 
     def close(self):
         if getattr(self, "_h", None):
@@ -160,7 +189,7 @@ class Engine:
         n = len(a_off) - 1
         out = np.empty(n, np.uint32) if out is None else out
         self._check(self._lib.ta_levenshtein_k_batch(self._h, _ptr(a), _ptr(a_off), _ptr(b), _ptr(b_off), n,
-                                                     int(k) & 0xFFFFFFFF, _as_costs(costs)._c(), _ptr(out)))
+                                                     _k32(k), _as_costs(costs)._c(), _ptr(out)))
         return out
 
     def levenshtein_exp_batch(self, a, a_off, b, b_off, costs=LEVENSHTEIN_COSTS, out=None):
@@ -189,7 +218,7 @@ class Engine:
 
     def levenshtein_k_trace_batch(self, a, a_off, b, b_off, k, costs=LEVENSHTEIN_COSTS):
         """trace_on = true for a batch: (dist[n], edits[total, 2] = (EditType, count), edit_off[n+1])."""
-        return self._trace(self._lib.ta_levenshtein_k_trace_batch, a, a_off, b, b_off, int(k) & 0xFFFFFFFF,
+        return self._trace(self._lib.ta_levenshtein_k_trace_batch, a, a_off, b, b_off, _k32(k),
                            _as_costs(costs)._c())
 
     def levenshtein_exp_trace_batch(self, a, a_off, b, b_off, costs=LEVENSHTEIN_COSTS):
@@ -202,7 +231,7 @@ class Engine:
         n = len(hay_off) - 1
         mp, op = C.POINTER(ta_match)(), C.POINTER(C.c_uint64)()
         rc = self._lib.ta_levenshtein_search_batch(self._h, _ptr(needle), len(needle), _ptr(hay), _ptr(hay_off), n,
-                                                   int(k) & 0xFFFFFFFF, int(search_type), _as_costs(costs)._c(),
+                                                   _k32(k), int(search_type), _as_costs(costs)._c(),
                                                    int(bool(anchored)), C.byref(mp), C.byref(op))
         self._check(rc)
         return self._take_matches(mp, op, n)
@@ -213,7 +242,7 @@ class Engine:
         n = len(hay_off) - 1
         mp, op = C.POINTER(ta_match)(), C.POINTER(C.c_uint64)()
         rc = self._lib.ta_hamming_search_batch(self._h, _ptr(needle), len(needle), _ptr(hay), _ptr(hay_off), n,
-                                               int(k) & 0xFFFFFFFF, int(search_type), C.byref(mp), C.byref(op))
+                                               _k32(k), int(search_type), C.byref(mp), C.byref(op))
         self._check(rc)
         return self._take_matches(mp, op, n)
 
@@ -260,7 +289,7 @@ class Engine:
     def levenshtein_k_batch_dev(self, a, a_off, b, b_off, k, costs, max_len, out, stream=None):
         n = a_off.numel() - 1
         self._check(self._lib.ta_levenshtein_k_batch_dev(self._h, a.data_ptr(), a_off.data_ptr(), b.data_ptr(),
-                                                         b_off.data_ptr(), n, int(k) & 0xFFFFFFFF,
+                                                         b_off.data_ptr(), n, _k32(k),
                                                          _as_costs(costs)._c(), int(max_len), out.data_ptr(),
                                                          self._stream(stream)))
         return out
@@ -278,7 +307,7 @@ class Engine:
         n = hay_off.numel() - 1
         mp, op = C.POINTER(ta_match)(), C.POINTER(C.c_uint64)()
         rc = self._lib.ta_levenshtein_search_batch_dev(self._h, _ptr(needle), len(needle), hay.data_ptr(),
-                                                       hay_off.data_ptr(), n, int(max_hay_len), int(k) & 0xFFFFFFFF,
+                                                       hay_off.data_ptr(), n, int(max_hay_len), _k32(k),
                                                        int(search_type), _as_costs(costs)._c(), int(bool(anchored)),
                                                        C.byref(mp), C.byref(op), self._stream(stream))
         self._check(rc)
@@ -303,7 +332,7 @@ class Engine:
             d, ed, _ = self.levenshtein_k_trace_batch(ab, ao, bb, bo, k, costs)
             return None if d[0] == TA_NONE else (int(d[0]), [Edit(int(e), int(c)) for e, c in ed])
         out = C.c_uint32()
-        self._check(self._lib.ta_levenshtein_simd_k_with_opts(self._h, a, len(a), b, len(b), int(k) & 0xFFFFFFFF,
+        self._check(self._lib.ta_levenshtein_simd_k_with_opts(self._h, a, len(a), b, len(b), _k32(k),
                                                               _as_costs(costs)._c(), C.byref(out)))
         return None if out.value == TA_NONE else (out.value, None)
 

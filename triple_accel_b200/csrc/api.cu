@@ -25,6 +25,8 @@ int ta_launch_lev(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const ui
                   size_t n, const uint32_t *idx, uint32_t k, ta_costs costs, uint32_t max_len, uint32_t *out,
                   cudaStream_t st) {
     static const bool force_band = getenv("TA_FORCE_BAND") != nullptr;  // testing: exercise the general kernel
+    if (!force_band && ta_fr_preferred(k, costs, max_len))  // long strings, small k: diagonal extension (lev_fr.cu)
+        return ta_launch_lev_fr(ctx, a, a_off, b, b_off, n, idx, k, costs, max_len, out, st);
     if (!force_band && ta_bitpar_can_handle(k, costs, max_len))
         return ta_launch_lev_bitpar(ctx, a, a_off, b, b_off, n, idx, k, costs, max_len, out, st);
     return ta_launch_lev_band(ctx, a, a_off, b, b_off, n, idx, k, costs, max_len, out, st);
@@ -57,6 +59,8 @@ int ta_pin_reserve(ta_ctx *ctx, DevBuf &b, size_t bytes) {
     return TA_OK;
 }
 
+static void destroy_ctx_resources(ta_ctx *ctx);
+
 extern "C" {
 
 int ta_abi_version(void) { return TA_ABI_VERSION; }
@@ -84,6 +88,7 @@ int ta_init(int device, ta_ctx **out) {
     auto fail = [&](cudaError_t e, const char *what) {
         ta_cuda_fail(ctx, e, what);
         fprintf(stderr, "triple_accel_b200: %s\n", ctx->last_error.c_str());
+        destroy_ctx_resources(ctx);  // whatever was created before the failure
         delete ctx;
         return TA_ERR_CUDA;
     };
@@ -92,6 +97,7 @@ int ta_init(int device, ta_ctx **out) {
     if ((e = cudaGetDeviceCount(&count)) != cudaSuccess) return fail(e, "cudaGetDeviceCount");
     if (device < 0 || device >= count) return fail(cudaErrorInvalidDevice, "ta_init(device)");
     if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(e, "cudaSetDevice");
+    if ((e = cudaFree(0)) != cudaSuccess) return fail(e, "cudaFree(0): no usable CUDA context");
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(e, "cudaGetDeviceProperties");
     ctx->sm_count = prop.multiProcessorCount;
@@ -110,8 +116,20 @@ int ta_init(int device, ta_ctx **out) {
 
 void ta_shutdown(ta_ctx *ctx) {
     if (!ctx) return;
+    if (ctx->multi) {  // a multi-device ctx owns sub-contexts, worker threads and the NCCL communicator only
+        ta_multi_shutdown(ctx);
+        delete ctx;
+        return;
+    }
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    destroy_ctx_resources(ctx);
+    delete ctx;
+}
+
+}  // extern "C"
+
+static void destroy_ctx_resources(ta_ctx *ctx) {
     DevBuf *dev[] = {&ctx->d_a[0], &ctx->d_a[1], &ctx->d_b[0], &ctx->d_b[1], &ctx->d_aoff[0], &ctx->d_aoff[1],
                      &ctx->d_boff[0], &ctx->d_boff[1], &ctx->d_out[0], &ctx->d_out[1], &ctx->d_work[0],
                      &ctx->d_work[1], &ctx->d_work[2], &ctx->d_work[3]};
@@ -125,8 +143,10 @@ void ta_shutdown(ta_ctx *ctx) {
         if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
-    delete ctx;
+    (void)cudaGetLastError();
 }
+
+extern "C" {
 
 const char *ta_last_error(ta_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
 int ta_device(ta_ctx *ctx) { return ctx ? ctx->device : -1; }
@@ -151,7 +171,9 @@ struct OutHdr {
     uint64_t magic, cap;
 };
 constexpr uint64_t OUT_MAGIC = 0x74615f6f75745f31ull;
+constexpr uint64_t OUT_PARKED = 0x74615f7061726b31ull;  // in the cache: a second ta_free of it is ignored
 constexpr int OUT_SLOTS = 6;
+constexpr uint64_t OUT_MAX_PARKED = 64ull << 20;  // larger blocks go straight back to the allocator
 std::mutex g_out_mu;
 OutHdr *g_out_cache[OUT_SLOTS] = {};
 }  // namespace
@@ -164,6 +186,7 @@ void *ta_out_alloc(size_t bytes) {
             OutHdr *h = g_out_cache[i];
             if (h && h->cap >= bytes && h->cap <= 2 * bytes + (64u << 10)) {
                 g_out_cache[i] = nullptr;
+                h->magic = OUT_MAGIC;
                 return h + 1;
             }
         }
@@ -178,10 +201,11 @@ void *ta_out_alloc(size_t bytes) {
 void ta_free(void *p) {
     if (!p) return;
     OutHdr *h = (OutHdr *)p - 1;
-    if (h->magic != OUT_MAGIC) return;  // not a (live) pointer this library returned: leave it alone
-    if (h->cap >= (64u << 10) && h->cap <= (256u << 20)) {
+    if (h->magic != OUT_MAGIC) return;  // not a live pointer this library returned (or already freed): leave it alone
+    if (h->cap >= (64u << 10) && h->cap <= OUT_MAX_PARKED) {
         std::lock_guard<std::mutex> lock(g_out_mu);
         int victim = -1;
+        h->magic = OUT_PARKED;
         for (int i = 0; i < OUT_SLOTS; i++) {
             if (!g_out_cache[i]) {
                 g_out_cache[i] = h;
@@ -197,6 +221,17 @@ void ta_free(void *p) {
     }
     h->magic = 0;
     free(h);
+}
+
+void ta_trim(void) {  // hands the parked output blocks back to the allocator
+    std::lock_guard<std::mutex> lock(g_out_mu);
+    for (int i = 0; i < OUT_SLOTS; i++) {
+        if (g_out_cache[i]) {
+            g_out_cache[i]->magic = 0;
+            free(g_out_cache[i]);
+            g_out_cache[i] = nullptr;
+        }
+    }
 }
 
 int ta_costs_valid(ta_costs c) {  // EditCosts::new, reference src/levenshtein.rs:44-52
@@ -242,10 +277,10 @@ int scan_offsets(const uint64_t *a_off, const uint64_t *b_off, size_t n, bool ne
         mismatch |= la ^ lb;
     }
     if (bad) return TA_ERR_BAD_ARG;
-    if (max_len > TA_MAX_STRING_LEN) return TA_ERR_TOO_LARGE;
+    if (max_len > TA_MAX_STRING_LEN && !need_equal) return TA_ERR_TOO_LARGE;  // DP cells are u32; Hamming has no such limit
     st.a_bytes = a_off[n] - a_off[0];
     st.b_bytes = b_off[n] - b_off[0];
-    st.max_len = (uint32_t)max_len;
+    st.max_len = (uint32_t)std::min<uint64_t>(max_len, 0xFFFFFFFFull);
     if (need_equal && mismatch != 0) return TA_ERR_LEN_MISMATCH;
     return TA_OK;
 }
@@ -331,6 +366,19 @@ int run_pairs(ta_ctx *ctx, Op op, const uint8_t *a, const uint64_t *a_off, const
     if (!a_off || !b_off || !out) return TA_ERR_BAD_ARG;
     if (n > 0xFFFFFFF0ull) return TA_ERR_TOO_LARGE;
     std::lock_guard<std::mutex> lock(ctx->mu);
+    if (ctx->multi) {
+        // one call, several GPUs: contiguous ranges of pairs balanced by bytes, each through the
+        // single-device path of its own sub-context and host thread, results straight into the caller's slices
+        const uint64_t total = (a_off[n] - a_off[0]) + (b_off[n] - b_off[0]);
+        const int parts = ta_multi_parts(ctx, total, n);
+        std::vector<size_t> bound;
+        ta_multi_bounds(a_off, b_off, n, parts, bound);
+        return ta_multi_run(ctx, parts, [&](int r) -> int {
+            const size_t lo = bound[r], cnt = bound[r + 1] - bound[r];
+            if (cnt == 0) return TA_OK;
+            return run_pairs(ta_multi_sub(ctx, r), op, a, a_off + lo, b, b_off + lo, cnt, k, costs, out + lo);
+        });
+    }
     TA_CUDA(ctx, cudaSetDevice(ctx->device));
     // Pipeline: the batch is cut into up to MAX_CHUNKS ranges of pairs.  All H2D copies are queued on the copy stream
     // first (a range only needs its first and last offsets), the offsets are validated on the host while the DMA
@@ -509,6 +557,26 @@ int trace_batch(ta_ctx *ctx, bool exp_mode, const uint8_t *a, const uint64_t *a_
     if (rc != TA_OK) return rc;
     if (n && (!a_off || !b_off || !out_dist)) return TA_ERR_BAD_ARG;
     if (n > 0xFFFFFFF0ull) return TA_ERR_TOO_LARGE;
+    if (ctx->multi && n) {
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        const uint64_t total = (a_off[n] - a_off[0]) + (b_off[n] - b_off[0]);
+        const int parts = ta_multi_parts(ctx, total, n);
+        std::vector<size_t> bound;
+        ta_multi_bounds(a_off, b_off, n, parts, bound);
+        std::vector<ta_edit *> ed(parts, nullptr);
+        std::vector<uint64_t *> eo(parts, nullptr);
+        rc = ta_multi_run(ctx, parts, [&](int r) -> int {
+            const size_t lo = bound[r], cnt = bound[r + 1] - bound[r];
+            if (cnt == 0) return TA_OK;
+            return trace_batch(ta_multi_sub(ctx, r), exp_mode, a, a_off + lo, b, b_off + lo, cnt, k, costs,
+                               out_dist + lo, &ed[r], &eo[r]);
+        });
+        if (rc != TA_OK) {
+            for (int r = 0; r < parts; r++) ta_free(ed[r]), ta_free(eo[r]);
+            return rc;
+        }
+        return ta_concat_lists<ta_edit>(parts, bound, n, ed, eo, out_edits, out_edit_off);
+    }
     uint64_t *eoff = (uint64_t *)ta_out_alloc((n + 1) * sizeof(uint64_t));
     if (eoff) memset(eoff, 0, (n + 1) * sizeof(uint64_t));
     if (!eoff) return TA_ERR_NOMEM;
@@ -603,7 +671,7 @@ int ta_levenshtein_exp_trace_batch(ta_ctx *ctx, const uint8_t *a, const uint64_t
 
 int ta_hamming_batch_dev(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b,
                          const uint64_t *b_off, size_t n, uint32_t *out, void *stream) {
-    if (!ctx) return TA_ERR_BAD_ARG;
+    if (!ctx || ctx->multi) return TA_ERR_BAD_ARG;  // device pointers belong to one device: use a single-device ctx
     if (n == 0) return TA_OK;
     if (!a_off || !b_off || !out) return TA_ERR_BAD_ARG;
     std::lock_guard<std::mutex> lock(ctx->mu);
@@ -615,7 +683,7 @@ int ta_hamming_batch_dev(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, c
 int ta_levenshtein_k_batch_dev(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b,
                                const uint64_t *b_off, size_t n, uint32_t k, ta_costs costs, uint32_t max_len,
                                uint32_t *out, void *stream) {
-    if (!ctx) return TA_ERR_BAD_ARG;
+    if (!ctx || ctx->multi) return TA_ERR_BAD_ARG;
     int rc = check_costs(costs);
     if (rc != TA_OK) return rc;
     if (n == 0) return TA_OK;
@@ -629,7 +697,7 @@ int ta_levenshtein_k_batch_dev(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_
 int ta_levenshtein_exp_batch_dev(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b,
                                  const uint64_t *b_off, size_t n, ta_costs costs, uint32_t max_len, uint32_t *out,
                                  void *stream) {
-    if (!ctx) return TA_ERR_BAD_ARG;
+    if (!ctx || ctx->multi) return TA_ERR_BAD_ARG;
     int rc = check_costs(costs);
     if (rc != TA_OK) return rc;
     if (n == 0) return TA_OK;
@@ -641,7 +709,7 @@ int ta_levenshtein_exp_batch_dev(ta_ctx *ctx, const uint8_t *a, const uint64_t *
 }
 
 int ta_dev_status(ta_ctx *ctx, void *stream) {
-    if (!ctx) return TA_ERR_BAD_ARG;
+    if (!ctx || ctx->multi) return TA_ERR_BAD_ARG;
     std::lock_guard<std::mutex> lock(ctx->mu);
     TA_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;

@@ -76,6 +76,25 @@ extern "C" int ta_hamming_search_batch(ta_ctx *ctx, const uint8_t *needle, size_
     }
     if (n) total_hay = hay_off[n] - hay_off[0];
     if (total_hay && !hay) return TA_ERR_BAD_ARG;
+    if (ctx->multi && n) {  // several GPUs: ranges of haystacks balanced by bytes, match lists concatenated in range order
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        const int parts = ta_multi_parts(ctx, total_hay, n);
+        std::vector<size_t> bound;
+        ta_multi_bounds(hay_off, nullptr, n, parts, bound);
+        std::vector<ta_match *> ms(parts, nullptr);
+        std::vector<uint64_t *> mo(parts, nullptr);
+        const int rc = ta_multi_run(ctx, parts, [&](int r) -> int {
+            const size_t lo = bound[r], cnt = bound[r + 1] - bound[r];
+            if (cnt == 0) return TA_OK;
+            return ta_hamming_search_batch(ta_multi_sub(ctx, r), needle, needle_len, hay, hay_off + lo, cnt, k,
+                                           search_type, &ms[r], &mo[r]);
+        });
+        if (rc != TA_OK) {
+            for (int r = 0; r < parts; r++) ta_free(ms[r]), ta_free(mo[r]);
+            return rc;
+        }
+        return ta_concat_lists<ta_match>(parts, bound, n, ms, mo, out_matches, out_match_off);
+    }
     uint64_t *moff = (uint64_t *)ta_out_alloc((n + 1) * sizeof(uint64_t));
     if (moff) memset(moff, 0, (n + 1) * sizeof(uint64_t));
     if (!moff) return TA_ERR_NOMEM;

@@ -627,6 +627,42 @@ static int export_matches(const std::vector<ta_match> &result, uint64_t *moff, t
     return TA_OK;
 }
 
+// Device + emit phases for the haystacks hay_off[0 .. n] on ONE device: uploads the haystacks (and the needle, unless
+// `needle` is null = it is already in ctx->d_b[0], put there by the multi-device broadcast), runs the kernels, and
+// fills moff[0 .. n] (moff[0] = 0 on entry) and `result` with this range's matches.  The caller holds ctx->mu.
+static int search_one_device(ta_ctx *ctx, const uint8_t *needle, size_t needle_len, const uint8_t *hay,
+                             const uint64_t *hay_off, size_t n, uint32_t k, bool best, ta_costs costs, int anchored,
+                             uint64_t *moff, std::vector<ta_match> &result) {
+    uint64_t max_hay = 0;
+    for (size_t i = 0; i < n; i++) max_hay = std::max(max_hay, hay_off[i + 1] - hay_off[i]);
+    const uint64_t total_hay = hay_off[n] - hay_off[0];
+    std::vector<Hit> hits;
+    auto run = [&]() -> int {
+        TA_CUDA(ctx, cudaSetDevice(ctx->device));
+        cudaStream_t st = ctx->stream;
+        int rc;
+        const uint64_t lo = hay_off[0];
+        const size_t skew = (size_t)(lo & 15);
+        if ((rc = ta_dev_reserve(ctx, ctx->d_a[0], skew + total_hay + 64)) != TA_OK) return rc;
+        if ((rc = ta_dev_reserve(ctx, ctx->d_aoff[0], (n + 1) * sizeof(uint64_t))) != TA_OK) return rc;
+        if (needle && (rc = ta_dev_reserve(ctx, ctx->d_b[0], needle_len + 64)) != TA_OK) return rc;
+        if (total_hay)
+            TA_CUDA(ctx, cudaMemcpyAsync((uint8_t *)ctx->d_a[0].p + skew, hay + lo, total_hay, cudaMemcpyHostToDevice, st));
+        TA_CUDA(ctx, cudaMemcpyAsync(ctx->d_aoff[0].p, hay_off, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        if (needle) TA_CUDA(ctx, cudaMemcpyAsync(ctx->d_b[0].p, needle, needle_len, cudaMemcpyHostToDevice, st));
+        return search_device(ctx, st, (const uint8_t *)ctx->d_b[0].p, needle_len,
+                             (const uint8_t *)ctx->d_a[0].p + skew - lo, (const uint64_t *)ctx->d_aoff[0].p, n, max_hay, k,
+                             costs, anchored, hits);
+    };
+    const int rc = run();
+    if (rc != TA_OK) {
+        cudaStreamSynchronize(ctx->stream);
+        return rc;
+    }
+    emit_matches(n, needle_len, k, best, costs, hits, moff, result);
+    return TA_OK;
+}
+
 extern "C" int ta_levenshtein_search_batch(ta_ctx *ctx, const uint8_t *needle, size_t needle_len, const uint8_t *hay,
                                            const uint64_t *hay_off, size_t n, uint32_t k, int search_type,
                                            ta_costs costs, int anchored, ta_match **out_matches,
@@ -680,35 +716,47 @@ extern "C" int ta_levenshtein_search_batch(ta_ctx *ctx, const uint8_t *needle, s
     }
     if (n == 0) return export_matches(result, moff, out_matches, out_match_off);
 
-    std::vector<Hit> hits;
+    if (ctx->multi) {
+        // one call, several GPUs: haystacks in contiguous ranges balanced by bytes, the needle broadcast from the first
+        // device with NCCL, per-range match lists concatenated in range order
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        const int parts = ta_multi_parts(ctx, total_hay, n);
+        std::vector<size_t> bound;
+        ta_multi_bounds(hay_off, nullptr, n, parts, bound);
+        int rc = ta_multi_needle(ctx, needle, needle_len, parts);
+        std::vector<ta_match *> ms(parts, nullptr);
+        std::vector<uint64_t *> mo(parts, nullptr);
+        if (rc == TA_OK)
+            rc = ta_multi_run(ctx, parts, [&](int r) -> int {
+                const size_t lo = bound[r], cnt = bound[r + 1] - bound[r];
+                if (cnt == 0) return TA_OK;
+                ta_ctx *sub = ta_multi_sub(ctx, r);
+                uint64_t *lm = (uint64_t *)ta_out_alloc((cnt + 1) * sizeof(uint64_t));
+                if (!lm) return TA_ERR_NOMEM;
+                lm[0] = 0;
+                std::vector<ta_match> res;
+                int rr = search_one_device(sub, nullptr, needle_len, hay, hay_off + lo, cnt, k, best, costs, anchored, lm, res);
+                if (rr != TA_OK) {
+                    ta_free(lm);
+                    return rr;
+                }
+                return export_matches(res, lm, &ms[r], &mo[r]);
+            });
+        ta_free(moff);
+        if (rc != TA_OK) {
+            for (int r = 0; r < parts; r++) ta_free(ms[r]), ta_free(mo[r]);
+            return rc;
+        }
+        return ta_concat_lists<ta_match>(parts, bound, n, ms, mo, out_matches, out_match_off);
+    }
     {
         std::lock_guard<std::mutex> lock(ctx->mu);
-        auto run = [&]() -> int {
-            TA_CUDA(ctx, cudaSetDevice(ctx->device));
-            cudaStream_t st = ctx->stream;
-            int rc;
-            const uint64_t lo = hay_off[0];
-            const size_t skew = (size_t)(lo & 15);
-            if ((rc = ta_dev_reserve(ctx, ctx->d_a[0], skew + total_hay + 64)) != TA_OK) return rc;
-            if ((rc = ta_dev_reserve(ctx, ctx->d_aoff[0], (n + 1) * sizeof(uint64_t))) != TA_OK) return rc;
-            if ((rc = ta_dev_reserve(ctx, ctx->d_b[0], needle_len + 64)) != TA_OK) return rc;
-            if (total_hay)
-                TA_CUDA(ctx, cudaMemcpyAsync((uint8_t *)ctx->d_a[0].p + skew, hay + lo, total_hay,
-                                             cudaMemcpyHostToDevice, st));
-            TA_CUDA(ctx, cudaMemcpyAsync(ctx->d_aoff[0].p, hay_off, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-            TA_CUDA(ctx, cudaMemcpyAsync(ctx->d_b[0].p, needle, needle_len, cudaMemcpyHostToDevice, st));
-            return search_device(ctx, st, (const uint8_t *)ctx->d_b[0].p, needle_len,
-                                 (const uint8_t *)ctx->d_a[0].p + skew - lo, (const uint64_t *)ctx->d_aoff[0].p, n,
-                                 max_hay, k, costs, anchored, hits);
-        };
-        const int rc = run();
+        const int rc = search_one_device(ctx, needle, needle_len, hay, hay_off, n, k, best, costs, anchored, moff, result);
         if (rc != TA_OK) {
-            cudaStreamSynchronize(ctx->stream);
             ta_free(moff);
             return rc;
         }
     }
-    emit_matches(n, needle_len, k, best, costs, hits, moff, result);
     return export_matches(result, moff, out_matches, out_match_off);
 }
 
@@ -717,7 +765,7 @@ extern "C" int ta_levenshtein_search_batch_dev(ta_ctx *ctx, const uint8_t *needl
                                                uint64_t max_hay_len, uint32_t k, int search_type, ta_costs costs,
                                                int anchored, ta_match **out_matches, uint64_t **out_match_off,
                                                void *stream) {
-    if (!ctx || !out_matches || !out_match_off) return TA_ERR_BAD_ARG;
+    if (!ctx || ctx->multi || !out_matches || !out_match_off) return TA_ERR_BAD_ARG;
     *out_matches = nullptr;
     *out_match_off = nullptr;
     if (search_type != TA_SEARCH_ALL && search_type != TA_SEARCH_BEST) return TA_ERR_BAD_ARG;

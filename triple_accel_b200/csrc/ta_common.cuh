@@ -3,9 +3,12 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
+#include <functional>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/triple_accel_b200.h"
 
@@ -33,6 +36,7 @@ struct ta_ctx {
     uint32_t *h_flags = nullptr;  // pinned mirror
     uint64_t launches = 0;
     std::string last_error;
+    struct ta_multi *multi = nullptr;  // non-null: this ctx spans several devices (multi.cu) and owns no CUDA state itself
 };
 
 // grow-only device / pinned-host buffers
@@ -41,6 +45,56 @@ int ta_pin_reserve(ta_ctx *ctx, DevBuf &b, size_t bytes);
 int ta_cuda_fail(ta_ctx *ctx, cudaError_t e, const char *what);
 // caller-owned output arrays (released with ta_free); freed blocks are cached for reuse, see api.cu
 extern "C" void *ta_out_alloc(size_t bytes);
+
+// ---- multi-device contexts (multi.cu) ----------------------------------------------------------------------------
+int ta_multi_size(ta_ctx *ctx);                                    // number of devices (1 for a plain ctx)
+ta_ctx *ta_multi_sub(ta_ctx *ctx, int r);                          // single-device sub-context r
+int ta_multi_parts(ta_ctx *ctx, uint64_t total_bytes, size_t n);   // how many shards a batch of this size is cut into
+// bound[r] .. bound[r + 1] = units of shard r, balanced by bytes (b_off may be null)
+void ta_multi_bounds(const uint64_t *a_off, const uint64_t *b_off, size_t n, int parts, std::vector<size_t> &bound);
+// fn(r) for every shard, shard 0 on the calling thread and the others on their device's worker thread; first error wins
+int ta_multi_run(ta_ctx *ctx, int parts, const std::function<int(int)> &fn);
+// needle -> ctx->d_b[0] of the first `parts` sub-contexts (ncclBroadcast from device 0 when all devices take part)
+int ta_multi_needle(ta_ctx *ctx, const uint8_t *needle, size_t needle_len, int parts);
+void ta_multi_shutdown(ta_ctx *ctx);
+
+// Concatenates per-shard (items, offsets) outputs -- shard r covers units bound[r] .. bound[r + 1] and its arrays came
+// from ta_out_alloc -- into one pair of caller-owned arrays; frees the shard arrays.
+template <typename T>
+int ta_concat_lists(int parts, const std::vector<size_t> &bound, size_t n, std::vector<T *> &items,
+                    std::vector<uint64_t *> &offs, T **out_items, uint64_t **out_off) {
+    uint64_t total = 0;
+    for (int r = 0; r < parts; r++)
+        if (offs[r]) total += offs[r][bound[r + 1] - bound[r]];
+    uint64_t *off = (uint64_t *)ta_out_alloc((n + 1) * sizeof(uint64_t));
+    T *it = (T *)ta_out_alloc((total ? total : 1) * sizeof(T));
+    int rc = (off && it) ? TA_OK : TA_ERR_NOMEM;
+    if (rc == TA_OK) {
+        uint64_t base = 0;
+        off[0] = 0;
+        for (int r = 0; r < parts; r++) {
+            const size_t cnt = bound[r + 1] - bound[r];
+            if (!offs[r]) {  // an empty shard
+                for (size_t i = 0; i < cnt; i++) off[bound[r] + i + 1] = base;
+                continue;
+            }
+            for (size_t i = 0; i < cnt; i++) off[bound[r] + i + 1] = base + offs[r][i + 1];
+            if (offs[r][cnt]) memcpy(it + base, items[r], offs[r][cnt] * sizeof(T));
+            base += offs[r][cnt];
+        }
+        *out_items = it;
+        *out_off = off;
+    } else {
+        ta_free(off);
+        ta_free(it);
+    }
+    for (int r = 0; r < parts; r++) {
+        ta_free(items[r]);
+        ta_free(offs[r]);
+    }
+    return rc;
+}
+
 
 #define TA_CUDA(ctx, call)                                        \
     do {                                                          \
@@ -63,6 +117,12 @@ bool ta_bitpar_can_handle(uint32_t k, ta_costs c, uint32_t max_len);
 int ta_launch_lev_bitpar(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b,
                          const uint64_t *b_off, size_t n, const uint32_t *idx, uint32_t k, ta_costs costs,
                          uint32_t max_len, uint32_t *out, cudaStream_t st);
+// Diagonal-extension kernel (unit costs, long strings, min(k, max_len) <= 64), lev_fr.cu
+bool ta_fr_can_handle(uint32_t k, ta_costs c, uint32_t max_len);
+bool ta_fr_preferred(uint32_t k, ta_costs c, uint32_t max_len);
+int ta_launch_lev_fr(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b, const uint64_t *b_off,
+                     size_t n, const uint32_t *idx, uint32_t k, ta_costs costs, uint32_t max_len, uint32_t *out,
+                     cudaStream_t st);
 // dispatcher: bit-parallel kernel when the cost model is unit and the band fits, else the general banded kernel
 int ta_launch_lev(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b, const uint64_t *b_off,
                   size_t n, const uint32_t *idx, uint32_t k, ta_costs costs, uint32_t max_len, uint32_t *out,

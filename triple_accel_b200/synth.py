@@ -4,7 +4,71 @@ Modelled on the reference's bench generators (benches/rand_benchmarks.rs:126-260
 bounded number of random edits), seeded with 1234 like the reference benches (benches/rand_benchmarks.rs:8).
 Everything is returned in the CSR layout of the C ABI: (bytes uint8[], offsets uint64[n+1]).
 """
+import ctypes as C
+import os
+import subprocess
+
 import numpy as np
+
+_TOOLS = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools")
+_native = None
+
+
+def native():
+    """tools/libta_synth.so (tools/ta_synth.c): every unit draws from its own splitmix64 stream keyed by (seed, global
+    unit index) -- 1 M pairs are 1 M different edit scripts, and rank r of N can make units [lo, hi) of ONE batch."""
+    global _native
+    if _native is None:
+        so, src = os.path.join(_TOOLS, "libta_synth.so"), os.path.join(_TOOLS, "ta_synth.c")
+        if not os.path.exists(so) or os.path.getmtime(src) > os.path.getmtime(so):
+            subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-pthread", "-o", so, src])
+        L = C.CDLL(so)
+        u64, u32, vp, i = C.c_uint64, C.c_uint32, C.c_void_p, C.c_int
+        L.synth_pair_lengths.restype = None
+        L.synth_pair_lengths.argtypes = [u64, u64, u64, u32, u32, u32, i, i, u32, vp, vp, i]
+        L.synth_pair_fill.restype = None
+        L.synth_pair_fill.argtypes = [u64, u64, u64, u32, u32, u32, i, i, u32, vp, vp, vp, vp, i]
+        L.synth_haystacks.restype = None
+        L.synth_haystacks.argtypes = [u64, u64, u64, u32, vp, u32, u32, u32, vp, i]
+        _native = L
+    return _native
+
+
+def _threads():
+    return max(1, min(32, len(os.sched_getaffinity(0))))
+
+
+def _vp(x):
+    return x.ctypes.data_as(C.c_void_p)
+
+
+def edited_pairs(n, len_lo, len_hi, max_edits, seed=1234, first=0, exact_edits=False, allow_swap=False, alphabet=256,
+                 threads=None):
+    """Set M, one independent edit script per pair (tools/ta_synth.c): |a| ~ U[len_lo, len_hi], b = a after
+    e ~ U[0, max_edits] (or exactly max_edits) random substitutions / insertions / deletions (/ adjacent swaps).
+    Units first .. first + n of the batch defined by `seed` (same bytes whatever n, first or the thread count)."""
+    L = native()
+    threads = threads or _threads()
+    la, lb = np.empty(n, np.uint32), np.empty(n, np.uint32)
+    args = (seed, first, n, len_lo, len_hi, max_edits, int(exact_edits), int(allow_swap), alphabet)
+    L.synth_pair_lengths(*args, _vp(la), _vp(lb), threads)
+    a_off, b_off = np.zeros(n + 1, np.uint64), np.zeros(n + 1, np.uint64)
+    np.cumsum(la, dtype=np.uint64, out=a_off[1:])
+    np.cumsum(lb, dtype=np.uint64, out=b_off[1:])
+    a, b = np.empty(int(a_off[-1]), np.uint8), np.empty(int(b_off[-1]), np.uint8)
+    L.synth_pair_fill(*args, _vp(a), _vp(a_off), _vp(b), _vp(b_off), threads)
+    return a, a_off, b, b_off
+
+
+def planted_haystacks(n, hay_len, needle, plant_frac=0.01, max_edits=3, seed=1234, first=0, threads=None):
+    """cfg 4 haystacks first .. first + n (bytes 1..255; the needle, mutated by <= max_edits edits, planted in
+    plant_frac of them), independent per haystack like edited_pairs."""
+    L = native()
+    needle = np.ascontiguousarray(needle, np.uint8)
+    hay = np.empty(n * hay_len, np.uint8)
+    L.synth_haystacks(seed, first, n, hay_len, _vp(needle), len(needle), int(round(plant_frac * 1e6)), max_edits,
+                      _vp(hay), threads or _threads())
+    return hay, fixed_offsets(n, hay_len)
 
 
 def _rng(seed):
