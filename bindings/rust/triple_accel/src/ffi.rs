@@ -1,4 +1,4 @@
-//! Raw bindings of include/triple_accel_b200.h (ABI version 1).
+//! Raw bindings of include/triple_accel_b200.h (ABI version 2).
 use std::os::raw::{c_char, c_int, c_void};
 
 #[repr(C)]
@@ -32,7 +32,13 @@ pub const TA_ERR_BAD_COSTS: c_int = -3;
 pub const TA_ERR_NUL_BYTE: c_int = -7;
 
 extern "C" {
+    pub fn ta_abi_version() -> c_int;
     pub fn ta_init(device: c_int, out: *mut *mut TaCtx) -> c_int;
+    /// one context over several GPUs: every host-buffer batch call is split inside the library
+    pub fn ta_init_multi(devices: *const c_int, n_devices: c_int, out: *mut *mut TaCtx) -> c_int;
+    pub fn ta_device_count(ctx: *mut TaCtx) -> c_int;
+    pub fn ta_multi_uses_nccl(ctx: *mut TaCtx) -> c_int;
+    pub fn ta_trim();
     pub fn ta_shutdown(ctx: *mut TaCtx);
     pub fn ta_strerror(code: c_int) -> *const c_char;
     pub fn ta_last_error(ctx: *mut TaCtx) -> *const c_char;
@@ -54,6 +60,9 @@ extern "C" {
                                        hay_off: *const u64, n: usize, k: u32, search_type: c_int, costs: TaCosts,
                                        anchored: c_int, out_matches: *mut *mut TaMatch,
                                        out_match_off: *mut *mut u64) -> c_int;
+    pub fn ta_hamming_search_naive_batch(ctx: *mut TaCtx, needle: *const u8, needle_len: usize, hay: *const u8,
+                                         hay_off: *const u64, n: usize, k: u32, search_type: c_int,
+                                         out_matches: *mut *mut TaMatch, out_match_off: *mut *mut u64) -> c_int;
     pub fn ta_hamming_search_batch(ctx: *mut TaCtx, needle: *const u8, needle_len: usize, hay: *const u8,
                                    hay_off: *const u64, n: usize, k: u32, search_type: c_int,
                                    out_matches: *mut *mut TaMatch, out_match_off: *mut *mut u64) -> c_int;

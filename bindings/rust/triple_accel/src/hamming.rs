@@ -44,16 +44,21 @@ pub fn hamming_search<'a>(needle: &'a [u8], haystack: &'a [u8]) -> Box<dyn Itera
     hamming_search_simd(needle, haystack)
 }
 
-/// reference `src/hamming.rs:96-146`.  (The scalar routine itself does not reject NUL bytes; this path does, like the
-/// crate's public entry.)
+/// reference `src/hamming.rs:96-146`: the scalar routine has no NUL-byte restriction (`ta_hamming_search_naive_batch`).
 pub fn hamming_search_naive_with_opts<'a>(needle: &'a [u8], haystack: &'a [u8], k: u32, search_type: SearchType)
     -> Box<dyn Iterator<Item = Match> + 'a> {
-    hamming_search_simd_with_opts(needle, haystack, k, search_type)
+    let off = [0u64, haystack.len() as u64];
+    let (mut m, mut mo) = (std::ptr::null_mut(), std::ptr::null_mut());
+    check(unsafe {
+        ffi::ta_hamming_search_naive_batch(ctx(), needle.as_ptr(), needle.len(), haystack.as_ptr(), off.as_ptr(), 1, k,
+                                           (search_type == SearchType::Best) as i32, &mut m, &mut mo)
+    });
+    Box::new(unsafe { take_matches(m, mo) }.into_iter())
 }
 
 /// reference `src/hamming.rs:70-72`
 pub fn hamming_search_naive<'a>(needle: &'a [u8], haystack: &'a [u8]) -> Box<dyn Iterator<Item = Match> + 'a> {
-    hamming_search_simd(needle, haystack)
+    hamming_search_naive_with_opts(needle, haystack, unsafe { ffi::ta_search_default_k(needle.len()) }, SearchType::Best)
 }
 
 /// New: the batch entry point (CSR: bytes + n + 1 offsets per side).

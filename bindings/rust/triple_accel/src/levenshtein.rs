@@ -185,13 +185,13 @@ pub fn levenshtein_naive_k(a: &[u8], b: &[u8], k: u32) -> Option<u32> {
     levenshtein_simd_k(a, b, k)
 }
 
-/// reference `src/levenshtein.rs:148-319`.  The distance is the k = u32::MAX case of the bounded routine; the
-/// unbounded routine's traceback follows its own tie order and is not offloaded.
+/// reference `src/levenshtein.rs:148-319`.  The k = u32::MAX case of the bounded routine, traceback included: the
+/// unbounded routine's tie order (a-gap, b-gap if <, substitution if <=, transposition if <=, `:207-249`) is the same
+/// decision function as the bounded one's (`:493-532`): substitution wins ties, the a-gap wins ties between gaps.
 pub fn levenshtein_naive_with_opts<T: PartialEq>(a: &[T], b: &[T], trace_on: bool, costs: EditCosts)
     -> (u32, Option<Vec<Edit>>) {
-    assert!(!trace_on, "levenshtein_naive_with_opts(trace_on = true) is not offloaded: use levenshtein_naive_k_with_opts");
     let (ca, cb) = to_codes(a, b);
-    (levenshtein_simd_k_with_opts(&ca, &cb, u32::MAX, false, costs).unwrap().0, None)
+    levenshtein_simd_k_with_opts(&ca, &cb, u32::MAX, trace_on, costs).unwrap()
 }
 
 /// reference `src/levenshtein.rs:105-107`
@@ -208,12 +208,66 @@ pub fn levenstein_naive_str(a: &str, b: &str) -> u32 {
 
 // ---- search -------------------------------------------------------------------------------------------------------------
 
-/// reference `src/levenshtein.rs:1911-1918`.  The reference returns a lazy iterator; the engine materialises the list
-/// (same items, same order), so `.next()` on the returned iterator behaves identically.
+/// `SearchType::All` on a long haystack, lazily like the reference's iterator (`src/levenshtein.rs:2282, 2448`;
+/// `tests/basic_tests.rs:631-632` takes one `.next()`): the haystack is searched `LAZY_CHUNK` bytes at a time, each
+/// chunk restarted `warm = 2 |needle| + start_gap / gap + 2` bytes early -- an optimal alignment of a needle prefix of
+/// length j costs at most j gap + start_gap, so it spans at most 2 j + start_gap / gap haystack bytes and every
+/// (cost, length) the reference computes for an end position inside the chunk is reproduced by the restarted run (the
+/// same argument the engine's own 128-byte work items rest on).  Matches that end in the warm-up belong
+/// to the previous chunk and are dropped.
+struct LazyAll<'a> {
+    needle: &'a [u8],
+    haystack: &'a [u8],
+    k: u32,
+    costs: EditCosts,
+    next_chunk: usize, // first end position (exclusive lower bound) of the next chunk
+    buf: std::vec::IntoIter<Match>,
+}
+const LAZY_CHUNK: usize = 1 << 20;
+
+impl<'a> Iterator for LazyAll<'a> {
+    type Item = Match;
+    fn next(&mut self) -> Option<Match> {
+        loop {
+            if let Some(m) = self.buf.next() {
+                return Some(m);
+            }
+            if self.next_chunk > self.haystack.len() {
+                return None;
+            }
+            let lo = self.next_chunk; // matches with lo <= end <= hi, except end == 0 which only the first chunk has
+            let hi = std::cmp::min(self.haystack.len(), lo + LAZY_CHUNK);
+            let raw = self.costs.raw();
+            let warm = 2 * self.needle.len() + (raw.start_gap / raw.gap) as usize + 2;
+            let from = lo.saturating_sub(warm);
+            let part = &self.haystack[from..hi];
+            let off = [0u64, part.len() as u64];
+            let (mut m, mut mo) = (std::ptr::null_mut(), std::ptr::null_mut());
+            check(unsafe {
+                ffi::ta_levenshtein_search_batch(ctx(), self.needle.as_ptr(), self.needle.len(), part.as_ptr(),
+                                                 off.as_ptr(), 1, self.k, 0, raw, 0, &mut m, &mut mo)
+            });
+            let first = lo == 0;
+            let v: Vec<Match> = unsafe { take_matches(m, mo) }
+                .into_iter()
+                .filter(|x| if first { true } else { x.end + from > lo })
+                .map(|x| Match { start: x.start + from, end: x.end + from, k: x.k })
+                .collect();
+            self.next_chunk = if hi == self.haystack.len() { hi + 1 } else { hi };
+            self.buf = v.into_iter();
+        }
+    }
+}
+
+/// reference `src/levenshtein.rs:1911-1918`.  `All` on an unanchored haystack longer than `LAZY_CHUNK` is lazy like
+/// the reference's iterator (see `LazyAll`); everything else is one call whose list is handed out item by item.
 pub fn levenshtein_search_simd_with_opts<'a>(needle: &'a [u8], haystack: &'a [u8], k: u32, search_type: SearchType,
                                              costs: EditCosts, anchored: bool) -> Box<dyn Iterator<Item = Match> + 'a> {
     if !needle.is_empty() {
         costs.check_search(); // reference :1965 (after the empty-needle special case)
+    }
+    if search_type == SearchType::All && !anchored && !needle.is_empty() && haystack.len() > LAZY_CHUNK {
+        return Box::new(LazyAll { needle, haystack, k, costs, next_chunk: 0, buf: Vec::new().into_iter() });
     }
     let off = [0u64, haystack.len() as u64];
     let (mut m, mut mo) = (std::ptr::null_mut(), std::ptr::null_mut());

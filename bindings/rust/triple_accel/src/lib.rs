@@ -60,13 +60,16 @@ pub fn fill_str(dest: &mut [u8], src: &[u8]) {
 
 // ---- plumbing shared by the two modules ---------------------------------------------------------------------------
 
-/// One engine context per thread (the crate's functions are re-entrant; so is this).  The device is LOCAL_RANK when
-/// set (one process per GPU), else 0.
+/// One engine context per thread (the crate's functions are re-entrant; so is this).  `TA_DEVICES=0,1,..,7` makes it
+/// ONE context over those GPUs (`ta_init_multi`: every batch call is split across them inside the library); else the
+/// device is LOCAL_RANK when set (one process per GPU), else 0.
 pub(crate) fn ctx() -> *mut ffi::TaCtx {
     thread_local!(static CTX: *mut ffi::TaCtx = unsafe {
         let mut c = std::ptr::null_mut();
+        let devs: Vec<i32> = std::env::var("TA_DEVICES").ok()
+            .map(|s| s.split(',').filter_map(|x| x.trim().parse().ok()).collect()).unwrap_or_default();
         let dev = std::env::var("LOCAL_RANK").ok().and_then(|s| s.parse().ok()).unwrap_or(0);
-        let rc = ffi::ta_init(dev, &mut c);
+        let rc = if devs.len() > 1 { ffi::ta_init_multi(devs.as_ptr(), devs.len() as i32, &mut c) } else { ffi::ta_init(dev, &mut c) };
         if rc != ffi::TA_OK {
             panic!("triple_accel_b200: ta_init failed ({}): there is no CPU fallback", rc)
         }

@@ -149,7 +149,9 @@ int ta_levenshtein_exp_batch(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_of
  * for every haystack of the batch.  *out_matches receives all matches, haystack by haystack, in the order the
  * reference iterator yields them; matches of haystack i are (*out_matches)[(*out_match_off)[i] ..
  * (*out_match_off)[i+1]).  Both arrays are allocated by the library: release with ta_free.  The needle is limited
- * to TA_MAX_STRING_LEN bytes, a haystack to 2^32 - 16 bytes (TA_ERR_TOO_LARGE beyond).
+ * to TA_MAX_STRING_LEN bytes (needles up to 256 bytes run on the warp kernel, up to ~450 bytes -- ~300 with
+ * transpositions -- with the DP rows in shared memory, longer ones with the rows in a device workspace of
+ * 16 (24) bytes per needle byte and resident thread), a haystack to 2^32 - 16 bytes (TA_ERR_TOO_LARGE beyond).
  * levenshtein_search(needle, haystack) (src/levenshtein.rs:2508-2513) is k = ta_search_default_k(needle_len),
  * TA_SEARCH_BEST, unit costs, anchored = 0. */
 int ta_levenshtein_search_batch(ta_ctx *ctx, const uint8_t *needle, size_t needle_len, const uint8_t *hay,
@@ -164,6 +166,12 @@ uint32_t ta_search_default_k(size_t needle_len); /* src/levenshtein.rs:1873 */
 int ta_hamming_search_batch(ta_ctx *ctx, const uint8_t *needle, size_t needle_len, const uint8_t *hay,
                             const uint64_t *hay_off, size_t n, uint32_t k, int search_type, ta_match **out_matches,
                             uint64_t **out_match_off);
+
+/* hamming_search_naive_with_opts (src/hamming.rs:96-146): as ta_hamming_search_batch, but NUL bytes in a haystack
+ * are ordinary bytes (the scalar routine has no such restriction; only the SIMD entry checks, src/hamming.rs:463). */
+int ta_hamming_search_naive_batch(ta_ctx *ctx, const uint8_t *needle, size_t needle_len, const uint8_t *hay,
+                                  const uint64_t *hay_off, size_t n, uint32_t k, int search_type,
+                                  ta_match **out_matches, uint64_t **out_match_off);
 
 /* ---- device-resident entry points (kernel-only; all pointers are device pointers on ctx's device) ---------- */
 /* `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  Calls are asynchronous.

@@ -73,11 +73,16 @@ def test_kat_distance(eng, r):
         assert res is None
     else:
         assert res is not None and res[0] == r["expect"]["dist"]
-    # trace_on = true KATs of the k-bounded routines (tests/basic_tests.rs:395-427, 545-577 and doc-tests); the
-    # unbounded levenshtein_naive_with_opts has its own tie rules and is not on the offloaded path
+    # trace_on = true KATs of the k-bounded routines (tests/basic_tests.rs:395-427, 545-577 and doc-tests) and of the
+    # unbounded levenshtein_naive_with_opts (tests/basic_tests.rs:163-195): same decision function, see api.py
     if r.get("trace") and fn in ("levenshtein_naive_k_with_opts", "levenshtein_simd_k_with_opts"):
         d, edits = eng.levenshtein_simd_k_with_opts(a, b, k, True, costs)
         assert d == r["expect"]["dist"] and [list(e) for e in edits] == r["expect"]["edits"]
+    if fn == "levenshtein_naive_with_opts":
+        d, edits = eng.levenshtein_naive_with_opts(a, b, bool(r.get("trace")), costs)
+        assert d == r["expect"]["dist"]
+        if r.get("trace"):
+            assert [list(e) for e in edits] == r["expect"]["edits"]
 
 
 @pytest.mark.parametrize("r", SEARCH, ids=_ids(SEARCH))
@@ -157,6 +162,24 @@ def test_hamming_search_random(eng):
 
 # ---------------------------------------------------------------------------------------------------------------
 # error behaviour of the boundary
+def test_hamming_search_naive_accepts_nul_bytes(eng):
+    """src/hamming.rs:96-146 has no NUL check (only the SIMD entry does, :463): haystacks with NUL bytes through the
+    *_naive* names equal the scalar oracle's, through the SIMD names they are the reference's panic"""
+    rng = random.Random(8)
+    needle = bytes(rng.randrange(0, 3) for _ in range(6))
+    hays = [bytes(rng.randrange(0, 3) for _ in range(rng.randrange(0, 300))) for _ in range(50)]
+    hay, hoff = _pack(hays)
+    for st in (0, 1):
+        got, goff = eng.hamming_search_batch(needle, hay, hoff, 2, st, naive=True)
+        for i, h in enumerate(hays):
+            want = orc.hamming_search_naive_with_opts(needle, h, 2, st)
+            assert [tuple(int(x) for x in m) for m in got[int(goff[i]):int(goff[i + 1])]] == want, (i, st)
+    assert [tuple(m) for m in eng.hamming_search_naive_with_opts(needle, hays[3], 2, 0)] == \
+        orc.hamming_search_naive_with_opts(needle, hays[3], 2, 0)
+    with pytest.raises(AssertionError):
+        eng.hamming_search_batch(needle, hay, hoff, 2, 0)
+
+
 def test_hamming_length_mismatch_panics(eng):
     with pytest.raises(AssertionError):
         eng.hamming(b"abc", b"ab")  # reference: assert at src/hamming.rs:38
@@ -272,6 +295,29 @@ def test_lev_k_mutated(eng, length, k, costs):
     # swapped argument order gives the same answers (the reference swaps so that a is the shorter string)
     got2 = eng.levenshtein_k_batch(b, bo, a, ao, k, costs)
     assert np.array_equal(got2, want)
+
+
+@pytest.mark.parametrize("costs", COST_MODELS, ids=[str(c) for c in COST_MODELS])
+def test_lev_diag16_large_batch(eng, costs):
+    """a batch large enough for the dispatcher's thread-per-pair u16 kernel (lev_diag16.cu; >= 16384 pairs, band <= 32
+    diagonals): ragged lengths incl. empty strings, every misalignment, small alphabets (ties, transpositions), the
+    bands of every register count (2, 3, 4, 6, 8 packed registers per anti-diagonal), None and within-k pairs"""
+    from triple_accel_b200 import synth
+    parts = [synth.edited_pairs(6000, 0, 70, 6, seed=sum(costs), allow_swap=True, alphabet=4),
+             synth.edited_pairs(6000, 90, 140, 12, seed=sum(costs) + 1, allow_swap=True),
+             synth.edited_pairs(5000, 1, 40, 3, seed=sum(costs) + 2, allow_swap=True, alphabet=2)]
+    a = np.concatenate([p[0] for p in parts])
+    b = np.concatenate([p[2] for p in parts])
+    ao = np.concatenate([[0]] + [p[1][1:] + sum(len(q[0]) for q in parts[:i]) for i, p in enumerate(parts)]).astype(np.uint64)
+    bo = np.concatenate([[0]] + [p[3][1:] + sum(len(q[2]) for q in parts[:i]) for i, p in enumerate(parts)]).astype(np.uint64)
+    mism, gap, sgap, _ = costs
+    for k in (0, 2, 5, 9, 14, 21, 30):
+        want = orc.levenshtein_k_batch(a, ao, b, bo, k, costs, threads=8)
+        got = eng.levenshtein_k_batch(a, ao, b, bo, k, costs)
+        bad = np.nonzero(got != want)[0]
+        assert len(bad) == 0, (k, costs, len(bad), int(bad[0]), int(got[bad[0]]), int(want[bad[0]]),
+                               bytes(a[int(ao[bad[0]]):int(ao[bad[0] + 1])]), bytes(b[int(bo[bad[0]]):int(bo[bad[0] + 1])]))
+    assert np.array_equal(eng.levenshtein_k_batch(b, bo, a, ao, 9, costs), orc.levenshtein_k_batch(a, ao, b, bo, 9, costs, threads=8))
 
 
 @pytest.mark.parametrize("costs", [(1, 1, 0, 0), (1, 1, 0, 1)], ids=str)
@@ -488,6 +534,28 @@ def test_search_filter_long_needles_and_transpositions(eng):
                 assert np.array_equal(goff, woff) and np.array_equal(got, want), (nlen, costs, k)
 
 
+@pytest.mark.parametrize("nlen", [257, 301, 453, 1000])
+@pytest.mark.parametrize("costs", [(1, 1, 0, 0), (1, 1, 1, 1)], ids=str)
+def test_search_long_needles(eng, nlen, costs):
+    """needles beyond both exact kernels' on-chip limits (256 rows for the warp kernel, ~450 / ~300 rows of shared
+    memory for the thread kernel): DP rows in the global-memory workspace.  The reference takes any needle
+    (src/levenshtein.rs:2034-2151)."""
+    rng = random.Random(nlen + costs[3])
+    needle = bytes(rng.randrange(1, 5) for _ in range(nlen))
+    hays = []
+    for i in range(40):
+        h = bytearray(rng.randrange(1, 5) for _ in range(rng.randrange(0, 2500)))
+        if i % 3 == 0:
+            p = rng.randrange(0, len(h) + 1)
+            h[p:p] = _mutate(rng, needle, rng.randrange(0, 30), 5).replace(b"\0", b"\1")
+        hays.append(bytes(h))
+    hay, hoff = _pack(hays)
+    for k, st, anchored in ((25, 0, False), (25, 1, False), (40, 1, True)):
+        got, goff = eng.levenshtein_search_batch(needle, hay, hoff, k, st, costs, anchored)
+        want, woff = orc.levenshtein_search_batch(needle, hay, hoff, k, st, costs, anchored, threads=8)
+        assert np.array_equal(goff, woff) and np.array_equal(got, want), (nlen, k, st, anchored)
+
+
 @pytest.mark.parametrize("costs", [(1, 1, 0, 0), (1, 1, 0, 1), (2, 1, 3, 0), (2, 2, 1, 3)], ids=str)
 def test_lev_wide_band_block_kernel(eng, costs):
     """bands wider than 1024 diagonals go to the block-per-pair kernel: levenshtein()/rdamerau() on long strings
@@ -568,6 +636,29 @@ def test_traceback_longer_strings(eng):
                 assert dist[i] == want[0] and got == [tuple(e) for e in want[1]], (i, costs, k)
 
 
+def test_traceback_long_strings_unbounded_k(eng):
+    """levenshtein() / rdamerau()-style callers ask for the trace with k = u32::MAX: the band of the traceback must
+    follow the pairs' distances, not k or the string lengths (strings of 600..3000 bytes, a handful of edits; one
+    unrelated pair of short strings whose distance is large)."""
+    rng = random.Random(77)
+    A = _rand_strs(rng, 40, 600, 3000, 256)
+    B = [_mutate(rng, s, rng.randrange(0, 9), 256) for s in A]
+    A.append(bytes(rng.randrange(256) for _ in range(150)))
+    B.append(bytes(rng.randrange(256) for _ in range(140)))
+    a, ao = _pack(A)
+    b, bo = _pack(B)
+    for costs in ((1, 1, 0, 0), (1, 1, 0, 1), (2, 1, 2, 0)):
+        for exp in (False, True):
+            if exp:
+                dist, edits, eoff = eng.levenshtein_exp_trace_batch(a, ao, b, bo, costs)
+            else:
+                dist, edits, eoff = eng.levenshtein_k_trace_batch(a, ao, b, bo, 0xFFFFFFFF, costs)
+            for i in range(len(A)):
+                wd, we = orc.levenshtein_naive_k_with_opts(A[i], B[i], 0xFFFFFFFF, True, costs)  # the SIMD entry's tie order
+                got = [tuple(int(x) for x in e) for e in edits[int(eoff[i]):int(eoff[i + 1])]]
+                assert dist[i] == wd and got == [tuple(e) for e in we], (i, costs, exp)
+
+
 def test_full_size_properties(eng):
     """BASELINE.json sizes (1 M pairs, len 128, k = 8 and 16; 1 M x len 512 Damerau is covered by the bench's parity
     check) through size-independent properties: symmetry, identity, the edit budget as an upper bound, monotonicity
@@ -646,6 +737,9 @@ SEARCH_TESTS = ("test_search_random or test_search_planted or test_kat_search or
 @pytest.mark.parametrize("env,select", [
     ({"TA_FORCE_BAND": "1"}, LEV_TESTS),
     ({"TA_FR": "1"}, FR_TESTS),
+    ({"TA_DIAG16": "1"}, LEV_TESTS + " or test_lev_diag16_large_batch"),
+    ({"TA_DIAG16": "1", "TA_FORCE_BAND": "1"}, LEV_TESTS),
+    ({"TA_DIAG16": "0"}, "test_lev_diag16_large_batch"),
     ({"TA_FR": "0"}, "test_lev_fr_long_strings"),
     ({"TA_BITPAR": "simd"}, LEV_TESTS),
     ({"TA_BITPAR": "tab"}, LEV_TESTS),
@@ -659,14 +753,16 @@ SEARCH_TESTS = ("test_search_random or test_search_planted or test_kat_search or
     ({"TA_NO_SEARCH_FILTER": "1", "TA_SEARCH_KERNEL": "thread"}, SEARCH_TESTS),
     ({"TA_NO_SEARCH_FILTER": "1", "TA_SEARCH_KERNEL": "wave"}, SEARCH_TESTS),
     ({"TA_SEARCH_KERNEL": "thread"}, SEARCH_TESTS),
+    ({"TA_NO_SEARCH_FILTER": "1", "TA_SEARCH_KERNEL": "global"}, SEARCH_TESTS),
     ({"TA_SEARCH_FILTER": "myers"}, SEARCH_TESTS),
     ({"TA_SEARCH_FILTER": "pigeon"}, SEARCH_TESTS),
     ({"TA_SEARCH_FILTER": "pigeon", "TA_PIGEON_STAGED": "0"}, SEARCH_TESTS),
-], ids=["general-band-kernel", "diagonal-extension-kernel-forced", "diagonal-extension-kernel-off", "bitpar-simd-kernel", "bitpar-sliding-table-kernel",
+], ids=["general-band-kernel", "diagonal-extension-kernel-forced", "u16-thread-per-pair-kernel-forced", "u16-thread-per-pair-kernel-on-unit-costs",
+        "u16-thread-per-pair-kernel-off", "diagonal-extension-kernel-off", "bitpar-simd-kernel", "bitpar-sliding-table-kernel",
         "bitpar-sliding-table-32bit-on-narrow-bands", "bitpar-block-table-one-pair-per-thread", "length-bucketing-pre-pass", "bitpar-block-table-256-entries",
         "bitpar-block-table-8-blocks", "bitpar-block-table-256-entries-8-blocks",
         "bitpar-table-2plane-kernel", "search-thread-kernel-nofilter", "search-wave-kernel-nofilter",
-        "search-thread-kernel-filter", "search-myers-filter-forced", "search-pigeonhole-filter-forced",
+        "search-thread-kernel-filter", "search-global-rows-kernel-nofilter", "search-myers-filter-forced", "search-pigeonhole-filter-forced",
         "search-pigeonhole-filter-lane-per-segment-loads"])
 def test_every_kernel_variant_forced(env, select):
     """The dispatchers pick a kernel from the cost model, band width and batch size (bit-parallel vs general banded

@@ -236,15 +236,28 @@ class Engine:
         self._check(rc)
         return self._take_matches(mp, op, n)
 
-    def hamming_search_batch(self, needle, hay, hay_off, k, search_type=SearchType.All):
-        """Returns (matches[total, 3] uint64 = start,end,k ; match_off[n+1])."""
+    def hamming_search_batch(self, needle, hay, hay_off, k, search_type=SearchType.All, naive=False):
+        """Returns (matches[total, 3] uint64 = start,end,k ; match_off[n+1]).  naive=True: the scalar routine's contract
+        (src/hamming.rs:96-146): NUL bytes in a haystack are ordinary bytes, not a panic."""
         needle, hay, hay_off = _u8(needle), _u8(hay), _u64(hay_off)
         n = len(hay_off) - 1
         mp, op = C.POINTER(ta_match)(), C.POINTER(C.c_uint64)()
-        rc = self._lib.ta_hamming_search_batch(self._h, _ptr(needle), len(needle), _ptr(hay), _ptr(hay_off), n,
-                                               _k32(k), int(search_type), C.byref(mp), C.byref(op))
+        fn = self._lib.ta_hamming_search_naive_batch if naive else self._lib.ta_hamming_search_batch
+        rc = fn(self._h, _ptr(needle), len(needle), _ptr(hay), _ptr(hay_off), n, _k32(k), int(search_type),
+                C.byref(mp), C.byref(op))
         self._check(rc)
         return self._take_matches(mp, op, n)
+
+    def hamming_search_naive_with_opts(self, needle, haystack, k, search_type=SearchType.All):
+        """src/hamming.rs:96-146 (no NUL-byte check).  Returns a list of Match."""
+        haystack = _u8(haystack)
+        off = np.array([0, len(haystack)], np.uint64)
+        arr, _ = self.hamming_search_batch(needle, haystack, off, k, search_type, naive=True)
+        return [Match(int(s), int(e), int(c)) for s, e, c in arr]
+
+    def hamming_search_naive(self, needle, haystack):  # src/hamming.rs:70-72
+        k = self._lib.ta_search_default_k(len(bytes(needle)))
+        return self.hamming_search_naive_with_opts(needle, haystack, k, SearchType.Best)
 
     def hamming_search_simd_with_opts(self, needle, haystack, k, search_type=SearchType.All):
         """src/hamming.rs:454-475.  Returns a list of Match."""
@@ -411,17 +424,16 @@ class Engine:
     levenshtein_naive_k_with_opts = levenshtein_simd_k_with_opts  # src/levenshtein.rs:376-607 (the contract itself)
     levenshtein_search_naive = levenshtein_search_simd                        # src/levenshtein.rs:1549-1556
     levenshtein_search_naive_with_opts = levenshtein_search_simd_with_opts    # src/levenshtein.rs:1589-1838
-    # (the scalar Hamming search does not reject NUL bytes in the haystack; the public entry, and this path, do:
-    #  src/hamming.rs:463, src/lib.rs:237-243)
-    hamming_search_naive = hamming_search_simd                      # src/hamming.rs:70-72
-    hamming_search_naive_with_opts = hamming_search_simd_with_opts  # src/hamming.rs:96-146
 
     def levenshtein_naive_with_opts(self, a, b, trace_on=False, costs=LEVENSHTEIN_COSTS):
-        """src/levenshtein.rs:148-319: (distance, None).  The distance is the k = u32::MAX case of the bounded routine;
-        the unbounded routine's traceback has its own tie order and is not on the offloaded path."""
-        if trace_on:
-            raise NotImplementedError("levenshtein_naive_with_opts(trace_on=true): use levenshtein_simd_k_with_opts")
-        return self.levenshtein_simd_k_with_opts(a, b, 0xFFFFFFFF, False, costs)
+        """src/levenshtein.rs:148-319: (distance, None | [Edit, ...]).  The unbounded routine breaks ties in the order
+        a-gap, b-gap if <, substitution if <=, transposition if <= (src/levenshtein.rs:207-249); that is the same
+        decision function as the bounded routine's substitution, a-gap if <, b-gap if <, transposition if <=
+        (src/levenshtein.rs:493-532) -- substitution wins ties, the a-gap wins ties between gaps -- so this is the
+        k = u32::MAX case of the offloaded path (tests/test_oracle_kat.py pins the equality of the two restated
+        routines; tests/basic_tests.rs:163-195 run through it on the GPU)."""
+        d, ed = self.levenshtein_simd_k_with_opts(a, b, 0xFFFFFFFF, trace_on, costs)
+        return d, ed
 
     def levenstein_naive_str(self, a: str, b: str):
         """src/levenshtein.rs:123-127 (sic): distance between two `str`s counted in chars."""

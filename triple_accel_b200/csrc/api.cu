@@ -598,36 +598,40 @@ int trace_batch(ta_ctx *ctx, bool exp_mode, const uint8_t *a, const uint64_t *a_
             if ((r = upload_side(ctx, 0, false, b, b_off, n, &db, &db_off, st)) != TA_OK) return r;
             if ((r = ta_dev_reserve(ctx, ctx->d_out[0], n * sizeof(uint32_t))) != TA_OK) return r;
             uint32_t *d_out = (uint32_t *)ctx->d_out[0].p;
-            if (!exp_mode) {
-                r = run_trace_group(ctx, st, da, da_off, db, db_off, nullptr, nullptr, 0, n, k, costs, bs.max_len, d_out,
-                                    pool, pos, num);
-                if (r != TA_OK) return r;
-            } else {
-                // exact distances first (src/levenshtein.rs:1486-1493), then the traceback of each pair with the k of
-                // the round that accepted it (the decisions along an optimal path do not depend on the band width)
-                if ((r = exp_rounds_dev(ctx, da, da_off, db, db_off, n, costs, bs.max_len, d_out, st)) != TA_OK) return r;
-                TA_CUDA(ctx, cudaMemcpyAsync(out_dist, d_out, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-                TA_CUDA(ctx, cudaStreamSynchronize(st));
-                std::vector<std::vector<uint32_t>> rounds;
-                for (size_t i = 0; i < n; i++) {
-                    size_t rr = 0;
-                    uint64_t kk = 30;
-                    while (kk < out_dist[i]) kk *= 2, rr++;
-                    if (rounds.size() <= rr) rounds.resize(rr + 1);
-                    rounds[rr].push_back((uint32_t)i);
-                }
-                if ((r = ta_dev_reserve(ctx, ctx->d_aoff[1], n * sizeof(uint32_t))) != TA_OK) return r;
-                uint32_t *d_idx = (uint32_t *)ctx->d_aoff[1].p;
+            // Distances first -- the k-bounded call (src/levenshtein.rs:714-827) or the exponential search
+            // (:1486-1493); then the traceback of every pair that has a distance, in groups by distance with the
+            // thresholds 30, 60, 120, ...: the decisions along an optimal path do not depend on the band width once
+            // the band holds the path, so a pair at distance d is traced in the band of min(k, first threshold >= d)
+            // whatever k the caller passed (k = u32::MAX on long strings must not ask for a band as wide as the
+            // strings).  Only a pair whose OWN distance needs more than 1024 diagonals is TA_ERR_TOO_LARGE.
+            if (exp_mode)
+                r = exp_rounds_dev(ctx, da, da_off, db, db_off, n, costs, bs.max_len, d_out, st);
+            else
+                r = ta_launch_lev(ctx, da, da_off, db, db_off, n, nullptr, k, costs, bs.max_len, d_out, st);
+            if (r != TA_OK) return r;
+            TA_CUDA(ctx, cudaMemcpyAsync(out_dist, d_out, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            TA_CUDA(ctx, cudaStreamSynchronize(st));
+            std::vector<std::vector<uint32_t>> rounds;
+            for (size_t i = 0; i < n; i++) {
+                if (out_dist[i] == TA_NONE) continue;
+                size_t rr = 0;
                 uint64_t kk = 30;
-                for (size_t rr = 0; rr < rounds.size(); rr++, kk *= 2) {
-                    if (rounds[rr].empty()) continue;
-                    TA_CUDA(ctx, cudaMemcpyAsync(d_idx, rounds[rr].data(), rounds[rr].size() * sizeof(uint32_t),
-                                                 cudaMemcpyHostToDevice, st));
-                    r = run_trace_group(ctx, st, da, da_off, db, db_off, d_idx, rounds[rr].data(), 0, rounds[rr].size(),
-                                        (uint32_t)std::min<uint64_t>(kk, 0xFFFFFFFFull), costs, bs.max_len, d_out, pool,
-                                        pos, num);
-                    if (r != TA_OK) return r;
-                }
+                while (kk < out_dist[i]) kk *= 2, rr++;
+                if (rounds.size() <= rr) rounds.resize(rr + 1);
+                rounds[rr].push_back((uint32_t)i);
+            }
+            if ((r = ta_dev_reserve(ctx, ctx->d_aoff[1], n * sizeof(uint32_t))) != TA_OK) return r;
+            uint32_t *d_idx = (uint32_t *)ctx->d_aoff[1].p;
+            uint64_t kk = 30;
+            for (size_t rr = 0; rr < rounds.size(); rr++, kk *= 2) {
+                if (rounds[rr].empty()) continue;
+                TA_CUDA(ctx, cudaMemcpyAsync(d_idx, rounds[rr].data(), rounds[rr].size() * sizeof(uint32_t),
+                                             cudaMemcpyHostToDevice, st));
+                const uint64_t kr = exp_mode ? kk : std::min<uint64_t>(kk, k);
+                r = run_trace_group(ctx, st, da, da_off, db, db_off, d_idx, rounds[rr].data(), 0, rounds[rr].size(),
+                                    (uint32_t)std::min<uint64_t>(kr, 0xFFFFFFFFull), costs, bs.max_len, d_out, pool, pos,
+                                    num);
+                if (r != TA_OK) return r;
             }
             TA_CUDA(ctx, cudaMemcpyAsync(out_dist, d_out, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             TA_CUDA(ctx, cudaStreamSynchronize(st));

@@ -59,9 +59,27 @@ __global__ void __launch_bounds__(256) hamming_search_kernel(const uint8_t *__re
 
 }  // namespace
 
+static int hamming_search_impl(ta_ctx *ctx, bool check_nul, const uint8_t *needle, size_t needle_len, const uint8_t *hay,
+                               const uint64_t *hay_off, size_t n, uint32_t k, int search_type, ta_match **out_matches,
+                               uint64_t **out_match_off);
+
 extern "C" int ta_hamming_search_batch(ta_ctx *ctx, const uint8_t *needle, size_t needle_len, const uint8_t *hay,
                                        const uint64_t *hay_off, size_t n, uint32_t k, int search_type,
                                        ta_match **out_matches, uint64_t **out_match_off) {
+    return hamming_search_impl(ctx, true, needle, needle_len, hay, hay_off, n, k, search_type, out_matches, out_match_off);
+}
+
+// hamming_search_naive_with_opts (src/hamming.rs:96-146): the scalar routine has no NUL-byte restriction (the check
+// lives in the SIMD entry, src/hamming.rs:463); same kernel, the NUL flag is simply not an error.
+extern "C" int ta_hamming_search_naive_batch(ta_ctx *ctx, const uint8_t *needle, size_t needle_len, const uint8_t *hay,
+                                             const uint64_t *hay_off, size_t n, uint32_t k, int search_type,
+                                             ta_match **out_matches, uint64_t **out_match_off) {
+    return hamming_search_impl(ctx, false, needle, needle_len, hay, hay_off, n, k, search_type, out_matches, out_match_off);
+}
+
+static int hamming_search_impl(ta_ctx *ctx, bool check_nul, const uint8_t *needle, size_t needle_len, const uint8_t *hay,
+                               const uint64_t *hay_off, size_t n, uint32_t k, int search_type, ta_match **out_matches,
+                               uint64_t **out_match_off) {
     if (!ctx || !out_matches || !out_match_off) return TA_ERR_BAD_ARG;
     *out_matches = nullptr;
     *out_match_off = nullptr;
@@ -86,8 +104,8 @@ extern "C" int ta_hamming_search_batch(ta_ctx *ctx, const uint8_t *needle, size_
         const int rc = ta_multi_run(ctx, parts, [&](int r) -> int {
             const size_t lo = bound[r], cnt = bound[r + 1] - bound[r];
             if (cnt == 0) return TA_OK;
-            return ta_hamming_search_batch(ta_multi_sub(ctx, r), needle, needle_len, hay, hay_off + lo, cnt, k,
-                                           search_type, &ms[r], &mo[r]);
+            return hamming_search_impl(ta_multi_sub(ctx, r), check_nul, needle, needle_len, hay, hay_off + lo, cnt, k,
+                                       search_type, &ms[r], &mo[r]);
         });
         if (rc != TA_OK) {
             for (int r = 0; r < parts; r++) ta_free(ms[r]), ta_free(mo[r]);
@@ -144,7 +162,7 @@ extern "C" int ta_hamming_search_batch(ta_ctx *ctx, const uint8_t *needle, size_
                 TA_CUDA(ctx, cudaGetLastError());
                 TA_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags + 4, ctx->d_flags + 4, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
                 TA_CUDA(ctx, cudaStreamSynchronize(st));
-                if (ctx->h_flags[8]) return TA_ERR_NUL_BYTE;
+                if (check_nul && ctx->h_flags[8]) return TA_ERR_NUL_BYTE;
                 unsigned long long got;
                 memcpy(&got, ctx->h_flags + 4, sizeof got);
                 if (got <= cap) {

@@ -20,27 +20,10 @@
 
 #include <algorithm>
 
+#include "lev_band_common.cuh"
 #include "ta_common.cuh"
 
 namespace {
-
-struct BandArgs {
-    const uint8_t *a;
-    const uint64_t *a_off;
-    const uint8_t *b;
-    const uint64_t *b_off;
-    const uint32_t *idx;  // optional indirection: work item w -> pair idx[w]
-    size_t pair_base;     // without idx: work item w -> pair pair_base + w
-    size_t n;
-    uint32_t k;
-    uint32_t mism, gap, sgap, tcost;
-    uint32_t slot;  // shared-memory bytes reserved per string (SMEM variants)
-    uint32_t *out;
-    // traceback (TRACE variants): one byte per band cell, work item w owns trace[w * trace_stride ..), laid out
-    // [anti-diagonal s - s0][cell]; 0 = substitution/match, 1 = a-gap, 2 = b-gap, 3 = transposition
-    uint8_t *trace;
-    size_t trace_stride;
-};
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
@@ -49,30 +32,6 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t umin3(uint32_t x, uint32_t y, uint32_t z) { return min(min(x, y), z); }
-
-// Per-pair band: the reference's max_k / unit_k clamps (src/levenshtein.rs:400-430) and the Ukkonen band
-// [dlo, dlo + W - 1] = [-e, diff + e]; one extra diagonal each side when transpositions need the neighbours' match
-// flags.  Shared by every kernel of this file and by the traceback walker so that they agree cell by cell.
-struct BandInfo {
-    uint32_t max_k;
-    int dlo, W;
-    bool none;  // the length difference alone exceeds the band: Option::None
-};
-__device__ __forceinline__ BandInfo band_info(int m, int n, uint32_t k, uint32_t mism, uint32_t gap, uint32_t sgap,
-                                              bool trans) {
-    BandInfo bi;
-    const uint32_t diff = (uint32_t)(n - m);
-    uint32_t max_k = min((uint32_t)m * mism, ((uint32_t)m << 1) * gap + (m == 0 ? 0u : sgap + (n == m ? sgap : 0u)));
-    max_k = min(k, max_k + diff * gap + (n == m ? 0u : sgap));
-    const uint32_t unit_k = (max_k > sgap ? max_k - sgap : 0u) / gap;
-    bi.max_k = max_k;
-    bi.none = diff > unit_k;
-    const uint32_t spare = max_k >= 2 * sgap + diff * gap ? max_k - 2 * sgap - diff * gap : 0u;
-    const int e = (int)(spare / (2 * gap)) + (trans ? 1 : 0);
-    bi.dlo = -e;
-    bi.W = (int)diff + 2 * e + 1;
-    return bi;
-}
 
 template <int G, int C, bool AFFINE, bool TRANS, bool SMEM, bool TRACE>
 __global__ void __launch_bounds__(128) lev_band_kernel(const BandArgs args) {
@@ -595,6 +554,8 @@ int ta_launch_lev_band(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, con
     args.mism = costs.mismatch, args.gap = costs.gap, args.sgap = costs.start_gap, args.tcost = costs.transpose;
     args.slot = 0, args.out = out, args.trace = nullptr, args.trace_stride = 0, args.pair_base = 0;
     const uint32_t W = ta_band_width_bound(k, costs, max_len);
+    // narrow bands, large batches: one thread per pair with packed u16 cells (lev_diag16.cu)
+    if (ta_diag16_can_handle(n, k, costs, max_len, W)) return ta_launch_lev_diag16(ctx, args, costs, W, st);
     const bool affine = costs.start_gap != 0, trans = costs.transpose != 0;
     if (affine && trans) return launch_w<true, true>(ctx, args, W, max_len, st);
     if (affine) return launch_w<true, false>(ctx, args, W, max_len, st);

@@ -50,24 +50,33 @@ struct SearchArgs {
     Hit *hits;
     unsigned long long *hit_count;
     unsigned long long hit_cap;
+    uint32_t *rows_ws;  // search_exact_kernel<.., GLOBAL = true>: DP rows of every block, (4 | 6) * (N + 1) * T words each
 };
 
-template <bool TRANS>
+// GLOBAL = false: DP rows and the needle in shared memory (needles up to ~450 bytes).  GLOBAL = true: the rows live in a
+// global-memory workspace with the same [array][row][thread] layout (coalesced across the threads of a block) and the
+// needle is read through the read-only cache, for needles of any length the header promises (TA_MAX_STRING_LEN);
+// blocks are persistent there because the workspace bounds how many can run.
+template <bool TRANS, bool GLOBAL>
 __global__ void __launch_bounds__(64) search_exact_kernel(const SearchArgs args) {
-    extern __shared__ uint32_t sm[];
+    extern __shared__ uint32_t sm_rows[];
     const uint32_t N = args.needle_len;
     const uint32_t rows = N + 1;
     const uint32_t T = blockDim.x;
     const uint32_t tid = threadIdx.x;
+    uint32_t *const sm = GLOBAL ? args.rows_ws + (size_t)blockIdx.x * (TRANS ? 6 : 4) * rows * T : sm_rows;
     // array a, row j -> sm[(a * rows + j) * T + tid]
-    auto at = [&](uint32_t a, uint32_t j) -> uint32_t & { return sm[(a * rows + j) * T + tid]; };
+    auto at = [&](uint32_t a, uint32_t j) -> uint32_t & { return sm[((size_t)a * rows + j) * T + tid]; };
     enum { CUR_DP = 0, CUR_LEN = 1, NGAP = 2, NGAP_LEN = 3, PREV_DP = 4, PREV_LEN = 5 };
-    uint8_t *sneedle = (uint8_t *)(sm + (size_t)(TRANS ? 6 : 4) * rows * T);
-    for (uint32_t q = tid; q < N; q += T) sneedle[q] = args.needle[q];
-    __syncthreads();
+    const uint8_t *sneedle = args.needle;
+    if (!GLOBAL) {
+        uint8_t *sn = (uint8_t *)(sm_rows + (size_t)(TRANS ? 6 : 4) * rows * T);
+        for (uint32_t q = tid; q < N; q += T) sn[q] = args.needle[q];
+        __syncthreads();
+        sneedle = sn;
+    }
 
-    const size_t w = (size_t)blockIdx.x * T + tid;
-    if (w >= args.n) return;
+  for (size_t w = (size_t)blockIdx.x * T + tid; w < args.n; w += (size_t)gridDim.x * T) {
     const uint32_t hidx = args.idx ? args.idx[w] : (uint32_t)w;
     const uint64_t h0 = args.hay_off[hidx], h1 = args.hay_off[hidx + 1];
     const uint8_t *hay = args.hay + h0;
@@ -202,6 +211,7 @@ __global__ void __launch_bounds__(64) search_exact_kernel(const SearchArgs args)
             }
         }
     }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -469,7 +479,20 @@ static int search_device(ta_ctx *ctx, cudaStream_t st, const uint8_t *d_needle, 
     if (force && force[0] == 't' && thread_ok) use_wave = false;
     if (force && force[0] == 'w' && wave_ok) use_wave = true;
     if (segs) use_wave = true;  // segment work items are only understood by the wave kernel (needle <= 64 here)
-    if (!use_wave && !thread_ok) return TA_ERR_TOO_LARGE;
+    // needles that fit neither kernel (> 256 bytes and DP rows beyond shared memory; the reference takes any needle,
+    // src/levenshtein.rs:2034-2151): thread per haystack with the DP rows in a global-memory workspace
+    const bool use_global = (!use_wave && !thread_ok) || (force && force[0] == 'g' && !segs);
+    size_t global_blocks = 0;
+    if (use_global) {
+        use_wave = false;
+        threads = 32;
+        smem = 0;
+        const size_t per_block = (size_t)(trans ? 6 : 4) * (needle_len + 1) * threads * sizeof(uint32_t);
+        const size_t budget = (size_t)2 << 30;
+        global_blocks = std::max<size_t>(1, std::min<size_t>({budget / per_block, (work_n + threads - 1) / threads,
+                                                              (size_t)ctx->sm_count * 16}));
+        if ((rc = ta_dev_reserve(ctx, ctx->d_work[3], global_blocks * per_block)) != TA_OK) return rc;
+    }
     void (*kern)(const SearchArgs) = nullptr;
     if (use_wave) {
         const int C = needle_len <= 32 ? 1 : needle_len <= 64 ? 2 : needle_len <= 128 ? 4 : 8;
@@ -479,8 +502,10 @@ static int search_device(ta_ctx *ctx, cudaStream_t st, const uint8_t *d_needle, 
         if (C == 8) kern = trans ? search_wave_kernel<8, true> : search_wave_kernel<8, false>;
         threads = 128;
         smem = 0;
+    } else if (use_global) {
+        kern = trans ? search_exact_kernel<true, true> : search_exact_kernel<false, true>;
     } else {
-        kern = trans ? search_exact_kernel<true> : search_exact_kernel<false>;
+        kern = trans ? search_exact_kernel<true, false> : search_exact_kernel<false, false>;
         TA_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     if ((rc = ta_pin_reserve(ctx, ctx->h_pin[3], SPEC_HITS * sizeof(Hit))) != TA_OK) return rc;
@@ -497,9 +522,11 @@ static int search_device(ta_ctx *ctx, cudaStream_t st, const uint8_t *d_needle, 
         sa.needle_len = (uint32_t)needle_len, sa.k = k;
         sa.mism = costs.mismatch, sa.gap = costs.gap, sa.sgap = costs.start_gap, sa.tcost = costs.transpose;
         sa.anchored = anchored, sa.hits = (Hit *)ctx->d_work[1].p, sa.hit_count = d_count, sa.hit_cap = cap;
+        sa.rows_ws = use_global ? (uint32_t *)ctx->d_work[3].p : nullptr;
         const size_t per_block = use_wave ? (size_t)threads / 32 : (size_t)threads;
         size_t blocks = (work_n + per_block - 1) / per_block;
         if (use_wave) blocks = std::min<size_t>(blocks, (size_t)ctx->sm_count * 16);  // persistent warps
+        if (use_global) blocks = global_blocks;
         kern<<<(unsigned)blocks, threads, smem, st>>>(sa);
         ctx->launches++;
         TA_CUDA(ctx, cudaGetLastError());
