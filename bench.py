@@ -59,8 +59,19 @@ WORKLOADS = {
     "search_n32_h4096": ("search", 100_000, 4096, 3, (1, 1, 0, 0), "strong",
                          "levenshtein_search needle len=32 over 100k haystacks len=4096, k=3, Best, 1% planted hits, one "
                          "batch over all GPUs, needle broadcast from rank 0 with NCCL"),
+    "search_all_n32_h4096": ("search", 100_000, 4096, 3, (1, 1, 0, 0), "strong",
+                             "levenshtein_search SearchType::All, needle len=32, 100k haystacks len=4096, k=3, 1% planted hits"),
+    "search_n64_h4096": ("search", 100_000, 4096, 6, (1, 1, 0, 0), "strong",
+                         "levenshtein_search needle len=64 (Myers pre-filter), 100k haystacks len=4096, k=6, Best, 1% planted hits"),
+    "search_affine_n32_h4096": ("search", 20_000, 4096, 6, (2, 1, 3, 0), "strong",
+                                "levenshtein_search EditCosts(2,1,3,None): no pre-filter, exact (cost, length) kernel over whole "
+                                "haystacks; needle len=32, 20k haystacks len=4096, k=6, Best"),
     "hamming_len64": ("hamming", 10_000, 64, 0, (1, 1, 0, 0), "weak", "hamming, 10k pairs len=64 (plumbing case)"),
     "hamming_len4096": ("hamming", 262_144, 4096, 0, (1, 1, 0, 0), "weak", "hamming, 256Ki pairs len=4096"),
+}
+SEARCH_OPTS = {  # needle length, SearchType (0 All, 1 Best) of the search workloads
+    "search_n32_h4096": (32, 1), "search_all_n32_h4096": (32, 0), "search_n64_h4096": (64, 1),
+    "search_affine_n32_h4096": (32, 1),
 }
 HEADLINE = "lev_k8_len128"
 # the other BASELINE configs and north-star lines, reported in the `configs` array of the default line
@@ -96,16 +107,19 @@ def make_inputs(op, n, length, k, costs, seed, first=0, needle=None):
     return synth.edited_pairs(n, length, length, k, seed=seed, first=first, allow_swap=bool(costs[3]))
 
 
-def make_needle(seed):
-    return np.random.Generator(np.random.PCG64(seed)).integers(1, 256, size=32, dtype=np.uint8)
+def make_needle(seed, length=32):
+    return np.random.Generator(np.random.PCG64(seed)).integers(1, 256, size=length, dtype=np.uint8)
 
 
-def cells_per_unit(op, length, k):
+def cells_per_unit(op, length, k, needle_len=32):
     if op == "hamming":
         return length
     if op == "search":
-        return 32 * length  # needle_len x haystack_len cells of the reference's scalar search DP
+        return needle_len * length  # needle_len x haystack_len cells of the reference's scalar search DP
     return nominal_cells(length, k)
+
+
+SEARCH_TYPE = [1]  # SearchType of the search workload being measured (set by the callers from SEARCH_OPTS)
 
 
 def oracle_run(orc, op, a, ao, b, bo, k, costs, cnt, threads):
@@ -115,7 +129,7 @@ def oracle_run(orc, op, a, ao, b, bo, k, costs, cnt, threads):
     if op == "exp":
         return orc.levenshtein_exp_batch(a, ao[:cnt + 1], b, bo[:cnt + 1], costs, threads=threads)
     if op == "search":
-        m, off = orc.levenshtein_search_batch(a, b, bo[:cnt + 1], k, 1, costs, False, threads=threads)
+        m, off = orc.levenshtein_search_batch(a, b, bo[:cnt + 1], k, SEARCH_TYPE[0], costs, False, threads=threads)
         return np.concatenate([off.astype(np.uint64), m.reshape(-1)])
     return orc.levenshtein_k_batch(a, ao[:cnt + 1], b, bo[:cnt + 1], k, costs, threads=threads)
 
@@ -135,8 +149,8 @@ def reference_cpu_run(orc, op, a, ao, b, bo, k, costs, cnt, threads, length):
     if simd and op == "lev_k" and orc.lib().orc_simd_covers(length, length, k, orc.Costs(*costs)):
         return orc.levenshtein_simd_k_batch(a, ao[:cnt + 1], b, bo[:cnt + 1], k, costs, threads=threads), \
             "AVX2 restatement of levenshtein_simd_k_with_opts (Avx1x32x8 core)"
-    if simd and op == "search" and len(a) <= 32 and max(len(a) + k, k + 1) <= 255:
-        m, off = orc.levenshtein_search_simd_batch(a, b, bo[:cnt + 1], k, 1, costs, False, threads=threads)
+    if simd and op == "search" and len(a) <= 32 and max(len(a) + k, k + 1) <= 255 and tuple(costs) == (1, 1, 0, 0):
+        m, off = orc.levenshtein_search_simd_batch(a, b, bo[:cnt + 1], k, SEARCH_TYPE[0], costs, False, threads=threads)
         return np.concatenate([off.astype(np.uint64), m.reshape(-1)]), \
             "AVX2 restatement of levenshtein_search_simd_with_opts (Avx1x32x8 search core)"
     return oracle_run(orc, op, a, ao, b, bo, k, costs, cnt, threads), "scalar oracle (port of the reference's scalar routine)"
@@ -146,9 +160,11 @@ def dominant_kernel(op, k, costs, length):
     """name of the kernel the dispatcher picks for this workload (triple_accel_b200/csrc/api.cu: ta_launch_lev)"""
     if op == "hamming":
         return "hamming_kernel"
-    if op == "search":
-        return "search_pigeon_staged_kernel (+ search_wave_kernel on the flagged 128-byte sub-segments)"
     unit = tuple(costs[:3]) == (1, 1, 0) and costs[3] <= 1
+    if op == "search":
+        if not unit:
+            return "search_exact_kernel (thread per haystack, no pre-filter)"
+        return "search_pigeon_staged_kernel (+ search_wave_kernel on the flagged 128-byte sub-segments)"
     if op == "exp":
         k = 15 if costs[3] else 16  # first round of the exponential search
     kk = min(k, length)
@@ -156,7 +172,8 @@ def dominant_kernel(op, k, costs, length):
         return "lev_fr_kernel"
     band = kk + 1 + (1 if costs[3] else 0)
     if not unit or band > 64:
-        return "lev_band_kernel"
+        w_bound = (min(k, length * max(costs[0], costs[1]) + costs[2]) - costs[2]) // costs[1] + 1 + (2 if costs[3] else 0)
+        return "lev_diag16_kernel" if w_bound <= 32 else "lev_band_kernel"
     if band <= 9 and not costs[3]:
         return "lev_bitpar_duo_kernel"
     if band <= 25:
@@ -173,7 +190,7 @@ def workload_config(name, world, units_per_gpu=None):
             "l2": "inputs (%.0f MB per GPU) larger than the 126 MB L2" % (per_gpu_bytes / 1e6) if per_gpu_bytes > 126e6
             else "inputs (%.1f MB per GPU) fit in L2 (small config)" % (per_gpu_bytes / 1e6), "units_per_gpu": n if scaling == "weak" else None,
             "units_total": n * world if scaling == "weak" else n, "len": length, "k": k, "costs": list(costs),
-            "cells_per_unit": cells_per_unit(base_op(op), length, k), "scaling": scaling,
+            "cells_per_unit": cells_per_unit(base_op(op), length, k, SEARCH_OPTS.get(name, (32, 1))[0]), "scaling": scaling,
             "parallelism": "units sharded x%d" % world}
 
 
@@ -268,7 +285,8 @@ def run_reference(args, name):
     sample = min(n, ref_sample if op != "search" else max(1, ref_sample // 100))
     if op == "exp":
         sample = min(sample, 100_000)
-    needle = make_needle(1234) if op == "search" else None
+    nlen, SEARCH_TYPE[0] = SEARCH_OPTS.get(name, (32, 1))
+    needle = make_needle(1234, nlen) if op == "search" else None
     a, ao, b, bo = make_inputs(op, sample, length, k, costs, 1234, needle=needle)
     threads = ref_threads(orc)
     bop = base_op(op)
@@ -284,7 +302,7 @@ def run_reference(args, name):
     for _ in range(args.steps):
         step()
     dt = (time.perf_counter() - t0) / args.steps
-    cells = cells_per_unit(bop, length, k)
+    cells = cells_per_unit(bop, length, k, nlen)
     val = sample * cells / dt / 1e9
     line = {
         "impl": "reference", "metric": "dp_cell_updates_per_s", "value": val, "unit": "GCUPS", "n_gpus": args.gpus,
@@ -384,10 +402,12 @@ class Runner:
             if scaling == "strong":
                 first = 0
         needle = None
+        nlen, stype = SEARCH_OPTS.get(name, (32, 1))
+        SEARCH_TYPE[0] = stype
         if op == "search":
             # rank 0 alone knows the needle; the others receive it by NCCL broadcast (torch.distributed)
             from triple_accel_b200 import dist as tdist
-            mine = make_needle(1234) if rank == 0 else np.zeros(1, np.uint8)
+            mine = make_needle(1234, nlen) if rank == 0 else np.zeros(1, np.uint8)
             needle = tdist.broadcast_needle(mine) if self.dist is not None else mine
         a, ao, b, bo = make_inputs(op, n, length, k, costs, 1234, first=first, needle=needle)
         max_len = int(max((ao[1:] - ao[:-1]).max(), (bo[1:] - bo[:-1]).max())) if n else 0
@@ -405,7 +425,7 @@ class Runner:
             elif bop == "exp":
                 eng.levenshtein_exp_batch_dev(d_a, d_ao, d_b, d_bo, costs, max_len, d_out)
             elif bop == "search":
-                last["m"] = eng.levenshtein_search_batch_dev(a, d_b, d_bo, max_len, k, 1, costs, False)
+                last["m"] = eng.levenshtein_search_batch_dev(a, d_b, d_bo, max_len, k, stype, costs, False)
             else:
                 eng.levenshtein_k_batch_dev(d_a, d_ao, d_b, d_bo, k, costs, max_len, d_out)
 
@@ -446,7 +466,7 @@ class Runner:
         want = oracle_run(orc, bop, a, ao, b, bo, k, costs, chk, ref_threads(orc))
         parity_ok = bool(np.array_equal(got, want))
 
-        cells_unit = cells_per_unit(bop, length, k)
+        cells_unit = cells_per_unit(bop, length, k, nlen)
         value = total_units * cells_unit / (ms_step * 1e-3) / 1e9
         # algorithmic bytes of this rank's launch: |a| + |b| + 4 per pair (CSR offsets, +16 B/pair, not counted);
         # search: |haystack|
@@ -489,7 +509,7 @@ class Runner:
                 elif bop == "exp":
                     eng.levenshtein_exp_batch(pa, pao, pb, pbo, costs, out=pout)
                 elif bop == "search":
-                    last["m"] = eng.levenshtein_search_batch(pa, pb, pbo, k, 1, costs, False)
+                    last["m"] = eng.levenshtein_search_batch(pa, pb, pbo, k, stype, costs, False)
                 else:
                     eng.levenshtein_k_batch(pa, pao, pb, pbo, k, costs, out=pout)
 
@@ -549,7 +569,9 @@ def run_inproc(args, name):
     bop = base_op(op)
     eng = ta.Engine(devices=list(range(args.gpus)))
     lib = _ffi.load()
-    needle = make_needle(1234) if op == "search" else None
+    nlen, stype = SEARCH_OPTS.get(name, (32, 1))
+    SEARCH_TYPE[0] = stype
+    needle = make_needle(1234, nlen) if op == "search" else None
     a, ao, b, bo = make_inputs(op, n, length, k, costs, 1234, needle=needle)
     pin = Pinned(lib)
     pa, pb, pao, pbo = pin.copy(a), pin.copy(b), pin.copy(ao), pin.copy(bo)
@@ -562,7 +584,7 @@ def run_inproc(args, name):
         elif bop == "exp":
             eng.levenshtein_exp_batch(pa, pao, pb, pbo, costs, out=pout)
         elif bop == "search":
-            last["m"] = eng.levenshtein_search_batch(pa, pb, pbo, k, 1, costs, False)
+            last["m"] = eng.levenshtein_search_batch(pa, pb, pbo, k, stype, costs, False)
         else:
             eng.levenshtein_k_batch(pa, pao, pb, pbo, k, costs, out=pout)
 
@@ -580,7 +602,7 @@ def run_inproc(args, name):
         got = np.concatenate([off[:chk + 1].astype(np.uint64), m[:int(off[chk])].reshape(-1)])
     else:
         got = pout[:chk]
-    cells_unit = cells_per_unit(bop, length, k)
+    cells_unit = cells_per_unit(bop, length, k, nlen)
     h2d = int(a.nbytes + b.nbytes + ao.nbytes + bo.nbytes)
     line = {"metric": "dp_cell_updates_per_s", "mode": "inproc-multi (ta_init_multi, one host-buffer call per step)",
             "value": n * cells_unit / dt / 1e9, "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps,

@@ -273,8 +273,13 @@ class Engine:
     hamming_search = hamming_search_simd  # src/hamming.rs:588-590
 
     def _take_matches(self, mp, op, n):
+        """(matches[total, 3], match_off[n + 1]).  The offsets array (8 bytes per haystack: the large one) is a view of
+        the library's block, handed back with ta_free when the array is collected; the sparse match list is copied."""
+        import weakref
+        lib, addr = self._lib, C.cast(op, C.c_void_p).value
         try:
-            moff = np.ctypeslib.as_array(op, shape=(n + 1,)).copy()
+            moff = np.frombuffer((C.c_uint64 * (n + 1)).from_address(addr), np.uint64)
+            weakref.finalize(moff.base if moff.base is not None else moff, lib.ta_free, C.c_void_p(addr))
             total = int(moff[n])
             arr = np.zeros((total, 3), np.uint64)
             if total:
@@ -283,7 +288,6 @@ class Engine:
                 arr[:, 2] = raw[:, 2] & np.uint64(0xFFFFFFFF)
         finally:
             self._lib.ta_free(mp)
-            self._lib.ta_free(op)
         return arr, moff
 
     # ---- device-resident API (torch tensors on this engine's device) ----------------------------------------

@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(128, 9) lev_fr_kernel(const uint8_t *__restric
             const uint4 *h_a16 = a16;
             const uint2 *h_b8 = b8;
             int h_amis = 0, h_bmis = 0, h_last8 = 0, h_c = 0, h_row = 0, h_lim = 0, h_step = 128;
-            uint32_t gmask = 0xFFu << osh;
+            uint32_t gmask = 0xFFu << osh, g_boff = 0;
             for (;;) {
                 if (assign) {
                     assign = false;
@@ -253,6 +253,7 @@ __global__ void __launch_bounds__(128, 9) lev_fr_kernel(const uint8_t *__restric
                     h_c = ts.sc, h_lim = ts.slim;
                     h_row = ts.srow + 128 * boff;
                     h_step = 128 * power;
+                    g_boff = (uint32_t)boff;
                     serving = true;
                     __syncwarp();
                 }
@@ -282,6 +283,17 @@ __global__ void __launch_bounds__(128, 9) lev_fr_kernel(const uint8_t *__restric
                 const int rr = __reduce_min_sync(gmask, r_l);
                 const bool ended = rr != 0x7FFFFFFF;
                 if (ended) {
+                    // The next level resumes on the neighbouring diagonals just past row rr: its probes and the first
+                    // step of its slide read the lines that follow.  Ask L2 for them now (one 128-byte line of each
+                    // string per serving lane), so that they arrive while the round in between is computed instead of
+                    // costing that step a DRAM round trip.
+                    if (serving) {
+                        const int prow = rr + 128 * (int)(8u * g_boff + l);
+                        if (prow < h_lim + 128) {
+                            prefetch_l2_line((const uint8_t *)h_a16 + h_amis + min(prow, h_lim - 1));
+                            prefetch_l2_line((const uint8_t *)h_b8 + h_bmis + min(prow, h_lim - 1) + h_c);
+                        }
+                    }
                     if (in_slide) {
                         if (l == q) v = rr;
                         P &= P - 1u;

@@ -444,11 +444,18 @@ static int search_device(ta_ctx *ctx, cudaStream_t st, const uint8_t *d_needle, 
     uint32_t *counter = ctx->d_flags + 2;
     unsigned long long *d_count = (unsigned long long *)(ctx->d_flags + 4);
     TA_CUDA(ctx, cudaMemsetAsync(counter, 0, 4 * sizeof(uint32_t), st));  // item counter, pad, 64-bit hit counter
-    if (!no_filter && unit && needle_len <= 64 && !anchored && k < needle_len) {
+    // The pre-filters work with unit costs.  For any other cost model they run with the number of edit OPERATIONS a
+    // match can contain: an alignment of weighted cost <= k has at most ku = k / min(mismatch, gap, transpose) operations,
+    // so its end position also ends a unit-cost alignment of cost <= ku -- the flagged sub-segments are a superset of
+    // the weighted matches, and the exact kernel (which computes the real costs) decides.
+    uint32_t cmin = costs.mismatch < costs.gap ? costs.mismatch : costs.gap;
+    if (costs.transpose && costs.transpose < cmin) cmin = costs.transpose;
+    const uint32_t ku = unit ? k : k / cmin;
+    if (!no_filter && needle_len <= 64 && !anchored && ku < needle_len) {
         const uint64_t nseg = max_hay ? (max_hay + TA_SEARCH_SUB - 1) / TA_SEARCH_SUB : 1;
         if ((uint64_t)n * nseg <= 0xFFFFFFF0ull && nseg <= 65535) {
             if ((rc = ta_dev_reserve(ctx, ctx->d_work[0], n * nseg * sizeof(uint32_t))) != TA_OK) return rc;
-            rc = ta_launch_search_filter(ctx, d_needle, (uint32_t)needle_len, d_hay, d_off, n, max_hay, k,
+            rc = ta_launch_search_filter(ctx, d_needle, (uint32_t)needle_len, d_hay, d_off, n, max_hay, ku,
                                          costs.transpose != 0, (uint32_t *)ctx->d_work[0].p, counter, &segs, st);
             if (rc == TA_OK) {
                 work_n = n * nseg;
@@ -552,44 +559,56 @@ static int search_device(ta_ctx *ctx, cudaStream_t st, const uint8_t *d_needle, 
     return TA_ERR_TOO_LARGE;
 }
 
-// orders the hits by (haystack, end): LSD radix sort on the 64-bit key, 11 bits per pass, only over the bits in use
-// (a comparison sort of a few thousand 16-byte records costs more than the exact kernel that produced them)
+// orders the hits by (haystack, end): LSD radix sort on the haystack index alone (11 bits per pass, only over the bits
+// in use: two passes for up to 4 M haystacks), then each haystack's run -- a handful of hits as a rule -- by end position.
+// (A comparison sort of a few thousand 16-byte records costs more than the exact kernel that produced them; sorting
+// the full 64-bit key took three passes over 2048 counters and was a quarter of the search step.)
 static void sort_hits(std::vector<Hit> &hits) {
     const size_t n = hits.size();
     if (n < 2) return;
+    auto by_end = [](const Hit &x, const Hit &y) { return x.end < y.end; };
     if (n < 64) {
         std::sort(hits.begin(), hits.end(), [](const Hit &x, const Hit &y) {
             return x.hay != y.hay ? x.hay < y.hay : x.end < y.end;
         });
         return;
     }
-    uint32_t max_hay = 0, max_end = 0;
-    for (const Hit &h : hits) {
-        max_hay = std::max(max_hay, h.hay);
-        max_end = std::max(max_end, h.end);
-    }
-    int end_bits = 1, hay_bits = 1;
-    while (end_bits < 32 && (max_end >> end_bits)) end_bits++;
+    uint32_t max_hay = 0;
+    for (const Hit &h : hits) max_hay = std::max(max_hay, h.hay);
+    int hay_bits = 1;
     while (hay_bits < 32 && (max_hay >> hay_bits)) hay_bits++;
-    const int key_bits = end_bits + hay_bits;
-    auto key = [&](const Hit &h) { return ((uint64_t)h.hay << end_bits) | h.end; };
     std::vector<Hit> tmp(n);
     Hit *src = hits.data(), *dst = tmp.data();
     constexpr int RB = 11;
-    size_t count[1 << RB];
-    for (int shift = 0; shift < key_bits; shift += RB) {
+    uint32_t count[1 << RB];
+    for (int shift = 0; shift < hay_bits; shift += RB) {
         memset(count, 0, sizeof count);
-        for (size_t i = 0; i < n; i++) count[(key(src[i]) >> shift) & ((1u << RB) - 1)]++;
-        size_t sum = 0;
+        for (size_t i = 0; i < n; i++) count[(src[i].hay >> shift) & ((1u << RB) - 1)]++;
+        uint32_t sum = 0;
         for (int b = 0; b < (1 << RB); b++) {
-            const size_t c = count[b];
+            const uint32_t c = count[b];
             count[b] = sum;
             sum += c;
         }
-        for (size_t i = 0; i < n; i++) dst[count[(key(src[i]) >> shift) & ((1u << RB) - 1)]++] = src[i];
+        for (size_t i = 0; i < n; i++) dst[count[(src[i].hay >> shift) & ((1u << RB) - 1)]++] = src[i];
         std::swap(src, dst);
     }
     if (src != hits.data()) memcpy(hits.data(), src, n * sizeof(Hit));
+    for (size_t i = 0; i < n;) {  // runs of one haystack
+        size_t j = i + 1;
+        while (j < n && hits[j].hay == hits[i].hay) j++;
+        if (j - i > 16) {
+            std::sort(hits.begin() + i, hits.begin() + j, by_end);
+        } else {
+            for (size_t x = i + 1; x < j; x++) {  // insertion sort
+                const Hit h = hits[x];
+                size_t y = x;
+                for (; y > i && hits[y - 1].end > h.end; y--) hits[y] = hits[y - 1];
+                hits[y] = h;
+            }
+        }
+        i = j;
+    }
 }
 
 // Host phase: order the hits by (haystack, end) and apply the reference's emission rules -- the row-0 match
