@@ -90,6 +90,9 @@ int ta_init(int device, ta_ctx **out);
  * live on one device and therefore return TA_ERR_BAD_ARG on a multi-device context.  n_devices == 1 is ta_init. */
 int ta_init_multi(const int *devices, int n_devices, ta_ctx **out);
 int ta_device_count(ta_ctx *ctx);               /* devices this ctx spans */
+/* The split itself, as pure host arithmetic (no device needed): bounds_out[0 .. parts] with units bounds_out[r] ..
+ * bounds_out[r + 1] going to device r -- contiguous ranges with equal shares of the bytes (b_off may be NULL). */
+int ta_shard_bounds(const uint64_t *a_off, const uint64_t *b_off, size_t n, int parts, uint64_t *bounds_out);
 int ta_multi_uses_nccl(ta_ctx *ctx);            /* 1 = needle travels by ncclBroadcast */
 uint64_t ta_multi_needle_broadcasts(ta_ctx *ctx); /* ncclBroadcast calls issued so far */
 void ta_shutdown(ta_ctx *ctx);

@@ -49,7 +49,8 @@ def main():
         out[wl] = {"kernel": r[hdr.index("Kernel Name")].split("(")[0][:80], "units": units,
                    "warp_instructions": int(num("smsp__inst_executed.sum")),
                    "dram_bytes": int(to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum")),
-                   "time_under_ncu_us": t / (1e3 if rows[1][hdr.index("gpu__time_duration.sum")] in ("nsecond", "ns") else 1),
+                   "time_under_ncu_us": t * {"nsecond": 1e-3, "ns": 1e-3, "usecond": 1.0, "us": 1.0, "msecond": 1e3,
+                                             "ms": 1e3, "second": 1e6}.get(rows[1][hdr.index("gpu__time_duration.sum")], 1.0),
                    "source": os.path.basename(rep)}
     json.dump(out, open(os.path.join(ROOT, "profiles", "ncu_counts.json"), "w"), indent=1)
     for k, v in out.items():

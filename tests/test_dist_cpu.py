@@ -27,6 +27,39 @@ def test_shard_bounds_balanced_and_contiguous():
     assert tdist.shard_bounds(np.zeros(1, np.uint64), np.zeros(1, np.uint64), 4) == [0, 0, 0, 0, 0]
 
 
+def test_c_abi_shard_bounds_match_the_contract():
+    """ta_shard_bounds = the split ta_init_multi applies inside the library (csrc/multi.cu): contiguous, covers the batch,
+    balanced by bytes, tolerant of empty strings, empty batches and more devices than units"""
+    import ctypes as C
+    from triple_accel_b200 import _ffi
+    lib = _ffi.load()
+
+    def bounds(ao, bo, parts):
+        out = np.zeros(parts + 1, np.uint64)
+        rc = lib.ta_shard_bounds(ao.ctypes.data_as(C.c_void_p), None if bo is None else bo.ctypes.data_as(C.c_void_p),
+                                 len(ao) - 1, parts, out.ctypes.data_as(C.c_void_p))
+        assert rc == 0
+        return [int(x) for x in out]
+
+    a, ao, b, bo = synth.ragged_mutated_pairs(5000, 0, 300, 6, seed=9, templates=5000)
+    for parts in (1, 2, 3, 8):
+        bd = bounds(ao, bo, parts)
+        assert bd[0] == 0 and bd[-1] == 5000 and all(x <= y for x, y in zip(bd, bd[1:]))
+        total = int(ao[-1] + bo[-1])
+        shares = [int(ao[bd[r + 1]] - ao[bd[r]] + bo[bd[r + 1]] - bo[bd[r]]) for r in range(parts)]
+        assert max(shares) - min(shares) <= 2 * 600 + total // 1000, (parts, shares)   # within a pair or two of equal
+    lens = np.array([10] * 50 + [10000] + [10] * 49, np.uint64)     # one huge string must not starve the others
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    assert 45 <= bounds(off, off, 2)[1] <= 52
+    z = np.zeros(1, np.uint64)
+    assert bounds(z, z, 4) == [0, 0, 0, 0, 0]                       # empty batch
+    e = np.zeros(8, np.uint64)
+    assert bounds(e, e, 3) == [0, 2, 4, 7]                           # all-empty strings: balanced by count
+    two = np.array([0, 5, 9], np.uint64)
+    bd = bounds(two, None, 8)                                        # more devices than units
+    assert bd[0] == 0 and bd[-1] == 2 and all(x <= y for x, y in zip(bd, bd[1:]))
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

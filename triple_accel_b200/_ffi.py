@@ -41,6 +41,7 @@ SIGNATURES = {
     "ta_init": (_int, [_int, C.POINTER(_vp)]),
     "ta_init_multi": (_int, [C.POINTER(_int), _int, C.POINTER(_vp)]),
     "ta_device_count": (_int, [_vp]),
+    "ta_shard_bounds": (_int, [_vp, _vp, _sz, _int, _vp]),
     "ta_multi_uses_nccl": (_int, [_vp]),
     "ta_multi_needle_broadcasts": (C.c_uint64, [_vp]),
     "ta_trim": (None, []),

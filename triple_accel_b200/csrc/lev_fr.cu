@@ -285,10 +285,11 @@ __global__ void __launch_bounds__(128, 9) lev_fr_kernel(const uint8_t *__restric
                 if (ended) {
                     // The next level resumes on the neighbouring diagonals just past row rr: its probes and the first
                     // step of its slide read the lines that follow.  Ask L2 for them now (one 128-byte line of each
-                    // string per serving lane), so that they arrive while the round in between is computed instead of
-                    // costing that step a DRAM round trip.
-                    if (serving) {
-                        const int prow = rr + 128 * (int)(8u * g_boff + l);
+                    // string from two lanes of every serving octet; all eight lanes fetched 1.8x the algorithmic bytes), so
+                    // that they arrive while the round in between is computed instead of costing that step a DRAM round
+                    // trip.
+                    if (serving && l < 2u) {  // two lines per serving octet: 256 .. 1024 bytes ahead of rr
+                        const int prow = rr + 128 * (int)(2u * g_boff + l);
                         if (prow < h_lim + 128) {
                             prefetch_l2_line((const uint8_t *)h_a16 + h_amis + min(prow, h_lim - 1));
                             prefetch_l2_line((const uint8_t *)h_b8 + h_bmis + min(prow, h_lim - 1) + h_c);

@@ -272,6 +272,15 @@ int ta_init_multi(const int *devices, int n_devices, ta_ctx **out) {
 
 int ta_device_count(ta_ctx *ctx) { return ctx ? ta_multi_size(ctx) : 0; }
 
+/* The split a multi-device context applies to a batch (pure host arithmetic, no device needed). */
+int ta_shard_bounds(const uint64_t *a_off, const uint64_t *b_off, size_t n, int parts, uint64_t *bounds_out) {
+    if (!a_off || !bounds_out || parts < 1) return TA_ERR_BAD_ARG;
+    std::vector<size_t> bound;
+    shard_bounds(a_off, b_off, n, parts, bound);
+    for (int r = 0; r <= parts; r++) bounds_out[r] = bound[r];
+    return TA_OK;
+}
+
 /* 1 when the needle of a multi-device search travels by ncclBroadcast, 0 when it is copied host-to-device per device */
 int ta_multi_uses_nccl(ta_ctx *ctx) { return ctx && ctx->multi && ctx->multi->nccl && !ctx->multi->comms.empty() ? 1 : 0; }
 uint64_t ta_multi_needle_broadcasts(ta_ctx *ctx) { return ctx && ctx->multi ? ctx->multi->needle_bcasts : 0; }
