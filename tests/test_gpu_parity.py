@@ -739,6 +739,7 @@ SEARCH_TESTS = ("test_search_random or test_search_planted or test_kat_search or
     ({"TA_FR": "1"}, FR_TESTS),
     ({"TA_DIAG16": "1"}, LEV_TESTS + " or test_lev_diag16_large_batch"),
     ({"TA_DIAG16": "1", "TA_FORCE_BAND": "1"}, LEV_TESTS),
+    ({"TA_DIAG16": "1", "TA_DIAG16_STAGES": "1"}, "test_lev_diag16_large_batch or test_lev_k_mutated"),
     ({"TA_DIAG16": "0"}, "test_lev_diag16_large_batch"),
     ({"TA_FR": "0"}, "test_lev_fr_long_strings"),
     ({"TA_BITPAR": "simd"}, LEV_TESTS),
@@ -758,7 +759,7 @@ SEARCH_TESTS = ("test_search_random or test_search_planted or test_kat_search or
     ({"TA_SEARCH_FILTER": "pigeon"}, SEARCH_TESTS),
     ({"TA_SEARCH_FILTER": "pigeon", "TA_PIGEON_STAGED": "0"}, SEARCH_TESTS),
 ], ids=["general-band-kernel", "diagonal-extension-kernel-forced", "u16-thread-per-pair-kernel-forced", "u16-thread-per-pair-kernel-on-unit-costs",
-        "u16-thread-per-pair-kernel-off", "diagonal-extension-kernel-off", "bitpar-simd-kernel", "bitpar-sliding-table-kernel",
+        "u16-thread-per-pair-kernel-single-stage", "u16-thread-per-pair-kernel-off", "diagonal-extension-kernel-off", "bitpar-simd-kernel", "bitpar-sliding-table-kernel",
         "bitpar-sliding-table-32bit-on-narrow-bands", "bitpar-block-table-one-pair-per-thread", "length-bucketing-pre-pass", "bitpar-block-table-256-entries",
         "bitpar-block-table-8-blocks", "bitpar-block-table-256-entries-8-blocks",
         "bitpar-table-2plane-kernel", "search-thread-kernel-nofilter", "search-wave-kernel-nofilter",

@@ -36,31 +36,51 @@
 
 namespace {
 
+// `defer` (may be null): pairs whose own band does not fit 4 NR diagonals are appended to defer[1 ..] (count in
+// defer[0]) instead of being computed; `n_dev` (may be null): the number of work items lives on the device.
 template <int NR, bool AFFINE, bool TRANS>
-__global__ void __launch_bounds__(128) lev_diag16_kernel(const BandArgs args) {
-    const size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= args.n) return;
-    const size_t pair = args.idx ? (size_t)args.idx[w] : args.pair_base + w;
-    const uint64_t a0 = args.a_off[pair], a1 = args.a_off[pair + 1];
-    const uint64_t b0 = args.b_off[pair], b1 = args.b_off[pair + 1];
-    args.out[pair] = diag16::pair<NR, AFFINE, TRANS>(args.a + a0, a1 - a0, args.b + b0, b1 - b0, args.k, args.mism,
-                                                     args.gap, args.sgap, args.tcost);
+__global__ void __launch_bounds__(128) lev_diag16_kernel(const BandArgs args, uint32_t *__restrict__ defer,
+                                                         const uint32_t *__restrict__ n_dev) {
+    const size_t n = n_dev ? (size_t)*n_dev : args.n;
+    for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < n; w += (size_t)gridDim.x * blockDim.x) {
+        const size_t pair = args.idx ? (size_t)args.idx[w] : args.pair_base + w;
+        const uint64_t a0 = args.a_off[pair], a1 = args.a_off[pair + 1];
+        const uint64_t b0 = args.b_off[pair], b1 = args.b_off[pair + 1];
+        const uint32_t d = diag16::pair<NR, AFFINE, TRANS>(args.a + a0, a1 - a0, args.b + b0, b1 - b0, args.k, args.mism,
+                                                           args.gap, args.sgap, args.tcost);
+        if (d == diag16::TOO_WIDE && defer)
+            defer[1 + atomicAdd(defer, 1u)] = (uint32_t)pair;
+        else
+            args.out[pair] = d;
+    }
 }
 
 template <int NR>
-int launch_nr(ta_ctx *ctx, const BandArgs &args, bool affine, bool trans, cudaStream_t st) {
-    const unsigned blocks = (unsigned)((args.n + 127) / 128);
+int launch_nr(ta_ctx *ctx, const BandArgs &args, bool affine, bool trans, uint32_t *defer, const uint32_t *n_dev,
+              cudaStream_t st) {
+    // a thread per work item; with a device-side count the grid is a few waves of persistent threads
+    const size_t want = (args.n + 127) / 128;
+    const unsigned blocks = (unsigned)(n_dev ? std::min<size_t>(want, (size_t)ctx->sm_count * 4) : want);
     if (affine && trans)
-        lev_diag16_kernel<NR, true, true><<<blocks, 128, 0, st>>>(args);
+        lev_diag16_kernel<NR, true, true><<<blocks, 128, 0, st>>>(args, defer, n_dev);
     else if (affine)
-        lev_diag16_kernel<NR, true, false><<<blocks, 128, 0, st>>>(args);
+        lev_diag16_kernel<NR, true, false><<<blocks, 128, 0, st>>>(args, defer, n_dev);
     else if (trans)
-        lev_diag16_kernel<NR, false, true><<<blocks, 128, 0, st>>>(args);
+        lev_diag16_kernel<NR, false, true><<<blocks, 128, 0, st>>>(args, defer, n_dev);
     else
-        lev_diag16_kernel<NR, false, false><<<blocks, 128, 0, st>>>(args);
+        lev_diag16_kernel<NR, false, false><<<blocks, 128, 0, st>>>(args, defer, n_dev);
     ctx->launches++;
     TA_CUDA(ctx, cudaGetLastError());
     return TA_OK;
+}
+
+int launch_by_width(ta_ctx *ctx, const BandArgs &args, bool affine, bool trans, uint32_t W, uint32_t *defer,
+                    const uint32_t *n_dev, cudaStream_t st) {
+    if (W <= 8) return launch_nr<2>(ctx, args, affine, trans, defer, n_dev, st);
+    if (W <= 12) return launch_nr<3>(ctx, args, affine, trans, defer, n_dev, st);
+    if (W <= 16) return launch_nr<4>(ctx, args, affine, trans, defer, n_dev, st);
+    if (W <= 24) return launch_nr<6>(ctx, args, affine, trans, defer, n_dev, st);
+    return launch_nr<8>(ctx, args, affine, trans, defer, n_dev, st);
 }
 
 }  // namespace
@@ -78,11 +98,27 @@ bool ta_diag16_can_handle(size_t n, uint32_t k, ta_costs c, uint32_t max_len, ui
     return n >= 16384;  // a thread per pair: small batches are better off with a lane group per pair
 }
 
+// The register count follows the band.  W bounds the band of ANY pair of the batch (strings of very different lengths
+// need the most diagonals: W = diff + 2 e + 1 with e shrinking as diff grows), W0 is the band of a pair of EQUAL lengths
+// (+ 1 for small differences).  When W0 needs fewer registers than W, the batch runs with the smaller count and the
+// few pairs whose own band is wider are collected on the device and re-run with the larger one in a second, tiny
+// launch (no host round trip: it reads the count from the device) -- 25 % less work per pair on `affine_k16_len128`.
 int ta_launch_lev_diag16(ta_ctx *ctx, const BandArgs &args, ta_costs costs, uint32_t W, cudaStream_t st) {
     const bool affine = costs.start_gap != 0, trans = costs.transpose != 0;
-    if (W <= 8) return launch_nr<2>(ctx, args, affine, trans, st);
-    if (W <= 12) return launch_nr<3>(ctx, args, affine, trans, st);
-    if (W <= 16) return launch_nr<4>(ctx, args, affine, trans, st);
-    if (W <= 24) return launch_nr<6>(ctx, args, affine, trans, st);
-    return launch_nr<8>(ctx, args, affine, trans, st);
+    static const bool two_stage = !(getenv("TA_DIAG16_STAGES") && atoi(getenv("TA_DIAG16_STAGES")) == 1);
+    const uint32_t kk = args.k;  // (the batch bound already clamped W; W0 only needs k and the costs)
+    const uint64_t spare = kk >= 2u * costs.start_gap ? kk - 2u * costs.start_gap : 0u;
+    uint64_t W0 = 2 * (spare / (2u * costs.gap)) + 1 + (trans ? 2 : 0) + 1;
+    auto regs = [](uint64_t w) { return w <= 8 ? 2 : w <= 12 ? 3 : w <= 16 ? 4 : w <= 24 ? 6 : 8; };
+    if (!two_stage || W0 >= W || regs(W0) == regs(W) || args.n > 0xFFFFFFF0ull)
+        return launch_by_width(ctx, args, affine, trans, W, nullptr, nullptr, st);
+    int rc = ta_dev_reserve(ctx, ctx->d_work[2], (args.n + 1) * sizeof(uint32_t));
+    if (rc != TA_OK) return rc;
+    uint32_t *defer = (uint32_t *)ctx->d_work[2].p;
+    TA_CUDA(ctx, cudaMemsetAsync(defer, 0, sizeof(uint32_t), st));
+    if ((rc = launch_by_width(ctx, args, affine, trans, (uint32_t)W0, defer, nullptr, st)) != TA_OK) return rc;
+    BandArgs second = args;
+    second.idx = defer + 1;
+    second.pair_base = 0;
+    return launch_by_width(ctx, second, affine, trans, W, nullptr, defer, st);
 }

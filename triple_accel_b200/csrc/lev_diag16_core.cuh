@@ -19,6 +19,7 @@ namespace diag16 {
 
 constexpr uint32_t CAP2 = 0x7FFF7FFFu;
 constexpr uint32_t NONE = 0xFFFFFFFFu;
+constexpr uint32_t TOO_WIDE = 0xFFFFFFFEu;  // pair<NR> was asked for a band of more than 4 NR diagonals (never a distance)
 
 D16_HD uint32_t d16_addmin(uint32_t a, uint32_t b, uint32_t c) {  // per half: min(a + b, c)
 #if defined(__CUDA_ARCH__)
@@ -142,6 +143,7 @@ D16_HD uint32_t pair(const uint8_t *pa, uint64_t la, const uint8_t *pb, uint64_t
         const uint32_t d = (uint32_t)n * gap + (n ? sgap : 0u);
         return d <= bi.max_k ? d : NONE;
     }
+    if (bi.W > 4 * NR) return TOO_WIDE;  // the caller re-runs the pair with more registers (lev_diag16.cu)
     const int dlo = bi.dlo;  // <= 0; the host guarantees bi.W <= 4 NR and max_k < 0x7F00
     const uint32_t MM = mism * 0x10001u, GG = gap * 0x10001u, OO = (sgap + gap) * 0x10001u, TT = tcost * 0x10001u;
 

@@ -23,6 +23,10 @@
 //    of their own serve the others' (block j of every `power` blocks: a warp with one long slide moves 512 bytes
 //    of each string per step); measured lane utilisation of the slide loop went from 11 to ~27 of 32 lanes.
 //  Algorithmic bytes per pair: |a| + |b| + 4 (every byte on the alignment's path is read once).
+//  Tried and dropped (round 2, profiles/README.md): a lane per pair with one-byte probes and the octet serving its eight
+//  lanes' slides -- rounds become ~20 instructions per diagonal of one lane, but a lane's probes are a serial chain of
+//  scattered global loads (one L2 round trip per diagonal) and the lanes of a warp are rarely in the same phase
+//  (4 of 32 lanes active in the probe loop): 1.74 ms / 1.94 ms with queued slides against 1.10 ms for this form.
 #include <stdlib.h>
 
 #include <algorithm>
@@ -339,6 +343,7 @@ __global__ void __launch_bounds__(128, 9) lev_fr_kernel(const uint8_t *__restric
     }
 }
 
+
 }  // namespace
 
 // Largest min(k, max_len) this kernel takes (the level arrays live in shared memory: 2 (2 k + 3) words per octet)
@@ -367,14 +372,14 @@ int ta_launch_lev_fr(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const
                      cudaStream_t st) {
     if (n == 0) return TA_OK;
     const uint32_t kk = k < max_len ? k : max_len;
+    static const int env_per_sm = getenv("TA_FR_CTAS") ? atoi(getenv("TA_FR_CTAS")) : 0;
+    const int nt = 128;
     // 2 kk + 3 slots, rounded so that an octet's two arrays are 16-byte aligned and successive octets start 8 banks apart
     uint32_t slots_pad = (2u * kk + 3u + 3u) & ~3u;
     while ((2u * slots_pad) % 32u != 8u) slots_pad += 4u;
-    const int nt = 128;
     const size_t smem = (size_t)(nt / 8) * (2u * slots_pad * sizeof(int) + sizeof(FrSlot));
     auto kern = costs.transpose ? lev_fr_kernel<true> : lev_fr_kernel<false>;
     // persistent octets: exactly as many CTAs as are resident at once (a second, partial wave would leave SMs idle)
-    static const int env_per_sm = getenv("TA_FR_CTAS") ? atoi(getenv("TA_FR_CTAS")) : 0;
     int per_sm = 0;
     TA_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nt, smem));
     if (per_sm < 1) per_sm = 1;
