@@ -1,0 +1,50 @@
+"""Small invocation of every kernel added in round 2, for compute-sanitizer runs:
+    compute-sanitizer --tool memcheck  python scripts/sanitize_round2.py
+    compute-sanitizer --tool racecheck python scripts/sanitize_round2.py
+Tight numpy arrays (no slack after the last string) on purpose: the kernels must not read past a string's last aligned
+word.  Results are checked against the oracle as well (test infrastructure)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import _oracle as orc  # noqa: E402
+import triple_accel_b200 as ta  # noqa: E402
+from triple_accel_b200 import synth  # noqa: E402
+
+eng = ta.Engine(0)
+# diagonal-extension kernel (long strings; transpositions; a 2-letter alphabet = many cooperative slides)
+for alpha, costs in ((256, (1, 1, 0, 0)), (2, (1, 1, 0, 1)), (4, (1, 1, 0, 0))):
+    a, ao, b, bo = synth.edited_pairs(300, 1024, 2300, 12, seed=alpha, allow_swap=True, alphabet=alpha)
+    for k in (3, 16):
+        got = eng.levenshtein_k_batch(a, ao, b, bo, k, costs)
+        assert np.array_equal(got, orc.levenshtein_k_batch(a, ao, b, bo, k, costs, threads=4)), ("fr", alpha, k)
+    assert np.array_equal(eng.levenshtein_exp_batch(a, ao, b, bo, costs), orc.levenshtein_exp_batch(a, ao, b, bo, costs, threads=4))
+# thread-per-pair u16 kernel (>= 16384 pairs): affine, transpositions, two-stage register count, ragged incl. empty
+a, ao, b, bo = synth.edited_pairs(17000, 0, 90, 8, seed=5, allow_swap=True, alphabet=4)
+for costs, k in (((2, 1, 3, 0), 16), ((2, 2, 1, 3), 9), ((1, 1, 0, 1), 6), ((5, 4, 3, 0), 30)):
+    got = eng.levenshtein_k_batch(a, ao, b, bo, k, costs)
+    assert np.array_equal(got, orc.levenshtein_k_batch(a, ao, b, bo, k, costs, threads=4)), ("diag16", costs, k)
+# search: weighted costs through the pre-filter, long needle on the global-rows kernel
+needle, hay, hoff = synth.needle_haystacks(200, 3000, 32, plant_frac=0.2, max_edits=3, seed=9)
+for costs in ((2, 1, 3, 0), (2, 2, 1, 3)):
+    got, goff = eng.levenshtein_search_batch(needle, hay, hoff, 6, 1, costs)
+    want, woff = orc.levenshtein_search_batch(needle, hay, hoff, 6, 1, costs, threads=4)
+    assert np.array_equal(goff, woff) and np.array_equal(got, want), ("search weighted", costs)
+rng = np.random.default_rng(3)
+long_needle = rng.integers(1, 5, size=500, dtype=np.uint8)
+hay = rng.integers(1, 5, size=40 * 1500, dtype=np.uint8)
+hay[3000:3500] = long_needle
+hoff = synth.fixed_offsets(40, 1500)
+got, goff = eng.levenshtein_search_batch(long_needle, hay, hoff, 30, 1)
+want, woff = orc.levenshtein_search_batch(long_needle, hay, hoff, 30, 1, threads=4)
+assert np.array_equal(goff, woff) and np.array_equal(got, want), "search long needle"
+# traceback grouped by distance (k = u32::MAX on long strings)
+a, ao, b, bo = synth.edited_pairs(40, 600, 1500, 6, seed=11)
+dist, edits, eoff = eng.levenshtein_k_trace_batch(a, ao, b, bo, 0xFFFFFFFF, (1, 1, 0, 0))
+assert np.array_equal(dist, orc.levenshtein_k_batch(a, ao, b, bo, 0xFFFFFFFF, threads=4))
+print("sanitize_round2 ok: %d launches" % eng.launch_count)
+eng.close()
