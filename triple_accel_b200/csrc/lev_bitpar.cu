@@ -777,6 +777,164 @@ __global__ void __launch_bounds__(256) search_pigeon_staged_kernel(const uint8_t
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// search_qgram_kernel (round 2): the exact-piece filter at memory speed, for pieces of >= 7 bytes.
+// The shift-and scan above looks at EVERY haystack byte (8.3 instructions per byte: the kernel is issue-bound at a
+// third of the HBM rate).  But a piece of l >= 7 bytes that occurs exactly in the haystack covers at least one
+// 4-byte-ALIGNED word of memory completely, wherever it lies, and that word is one of the l - 3 four-byte substrings
+// ("4-grams") of the piece.  So it is enough to look at the aligned words: hash each one into a 64 Kbit shared-memory
+// bitmap of the needle's 4-grams (all pieces, all offsets: a few dozen entries), i.e. ~2 instructions per haystack
+// byte, with the haystacks streamed as ONE flat byte range by coalesced 16-byte loads -- no per-haystack work items,
+// no staging.  A bitmap hit (a real piece word, or one false positive per ~3000 words) is compared with the 4-gram
+// list; each exact match names the piece and the offset, hence where the piece would end, and the same bounded Myers
+// verification as above confirms the match ends this occurrence allows.  Confirmed ends flag their 128-byte
+// sub-segment exactly once (a global bitmap with atomicOr de-duplicates across threads and pieces).
+// Coverage: an alignment with <= k edits leaves one of the k + 1 (2k + 1) pieces intact; the intact piece contains an
+// aligned word; that word is in the bitmap; its verification window holds the match.
+struct QGram {
+    uint32_t gram;    // the four bytes, little endian as loaded from memory
+    uint16_t to_end;  // bytes from the word's first byte to the piece's last byte
+    uint16_t fin;     // needle index of the piece's last byte
+};
+constexpr uint32_t QG_BITS = 1u << 16;
+constexpr int QG_MAX = 64;
+constexpr int QG_UNROLL = 4;
+
+__device__ __forceinline__ uint32_t qg_hash(uint32_t x) { return (x * 0x9E3779B1u) >> 16; }
+
+template <bool TRANS>
+__global__ void __launch_bounds__(256, 4) search_qgram_kernel(const uint8_t *__restrict__ needle, uint32_t N,
+                                                           const uint8_t *__restrict__ hay,
+                                                           const uint64_t *__restrict__ hay_off, size_t n, uint32_t k,
+                                                           uint32_t pieces, uint32_t subs,
+                                                           uint32_t *__restrict__ sub_flags,
+                                                           uint32_t *__restrict__ idx_out,
+                                                           uint32_t *__restrict__ counter) {
+    __shared__ uint32_t bitmap[QG_BITS / 32];
+    __shared__ uint32_t peq[256];
+    __shared__ QGram grams[QG_MAX];
+    __shared__ uint32_t n_grams;
+    for (uint32_t q = threadIdx.x; q < QG_BITS / 32; q += blockDim.x) bitmap[q] = 0;
+    for (uint32_t q = threadIdx.x; q < 256; q += blockDim.x) peq[q] = 0;
+    if (threadIdx.x == 0) n_grams = 0;
+    __syncthreads();
+    for (uint32_t q = threadIdx.x; q < N; q += blockDim.x) atomicOr(&peq[needle[q]], 1u << q);
+    if (threadIdx.x == 0) {  // the 4-grams of every piece (a few dozen: one thread)
+        const uint32_t base_len = N / pieces, extra = N % pieces;
+        uint32_t cnt = 0;
+        for (uint32_t i = 0, s0 = 0; i < pieces; i++) {
+            const uint32_t l = base_len + (i < extra ? 1u : 0u);
+            for (uint32_t o = 0; o + 4 <= l && cnt < (uint32_t)QG_MAX; o++) {
+                const uint32_t g = (uint32_t)needle[s0 + o] | ((uint32_t)needle[s0 + o + 1] << 8) |
+                                   ((uint32_t)needle[s0 + o + 2] << 16) | ((uint32_t)needle[s0 + o + 3] << 24);
+                grams[cnt].gram = g, grams[cnt].to_end = (uint16_t)(l - 1 - o), grams[cnt].fin = (uint16_t)(s0 + l - 1);
+                const uint32_t hsh = qg_hash(g);
+                bitmap[hsh >> 5] |= 1u << (hsh & 31u);
+                cnt++;
+            }
+            s0 += l;
+        }
+        n_grams = cnt;
+    }
+    __syncthreads();
+    if (n == 0) return;
+    const uint64_t B0 = hay_off[0], B1 = hay_off[n];
+    if (B1 - B0 < 4) return;
+    // aligned words that lie fully inside the haystack bytes: word index j = address / 4, [first_w, end_w)
+    const uintptr_t abase = (uintptr_t)hay;
+    const uint64_t first_w = (abase + B0 + 3) >> 2, end_w = (abase + B1) >> 2;
+
+    // a word at flat offset g that hit the bitmap: which piece words it equals, and what those occurrences allow
+    auto candidate = [&](const uint32_t word, const uint64_t g) {
+        const uint32_t ng = n_grams;
+        bool any = false;
+        for (uint32_t j = 0; j < ng; j++) any |= grams[j].gram == word;
+        if (!any) return;
+        size_t lo = 0, hi = n;  // the haystack that holds byte g: largest h with hay_off[h] <= g
+        while (hi - lo > 1) {
+            const size_t mid = lo + (hi - lo) / 2;
+            if (hay_off[mid] <= g)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        const size_t h = lo;
+        const uint64_t h0 = hay_off[h], H = hay_off[h + 1] - h0;
+        const uint8_t *p = hay + h0;
+        const uint64_t x = g - h0;
+        for (uint32_t j = 0; j < ng; j++) {
+            if (grams[j].gram != word) continue;
+            const uint64_t q = x + grams[j].to_end;  // haystack index of the piece's last byte
+            const uint32_t fin = grams[j].fin;
+            if (q >= H) continue;          // the piece would run past the haystack (the word straddles two haystacks)
+            const uint32_t r = N - 1 - fin;  // needle bytes after the piece
+            // end byte indices of matches through this occurrence: [q + r - k, q + r + k]
+            uint64_t elo = q + r > k ? q + r - k : 0, ehi = q + r + k;
+            if (ehi > H - 1) ehi = H - 1;
+            if (elo > ehi) continue;
+            const uint64_t st = q + 1 > (uint64_t)fin + 1 + k ? q + 1 - (fin + 1 + k) : 0;
+            uint32_t VP = 0xffffffffu, VN = 0, D0prev = 0xffffffffu, Eqprev = 0, score = N;
+            const uint32_t top = 1u << (N - 1);
+            for (uint64_t t = st; t <= ehi; t++) {
+                const uint32_t Eq = peq[p[t]];
+                uint32_t D0 = (((Eq & VP) + VP) ^ VP) | Eq | VN;
+                if (TRANS) {
+                    D0 |= ((~D0prev & Eq) << 1) & Eqprev;
+                    D0prev = D0;
+                    Eqprev = Eq;
+                }
+                uint32_t HP = VN | ~(D0 | VP);
+                uint32_t HN = D0 & VP;
+                score += (HP & top) ? 1u : 0u;
+                score -= (HN & top) ? 1u : 0u;
+                HP <<= 1;
+                HN <<= 1;
+                VP = HN | ~(D0 | HP);
+                VN = D0 & HP;
+                if (t >= elo && score <= k) {
+                    const uint64_t code = (uint64_t)h * subs + t / TA_SEARCH_SUB;
+                    const uint32_t bit = 1u << (code & 31u);
+                    if (!(atomicOr(&sub_flags[code >> 5], bit) & bit)) idx_out[atomicAdd(counter, 1u)] = (uint32_t)code;
+                }
+            }
+        }
+    };
+    auto probe = [&](const uint32_t word, const uint64_t widx) {
+        const uint32_t hsh = qg_hash(word);
+        if (bitmap[hsh >> 5] >> (hsh & 31u) & 1u) candidate(word, (widx << 2) - abase);
+    };
+
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (uint64_t)gridDim.x * blockDim.x;
+    // body: 16-byte vectors [v0, v1), each four aligned words; head and tail words one by one
+    const uint64_t v0 = (first_w + 3) >> 2, v1 = end_w >> 2;
+    auto ldw = [](uint64_t wi) { return __ldg(reinterpret_cast<const uint32_t *>(wi << 2)); };  // wi = address / 4
+    if (v0 < v1) {
+        // QG_UNROLL independent 16-byte loads in flight per thread: the scan is pure latency otherwise (one load, then
+        // ~20 dependent instructions; measured 1.8 TB/s with one load per thread and 44 % of the warps resident)
+        auto ldv = [](uint64_t v) { return __ldg(reinterpret_cast<const uint4 *>(v << 4)); };  // v = address / 16
+        auto probe4 = [&](const uint4 x, const uint64_t v) {
+            probe(x.x, 4 * v);
+            probe(x.y, 4 * v + 1);
+            probe(x.z, 4 * v + 2);
+            probe(x.w, 4 * v + 3);
+        };
+        uint64_t v = v0 + tid;
+        for (; v + (QG_UNROLL - 1) * nthreads < v1; v += QG_UNROLL * nthreads) {
+            uint4 x[QG_UNROLL];
+#pragma unroll
+            for (int u = 0; u < QG_UNROLL; u++) x[u] = ldv(v + u * nthreads);
+#pragma unroll
+            for (int u = 0; u < QG_UNROLL; u++) probe4(x[u], v + u * nthreads);
+        }
+        for (; v < v1; v += nthreads) probe4(ldv(v), v);
+        for (uint64_t wi = first_w + tid; wi < 4 * v0; wi += nthreads) probe(ldw(wi), wi);
+        for (uint64_t wi = 4 * v1 + tid; wi < end_w; wi += nthreads) probe(ldw(wi), wi);
+    } else {
+        for (uint64_t wi = first_w + tid; wi < end_w; wi += nthreads) probe(ldw(wi), wi);
+    }
+}
+
 }  // namespace
 
 // appends the codes (haystack * subs + sub-segment, unordered) of the TA_SEARCH_SUB-byte haystack sub-segments that
@@ -799,6 +957,36 @@ int ta_launch_search_filter(ta_ctx *ctx, const uint8_t *needle_dev, uint32_t nee
     bool pigeon = needle_len <= 32 && pieces <= needle_len && needle_len / pieces >= PIGEON_MIN_PIECE;
     if (force && force[0] == 'm') pigeon = false;
     if (force && force[0] == 'p' && needle_len <= 32 && pieces <= needle_len) pigeon = true;
+    // pieces of >= 7 bytes: aligned-word sampling at memory speed (TA_SEARCH_FILTER=pigeon|myers keep the others testable)
+    bool qgram = needle_len <= 32 && pieces <= needle_len && needle_len / pieces >= 7 &&
+                 pieces * (needle_len / pieces + 1 - 3) <= (uint32_t)QG_MAX;
+    if (force && force[0] != 'q') qgram = false;
+    if (qgram) {
+        const uint64_t nbits = (uint64_t)n * subs;
+        const size_t words = (size_t)((nbits + 31) / 32);
+        int rc = ta_dev_reserve(ctx, ctx->d_work[2], words * sizeof(uint32_t));
+        if (rc != TA_OK) return rc;
+        uint32_t *sub_flags = (uint32_t *)ctx->d_work[2].p;
+        TA_CUDA(ctx, cudaMemsetAsync(sub_flags, 0, words * sizeof(uint32_t), st));
+        static int occ[2] = {0, 0};  // one wave of resident CTAs: the scan is a grid-stride loop
+        if (!occ[transpose]) {
+            int o = 0;
+            if (transpose)
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, search_qgram_kernel<true>, 256, 0);
+            else
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, search_qgram_kernel<false>, 256, 0);
+            occ[transpose] = o > 0 ? o : 1;
+        }
+        static const int env_ctas = getenv("TA_QGRAM_CTAS") ? atoi(getenv("TA_QGRAM_CTAS")) : 0;
+        const unsigned blocks = (unsigned)ctx->sm_count * (unsigned)(env_ctas > 0 ? env_ctas : occ[transpose]);
+        if (transpose)
+            search_qgram_kernel<true><<<blocks, 256, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, k, pieces, (uint32_t)subs, sub_flags, idx_out, counter);
+        else
+            search_qgram_kernel<false><<<blocks, 256, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, k, pieces, (uint32_t)subs, sub_flags, idx_out, counter);
+        ctx->launches++;
+        TA_CUDA(ctx, cudaGetLastError());
+        return TA_OK;
+    }
     if (pigeon) {
         // 256-thread blocks: the 32 KB bank-replicated table is shared by 8 warps (TA_PIGEON_THREADS overrides)
         static const int env_pt = getenv("TA_PIGEON_THREADS") ? atoi(getenv("TA_PIGEON_THREADS")) : 0;
