@@ -120,6 +120,7 @@ def cells_per_unit(op, length, k, needle_len=32):
 
 
 SEARCH_TYPE = [1]  # SearchType of the search workload being measured (set by the callers from SEARCH_OPTS)
+SEARCH_NEEDLE = [32]  # its needle length
 
 
 def oracle_run(orc, op, a, ao, b, bo, k, costs, cnt, threads):
@@ -164,7 +165,14 @@ def dominant_kernel(op, k, costs, length):
     if op == "search":
         if not unit:
             return "search_exact_kernel (thread per haystack, no pre-filter)"
-        return "search_pigeon_staged_kernel (+ search_wave_kernel on the flagged 128-byte sub-segments)"
+        nlen = SEARCH_NEEDLE[0]
+        pieces = (2 * k + 1) if costs[3] else (k + 1)
+        forced = os.environ.get("TA_SEARCH_FILTER", "")
+        if nlen <= 32 and pieces <= nlen and nlen // pieces >= 7 and forced in ("", "qgram"):
+            return "search_qgram_kernel (+ search_qgram_resolve_kernel, search_wave_kernel on the flagged 128-byte sub-segments)"
+        if nlen <= 32 and pieces <= nlen and nlen // pieces >= 4 and forced != "myers":
+            return "search_pigeon_staged_kernel (+ search_wave_kernel on the flagged 128-byte sub-segments)"
+        return "search_filter_kernel (+ search_wave_kernel on the flagged 128-byte sub-segments)"
     if op == "exp":
         k = 15 if costs[3] else 16  # first round of the exponential search
     kk = min(k, length)
@@ -286,6 +294,7 @@ def run_reference(args, name):
     if op == "exp":
         sample = min(sample, 100_000)
     nlen, SEARCH_TYPE[0] = SEARCH_OPTS.get(name, (32, 1))
+    SEARCH_NEEDLE[0] = nlen
     needle = make_needle(1234, nlen) if op == "search" else None
     a, ao, b, bo = make_inputs(op, sample, length, k, costs, 1234, needle=needle)
     threads = ref_threads(orc)
@@ -404,6 +413,7 @@ class Runner:
         needle = None
         nlen, stype = SEARCH_OPTS.get(name, (32, 1))
         SEARCH_TYPE[0] = stype
+        SEARCH_NEEDLE[0] = nlen
         if op == "search":
             # rank 0 alone knows the needle; the others receive it by NCCL broadcast (torch.distributed)
             from triple_accel_b200 import dist as tdist
@@ -571,6 +581,7 @@ def run_inproc(args, name):
     lib = _ffi.load()
     nlen, stype = SEARCH_OPTS.get(name, (32, 1))
     SEARCH_TYPE[0] = stype
+    SEARCH_NEEDLE[0] = nlen
     needle = make_needle(1234, nlen) if op == "search" else None
     a, ao, b, bo = make_inputs(op, n, length, k, costs, 1234, needle=needle)
     pin = Pinned(lib)

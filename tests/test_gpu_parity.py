@@ -534,6 +534,31 @@ def test_search_filter_long_needles_and_transpositions(eng):
                 assert np.array_equal(goff, woff) and np.array_equal(got, want), (nlen, costs, k)
 
 
+def test_search_qgram_filter(eng):
+    """the aligned-word (4-gram) pre-filter: needles whose k + 1 (2k + 1) pieces are >= 7 bytes.  Alphabets of 2 / 4
+    symbols make every word a candidate (the queue, the whole-piece compare and the verification do the work; big
+    batches overflow the queue and take the shift-and fallback), 256 symbols is the case it is built for; haystacks
+    are ragged, start at every alignment, and include empty and shorter-than-a-word ones."""
+    rng = random.Random(1717)
+    for nlen, k, costs in ((14, 1, (1, 1, 0, 0)), (21, 2, (1, 1, 0, 0)), (32, 3, (1, 1, 0, 0)), (28, 3, (1, 1, 0, 0)),
+                           (32, 1, (1, 1, 0, 1)), (21, 1, (1, 1, 0, 1)), (32, 6, (2, 2, 0, 0)), (30, 0, (1, 1, 0, 0))):
+        for alpha in (2, 4, 256):
+            needle = bytes(rng.randrange(alpha) for _ in range(nlen))
+            hays = [b"", b"ab", needle, needle[1:], needle + needle]
+            for _ in range(300):
+                h = bytearray(rng.randrange(alpha) for _ in range(rng.randrange(0, 700)))
+                for _ in range(rng.randrange(0, 3)):
+                    if len(h) > nlen + 2:
+                        pos = rng.randrange(len(h) - nlen)
+                        h[pos:pos + nlen] = _mutate(rng, needle, rng.randrange(0, 5), alpha)[:nlen]
+                hays.append(bytes(h))
+            hay, hoff = _pack(hays)
+            for st in (0, 1):
+                got, goff = eng.levenshtein_search_batch(needle, hay, hoff, k, st, costs)
+                want, woff = orc.levenshtein_search_batch(needle, hay, hoff, k, st, costs, threads=8)
+                assert np.array_equal(goff, woff) and np.array_equal(got, want), (nlen, k, costs, alpha, st)
+
+
 @pytest.mark.parametrize("nlen", [257, 301, 453, 1000])
 @pytest.mark.parametrize("costs", [(1, 1, 0, 0), (1, 1, 1, 1)], ids=str)
 def test_search_long_needles(eng, nlen, costs):
@@ -730,7 +755,7 @@ def test_cpp_header_mirror(tmp_path):
 
 LEV_TESTS = "test_lev_k_mutated or test_lev_k_random_short or test_nul_bytes or test_lev_exp"
 FR_TESTS = LEV_TESTS + " or test_lev_fr_long_strings or test_lev_full_matrix"
-SEARCH_TESTS = ("test_search_random or test_search_planted or test_kat_search or "
+SEARCH_TESTS = ("test_search_random or test_search_planted or test_kat_search or test_search_qgram_filter or "
                 "test_search_filter_long_needles_and_transpositions or test_search_segment_warmup")
 
 
@@ -758,13 +783,14 @@ SEARCH_TESTS = ("test_search_random or test_search_planted or test_kat_search or
     ({"TA_SEARCH_FILTER": "myers"}, SEARCH_TESTS),
     ({"TA_SEARCH_FILTER": "pigeon"}, SEARCH_TESTS),
     ({"TA_SEARCH_FILTER": "pigeon", "TA_PIGEON_STAGED": "0"}, SEARCH_TESTS),
+    ({"TA_QGRAM_QCAP": "1"}, SEARCH_TESTS),
 ], ids=["general-band-kernel", "diagonal-extension-kernel-forced", "u16-thread-per-pair-kernel-forced", "u16-thread-per-pair-kernel-on-unit-costs",
         "u16-thread-per-pair-kernel-single-stage", "u16-thread-per-pair-kernel-off", "diagonal-extension-kernel-off", "bitpar-simd-kernel", "bitpar-sliding-table-kernel",
         "bitpar-sliding-table-32bit-on-narrow-bands", "bitpar-block-table-one-pair-per-thread", "length-bucketing-pre-pass", "bitpar-block-table-256-entries",
         "bitpar-block-table-8-blocks", "bitpar-block-table-256-entries-8-blocks",
         "bitpar-table-2plane-kernel", "search-thread-kernel-nofilter", "search-wave-kernel-nofilter",
         "search-thread-kernel-filter", "search-global-rows-kernel-nofilter", "search-myers-filter-forced", "search-pigeonhole-filter-forced",
-        "search-pigeonhole-filter-lane-per-segment-loads"])
+        "search-pigeonhole-filter-lane-per-segment-loads", "search-qgram-filter-gives-up-and-falls-back"])
 def test_every_kernel_variant_forced(env, select):
     """The dispatchers pick a kernel from the cost model, band width and batch size (bit-parallel vs general banded
     kernel; pre-filter + warp-wavefront vs thread-per-haystack exact search).  These switches force the variants

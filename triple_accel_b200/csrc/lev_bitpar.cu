@@ -623,7 +623,10 @@ __global__ void __launch_bounds__(256) search_pigeon_staged_kernel(const uint8_t
                                                                    const uint64_t *__restrict__ hay_off, size_t n,
                                                                    uint32_t k, uint32_t pieces, uint32_t subs,
                                                                    uint32_t segs, uint32_t *__restrict__ idx_out,
-                                                                   uint32_t *__restrict__ counter) {
+                                                                   uint32_t *__restrict__ counter,
+                                                                   const uint32_t *__restrict__ only_if) {
+    // queued behind search_qgram_kernel as its fallback: runs only if that kernel gave up (flag set on the device)
+    if (only_if && *only_if == 0) return;
     extern __shared__ __align__(16) uint8_t pg_smem[];
     uint32_t *peqr = (uint32_t *)pg_smem;  // [256][32]
     for (uint32_t q = threadIdx.x; q < 256u * 32u; q += blockDim.x) peqr[q] = 0;
@@ -779,63 +782,105 @@ __global__ void __launch_bounds__(256) search_pigeon_staged_kernel(const uint8_t
 
 
 // ---------------------------------------------------------------------------------------------------------------------
-// search_qgram_kernel (round 2): the exact-piece filter at memory speed, for pieces of >= 7 bytes.
-// The shift-and scan above looks at EVERY haystack byte (8.3 instructions per byte: the kernel is issue-bound at a
-// third of the HBM rate).  But a piece of l >= 7 bytes that occurs exactly in the haystack covers at least one
-// 4-byte-ALIGNED word of memory completely, wherever it lies, and that word is one of the l - 3 four-byte substrings
-// ("4-grams") of the piece.  So it is enough to look at the aligned words: hash each one into a 64 Kbit shared-memory
-// bitmap of the needle's 4-grams (all pieces, all offsets: a few dozen entries), i.e. ~2 instructions per haystack
-// byte, with the haystacks streamed as ONE flat byte range by coalesced 16-byte loads -- no per-haystack work items,
-// no staging.  A bitmap hit (a real piece word, or one false positive per ~3000 words) is compared with the 4-gram
-// list; each exact match names the piece and the offset, hence where the piece would end, and the same bounded Myers
-// verification as above confirms the match ends this occurrence allows.  Confirmed ends flag their 128-byte
-// sub-segment exactly once (a global bitmap with atomicOr de-duplicates across threads and pieces).
+// search_qgram_kernel + search_qgram_resolve_kernel (round 2): the exact-piece filter at memory speed, for pieces of
+// >= 7 bytes.  The shift-and scan above looks at EVERY haystack byte (8.3 instructions per byte: the kernel is
+// issue-bound at a third of the HBM rate).  But a piece of l >= 7 bytes that occurs exactly in the haystack covers at
+// least one 4-byte-ALIGNED word of memory completely, wherever it lies, and that word is one of the l - 3 four-byte
+// substrings ("4-grams") of the piece.  So it is enough to look at the aligned words: hash each one into a 256 Kbit
+// shared-memory bitmap of the needle's 4-grams (all pieces, all offsets: a few dozen entries), ~2 instructions per
+// haystack byte, with the haystacks streamed as ONE flat byte range by coalesced 16-byte loads -- no per-haystack work
+// items, no staging.  A bitmap hit (a real piece word, or one false positive per ~13 000 words) is compared with the
+// 4-gram list; an exact match is QUEUED (flat offset + word) and the scan goes on.  The resolve kernel takes one queue
+// entry per thread: finds the haystack, compares the whole piece, and runs the same bounded Myers verification as above
+// over the match ends this occurrence allows; confirmed ends flag their 128-byte sub-segment exactly once (a global
+// bitmap with atomicOr de-duplicates across threads and pieces).  (Resolving inline was the first form: a planted
+// needle gives ~7 gram hits in one or two lanes of ONE warp, ~10 us of dependent loads each, and the scan waited 70 us
+// for the slowest warps -- SMSP active cycles min 121 k / avg 193 k / max 342 k.)
+// Low-entropy input (DNA, text: common 4-grams everywhere) would drown the queue; when it overflows the scan sets a
+// flag and stops, the resolve kernel does nothing, and the shift-and kernel queued behind them (`only_if`) does the
+// job instead -- same output contract, no host round trip.
 // Coverage: an alignment with <= k edits leaves one of the k + 1 (2k + 1) pieces intact; the intact piece contains an
-// aligned word; that word is in the bitmap; its verification window holds the match.
+// aligned word; that word is in the bitmap and the list; its verification window holds the match.
 struct QGram {
-    uint32_t gram;    // the four bytes, little endian as loaded from memory
-    uint16_t to_end;  // bytes from the word's first byte to the piece's last byte
-    uint16_t fin;     // needle index of the piece's last byte
+    uint32_t gram;  // the four bytes, little endian as loaded from memory
+    uint8_t off;    // offset of the word in its piece
+    uint8_t len;    // piece length
+    uint16_t fin;   // needle index of the piece's last byte
 };
-constexpr uint32_t QG_BITS = 1u << 16;
+struct QCand {
+    uint64_t g;  // flat byte offset of the word (from `hay`)
+    uint32_t word;
+    uint32_t pad;
+};
+constexpr uint32_t QG_LOG = 18;  // 256 Kbit = 32 KB of shared memory
+constexpr uint32_t QG_BITS = 1u << QG_LOG;
 constexpr int QG_MAX = 64;
 constexpr int QG_UNROLL = 4;
 
-__device__ __forceinline__ uint32_t qg_hash(uint32_t x) { return (x * 0x9E3779B1u) >> 16; }
+__device__ __forceinline__ uint32_t qg_mul(uint32_t x) { return x * 0x9E3779B1u; }  // hash = top QG_LOG bits
 
-template <bool TRANS>
-__global__ void __launch_bounds__(256, 4) search_qgram_kernel(const uint8_t *__restrict__ needle, uint32_t N,
-                                                           const uint8_t *__restrict__ hay,
-                                                           const uint64_t *__restrict__ hay_off, size_t n, uint32_t k,
-                                                           uint32_t pieces, uint32_t subs,
-                                                           uint32_t *__restrict__ sub_flags,
-                                                           uint32_t *__restrict__ idx_out,
-                                                           uint32_t *__restrict__ counter) {
-    __shared__ uint32_t bitmap[QG_BITS / 32];
-    __shared__ uint32_t peq[256];
-    __shared__ QGram grams[QG_MAX];
-    __shared__ uint32_t n_grams;
-    for (uint32_t q = threadIdx.x; q < QG_BITS / 32; q += blockDim.x) bitmap[q] = 0;
-    for (uint32_t q = threadIdx.x; q < 256; q += blockDim.x) peq[q] = 0;
-    if (threadIdx.x == 0) n_grams = 0;
-    __syncthreads();
-    for (uint32_t q = threadIdx.x; q < N; q += blockDim.x) atomicOr(&peq[needle[q]], 1u << q);
-    if (threadIdx.x == 0) {  // the 4-grams of every piece (a few dozen: one thread)
-        const uint32_t base_len = N / pieces, extra = N % pieces;
-        uint32_t cnt = 0;
-        for (uint32_t i = 0, s0 = 0; i < pieces; i++) {
-            const uint32_t l = base_len + (i < extra ? 1u : 0u);
-            for (uint32_t o = 0; o + 4 <= l && cnt < (uint32_t)QG_MAX; o++) {
-                const uint32_t g = (uint32_t)needle[s0 + o] | ((uint32_t)needle[s0 + o + 1] << 8) |
-                                   ((uint32_t)needle[s0 + o + 2] << 16) | ((uint32_t)needle[s0 + o + 3] << 24);
-                grams[cnt].gram = g, grams[cnt].to_end = (uint16_t)(l - 1 - o), grams[cnt].fin = (uint16_t)(s0 + l - 1);
-                const uint32_t hsh = qg_hash(g);
-                bitmap[hsh >> 5] |= 1u << (hsh & 31u);
-                cnt++;
-            }
-            s0 += l;
+// the 4-grams of every piece, in a fixed order (both kernels build the same list); returns their number
+__device__ __forceinline__ uint32_t qg_build(const uint8_t *nd, uint32_t N, uint32_t pieces, QGram *grams) {
+    const uint32_t base_len = N / pieces, extra = N % pieces;
+    uint32_t cnt = 0;
+    for (uint32_t i = 0, s0 = 0; i < pieces; i++) {
+        const uint32_t l = base_len + (i < extra ? 1u : 0u);
+        for (uint32_t o = 0; o + 4 <= l && cnt < (uint32_t)QG_MAX; o++) {
+            grams[cnt].gram = (uint32_t)nd[s0 + o] | ((uint32_t)nd[s0 + o + 1] << 8) | ((uint32_t)nd[s0 + o + 2] << 16) |
+                              ((uint32_t)nd[s0 + o + 3] << 24);
+            grams[cnt].off = (uint8_t)o, grams[cnt].len = (uint8_t)l, grams[cnt].fin = (uint16_t)(s0 + l - 1);
+            cnt++;
         }
-        n_grams = cnt;
+        s0 += l;
+    }
+    return cnt;
+}
+
+struct QGramShared {
+    uint32_t bitmap[QG_BITS / 32];
+    QGram grams[QG_MAX];
+    uint32_t n_grams;
+    uint8_t needle[32];
+};
+
+// a word that hit the bitmap: if it really is one of the 4-grams, queue it.  Out of line: it runs for one word in ~10^4
+// and the scan loop around it must stay small (inlined 16 times it made the kernel 110 KB of SASS, every probe its own
+// reconvergence region, and the scan ran at a quarter of the issue rate with `no_instruction` / `wait` stalls).
+// Returns false when the queue is full (the caller stops scanning).
+__device__ __noinline__ bool qgram_push(const QGramShared &sh, const uint32_t word, const uint64_t g, QCand *__restrict__ queue,
+                                        uint32_t *__restrict__ qcount, const uint32_t qcap, uint32_t *__restrict__ gave_up) {
+    const uint32_t ng = sh.n_grams;
+    bool any = false;
+    for (uint32_t j = 0; j < ng; j++) any |= sh.grams[j].gram == word;
+    if (!any) return true;
+    const uint32_t slot = atomicAdd(qcount, 1u);
+    if (slot >= qcap) {
+        *gave_up = 1u;
+        return false;
+    }
+    QCand c;
+    c.g = g, c.word = word, c.pad = 0;
+    queue[slot] = c;
+    return true;
+}
+
+__global__ void __launch_bounds__(256, 6) search_qgram_kernel(const uint8_t *__restrict__ needle, uint32_t N,
+                                                              const uint8_t *__restrict__ hay,
+                                                              const uint64_t *__restrict__ hay_off, size_t n,
+                                                              uint32_t pieces, QCand *__restrict__ queue,
+                                                              uint32_t *__restrict__ qcount, uint32_t qcap,
+                                                              uint32_t *__restrict__ gave_up) {
+    __shared__ QGramShared sh;
+    for (uint32_t q = threadIdx.x; q < QG_BITS / 32; q += blockDim.x) sh.bitmap[q] = 0;
+    if (threadIdx.x < 32) sh.needle[threadIdx.x] = threadIdx.x < N ? needle[threadIdx.x] : 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {  // a few dozen entries: one thread, needle bytes from shared memory
+        const uint32_t cnt = qg_build(sh.needle, N, pieces, sh.grams);
+        for (uint32_t j = 0; j < cnt; j++) {
+            const uint32_t hsh = qg_mul(sh.grams[j].gram) >> (32 - QG_LOG);
+            sh.bitmap[hsh >> 5] |= 1u << (hsh & 31u);
+        }
+        sh.n_grams = cnt;
     }
     __syncthreads();
     if (n == 0) return;
@@ -845,13 +890,90 @@ __global__ void __launch_bounds__(256, 4) search_qgram_kernel(const uint8_t *__r
     const uintptr_t abase = (uintptr_t)hay;
     const uint64_t first_w = (abase + B0 + 3) >> 2, end_w = (abase + B1) >> 2;
 
-    // a word at flat offset g that hit the bitmap: which piece words it equals, and what those occurrences allow
-    auto candidate = [&](const uint32_t word, const uint64_t g) {
-        const uint32_t ng = n_grams;
-        bool any = false;
-        for (uint32_t j = 0; j < ng; j++) any |= grams[j].gram == word;
-        if (!any) return;
-        size_t lo = 0, hi = n;  // the haystack that holds byte g: largest h with hay_off[h] <= g
+    // bit 0 of the result = the word is in the bitmap (branch-free: ~7 instructions, independent across words)
+    auto test = [&](const uint32_t word) {
+        const uint32_t m = qg_mul(word);
+        return sh.bitmap[m >> (32 - QG_LOG + 5)] >> ((m >> (32 - QG_LOG)) & 31u);
+    };
+    auto ldw = [](uint64_t wi) { return __ldg(reinterpret_cast<const uint32_t *>(wi << 2)); };  // wi = address / 4
+    auto ldv = [](uint64_t v) { return __ldg(reinterpret_cast<const uint4 *>(v << 4)); };       // v = address / 16
+    auto slow = [&](const uint64_t wi) {  // one word, rare: test again and follow up
+        const uint32_t word = ldw(wi);
+        if (test(word) & 1u) return qgram_push(sh, word, (wi << 2) - abase, queue, qcount, qcap, gave_up);
+        return true;
+    };
+
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (uint64_t)gridDim.x * blockDim.x;
+    // body: 16-byte vectors [v0, v1), each four aligned words; head and tail words one by one.  QG_UNROLL independent
+    // 16-byte loads are in flight per thread and their 16 bitmap tests are OR-ed into one flag: one branch per 64 bytes.
+    const uint64_t v0 = (first_w + 3) >> 2, v1 = end_w >> 2;
+    bool go = true;
+    if (v0 < v1) {
+        uint64_t v = v0 + tid;
+        for (; go && v + (QG_UNROLL - 1) * nthreads < v1; v += QG_UNROLL * nthreads) {
+            uint4 x[QG_UNROLL];
+#pragma unroll
+            for (int u = 0; u < QG_UNROLL; u++) x[u] = ldv(v + u * nthreads);
+            uint32_t any = 0;
+#pragma unroll
+            for (int u = 0; u < QG_UNROLL; u++) any |= test(x[u].x) | test(x[u].y) | test(x[u].z) | test(x[u].w);
+            if (any & 1u) {
+#pragma unroll 1
+                for (int u = 0; u < QG_UNROLL; u++)
+#pragma unroll 1
+                    for (int i = 0; i < 4; i++) go = go && slow(4 * (v + u * nthreads) + i);
+            }
+        }
+        for (; go && v < v1; v += nthreads)
+#pragma unroll 1
+            for (int i = 0; i < 4; i++) go = go && slow(4 * v + i);
+        for (uint64_t wi = first_w + tid; go && wi < 4 * v0; wi += nthreads) go = slow(wi);
+        for (uint64_t wi = 4 * v1 + tid; go && wi < end_w; wi += nthreads) go = slow(wi);
+    } else {
+        for (uint64_t wi = first_w + tid; go && wi < end_w; wi += nthreads) go = slow(wi);
+    }
+}
+
+// one queued word per thread: which haystack, which pieces, and what the occurrence allows
+template <bool TRANS>
+__global__ void __launch_bounds__(128) search_qgram_resolve_kernel(const uint8_t *__restrict__ needle, uint32_t N,
+                                                                   const uint8_t *__restrict__ hay,
+                                                                   const uint64_t *__restrict__ hay_off, size_t n,
+                                                                   uint32_t k, uint32_t pieces, uint32_t subs,
+                                                                   const QCand *__restrict__ queue,
+                                                                   const uint32_t *__restrict__ qcount,
+                                                                   const uint32_t *__restrict__ gave_up,
+                                                                   uint32_t *__restrict__ sub_flags,
+                                                                   uint32_t *__restrict__ idx_out,
+                                                                   uint32_t *__restrict__ counter) {
+    if (*gave_up) return;
+    __shared__ uint32_t peq[256];
+    __shared__ QGram grams[QG_MAX];
+    __shared__ uint8_t nd[32];
+    __shared__ uint32_t n_grams;
+    for (uint32_t q = threadIdx.x; q < 256; q += blockDim.x) peq[q] = 0;
+    if (threadIdx.x < 32) nd[threadIdx.x] = threadIdx.x < N ? needle[threadIdx.x] : 0;
+    __syncthreads();
+    if (threadIdx.x < N) atomicOr(&peq[nd[threadIdx.x]], 1u << threadIdx.x);
+    if (threadIdx.x == 0) n_grams = qg_build(nd, N, pieces, grams);
+    __syncthreads();
+    const uint32_t total = *qcount, ng = n_grams;
+    const uint64_t B0 = hay_off[0], span = hay_off[n] - B0;
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const uint64_t g = queue[e].g;
+        const uint32_t word = queue[e].word;
+        // the haystack that holds byte g (largest h with hay_off[h] <= g): interpolate, then bisect what is left
+        size_t lo = 0, hi = n;
+        {
+            const size_t est = (size_t)(((unsigned __int128)(g - B0) * n) / (span ? span : 1));
+            const size_t e0 = est < n ? est : n - 1;
+            if (hay_off[e0] <= g) {
+                lo = e0;
+                if (hay_off[e0 + 1] > g) hi = e0 + 1;
+            } else {
+                hi = e0;
+            }
+        }
         while (hi - lo > 1) {
             const size_t mid = lo + (hi - lo) / 2;
             if (hay_off[mid] <= g)
@@ -865,9 +987,14 @@ __global__ void __launch_bounds__(256, 4) search_qgram_kernel(const uint8_t *__r
         const uint64_t x = g - h0;
         for (uint32_t j = 0; j < ng; j++) {
             if (grams[j].gram != word) continue;
-            const uint64_t q = x + grams[j].to_end;  // haystack index of the piece's last byte
-            const uint32_t fin = grams[j].fin;
-            if (q >= H) continue;          // the piece would run past the haystack (the word straddles two haystacks)
+            const uint32_t off = grams[j].off, len = grams[j].len, fin = grams[j].fin;
+            if (x < off) continue;            // the piece would start before the haystack
+            const uint64_t q = x - off + len - 1;  // haystack index of the piece's last byte
+            if (q >= H) continue;             // ... or run past it (the word straddles two haystacks)
+            uint32_t diff = 0;                // the rest of the piece
+            for (uint32_t i = 0; i < len; i++)
+                if (i < off || i >= off + 4) diff |= (uint32_t)p[x - off + i] ^ (uint32_t)nd[fin + 1 - len + i];
+            if (diff) continue;
             const uint32_t r = N - 1 - fin;  // needle bytes after the piece
             // end byte indices of matches through this occurrence: [q + r - k, q + r + k]
             uint64_t elo = q + r > k ? q + r - k : 0, ehi = q + r + k;
@@ -899,39 +1026,6 @@ __global__ void __launch_bounds__(256, 4) search_qgram_kernel(const uint8_t *__r
                 }
             }
         }
-    };
-    auto probe = [&](const uint32_t word, const uint64_t widx) {
-        const uint32_t hsh = qg_hash(word);
-        if (bitmap[hsh >> 5] >> (hsh & 31u) & 1u) candidate(word, (widx << 2) - abase);
-    };
-
-    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (uint64_t)gridDim.x * blockDim.x;
-    // body: 16-byte vectors [v0, v1), each four aligned words; head and tail words one by one
-    const uint64_t v0 = (first_w + 3) >> 2, v1 = end_w >> 2;
-    auto ldw = [](uint64_t wi) { return __ldg(reinterpret_cast<const uint32_t *>(wi << 2)); };  // wi = address / 4
-    if (v0 < v1) {
-        // QG_UNROLL independent 16-byte loads in flight per thread: the scan is pure latency otherwise (one load, then
-        // ~20 dependent instructions; measured 1.8 TB/s with one load per thread and 44 % of the warps resident)
-        auto ldv = [](uint64_t v) { return __ldg(reinterpret_cast<const uint4 *>(v << 4)); };  // v = address / 16
-        auto probe4 = [&](const uint4 x, const uint64_t v) {
-            probe(x.x, 4 * v);
-            probe(x.y, 4 * v + 1);
-            probe(x.z, 4 * v + 2);
-            probe(x.w, 4 * v + 3);
-        };
-        uint64_t v = v0 + tid;
-        for (; v + (QG_UNROLL - 1) * nthreads < v1; v += QG_UNROLL * nthreads) {
-            uint4 x[QG_UNROLL];
-#pragma unroll
-            for (int u = 0; u < QG_UNROLL; u++) x[u] = ldv(v + u * nthreads);
-#pragma unroll
-            for (int u = 0; u < QG_UNROLL; u++) probe4(x[u], v + u * nthreads);
-        }
-        for (; v < v1; v += nthreads) probe4(ldv(v), v);
-        for (uint64_t wi = first_w + tid; wi < 4 * v0; wi += nthreads) probe(ldw(wi), wi);
-        for (uint64_t wi = 4 * v1 + tid; wi < end_w; wi += nthreads) probe(ldw(wi), wi);
-    } else {
-        for (uint64_t wi = first_w + tid; wi < end_w; wi += nthreads) probe(ldw(wi), wi);
     }
 }
 
@@ -961,48 +1055,60 @@ int ta_launch_search_filter(ta_ctx *ctx, const uint8_t *needle_dev, uint32_t nee
     bool qgram = needle_len <= 32 && pieces <= needle_len && needle_len / pieces >= 7 &&
                  pieces * (needle_len / pieces + 1 - 3) <= (uint32_t)QG_MAX;
     if (force && force[0] != 'q') qgram = false;
+    const uint32_t *only_if = nullptr;  // set when the shift-and kernel below is only the q-gram scan's fallback
     if (qgram) {
         const uint64_t nbits = (uint64_t)n * subs;
         const size_t words = (size_t)((nbits + 31) / 32);
-        int rc = ta_dev_reserve(ctx, ctx->d_work[2], words * sizeof(uint32_t));
+        // queue: one entry per exact 4-gram match; a few per real occurrence on high-entropy input.  More than one per
+        // 1024 haystack words means common 4-grams (text, DNA): give up and let the shift-and kernel do it.
+        static const long env_cap = getenv("TA_QGRAM_QCAP") ? atol(getenv("TA_QGRAM_QCAP")) : 0;  // testing: force the fallback
+        const uint64_t total_bytes = (uint64_t)n * max_hay;  // upper bound of the flat range
+        const uint32_t qcap = env_cap > 0 ? (uint32_t)env_cap : (uint32_t)std::min<uint64_t>(total_bytes / 4096 + 4096, 1u << 24);
+        const size_t flag_bytes = (words * sizeof(uint32_t) + 15) & ~(size_t)15;
+        int rc = ta_dev_reserve(ctx, ctx->d_work[2], flag_bytes + (size_t)qcap * sizeof(QCand));
         if (rc != TA_OK) return rc;
         uint32_t *sub_flags = (uint32_t *)ctx->d_work[2].p;
+        QCand *queue = (QCand *)((uint8_t *)ctx->d_work[2].p + flag_bytes);
+        uint32_t *qcount = ctx->d_flags + 16, *gave_up = ctx->d_flags + 17;
         TA_CUDA(ctx, cudaMemsetAsync(sub_flags, 0, words * sizeof(uint32_t), st));
-        static int occ[2] = {0, 0};  // one wave of resident CTAs: the scan is a grid-stride loop
-        if (!occ[transpose]) {
+        TA_CUDA(ctx, cudaMemsetAsync(qcount, 0, 2 * sizeof(uint32_t), st));
+        static int occ = 0;  // one wave of resident CTAs: the scan is a grid-stride loop
+        if (!occ) {
             int o = 0;
-            if (transpose)
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, search_qgram_kernel<true>, 256, 0);
-            else
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, search_qgram_kernel<false>, 256, 0);
-            occ[transpose] = o > 0 ? o : 1;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, search_qgram_kernel, 256, 0);
+            occ = o > 0 ? o : 1;
         }
         static const int env_ctas = getenv("TA_QGRAM_CTAS") ? atoi(getenv("TA_QGRAM_CTAS")) : 0;
-        const unsigned blocks = (unsigned)ctx->sm_count * (unsigned)(env_ctas > 0 ? env_ctas : occ[transpose]);
-        if (transpose)
-            search_qgram_kernel<true><<<blocks, 256, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, k, pieces, (uint32_t)subs, sub_flags, idx_out, counter);
-        else
-            search_qgram_kernel<false><<<blocks, 256, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, k, pieces, (uint32_t)subs, sub_flags, idx_out, counter);
+        const unsigned blocks = (unsigned)ctx->sm_count * (unsigned)(env_ctas > 0 ? env_ctas : occ);
+        search_qgram_kernel<<<blocks, 256, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, pieces, queue, qcount, qcap, gave_up);
         ctx->launches++;
         TA_CUDA(ctx, cudaGetLastError());
-        return TA_OK;
+        const unsigned rblocks = (unsigned)std::min<uint64_t>(((uint64_t)qcap + 127) / 128, (uint64_t)ctx->sm_count * 8);
+        if (transpose)
+            search_qgram_resolve_kernel<true><<<rblocks, 128, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, k, pieces, (uint32_t)subs, queue, qcount, gave_up, sub_flags, idx_out, counter);
+        else
+            search_qgram_resolve_kernel<false><<<rblocks, 128, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, k, pieces, (uint32_t)subs, queue, qcount, gave_up, sub_flags, idx_out, counter);
+        ctx->launches++;
+        TA_CUDA(ctx, cudaGetLastError());
+        only_if = gave_up;  // the staged shift-and kernel below runs only if the scan gave up
+        pigeon = true;
     }
     if (pigeon) {
         // 256-thread blocks: the 32 KB bank-replicated table is shared by 8 warps (TA_PIGEON_THREADS overrides)
         static const int env_pt = getenv("TA_PIGEON_THREADS") ? atoi(getenv("TA_PIGEON_THREADS")) : 0;
         const int pt = env_pt ? env_pt : 256;
         static const int staged = getenv("TA_PIGEON_STAGED") ? atoi(getenv("TA_PIGEON_STAGED")) : 1;
-        if (staged) {  // coalesced cp.async rows through shared memory (default); TA_PIGEON_STAGED=0 = lane-per-segment loads
+        if (staged || only_if) {  // coalesced cp.async rows through shared memory (default); TA_PIGEON_STAGED=0 = lane-per-segment loads
             const size_t items = n * (size_t)segs;
             const size_t warps = (items + 31) / 32;
             const unsigned blocks = (unsigned)((warps + (pt / 32) - 1) / (pt / 32));
             const size_t smem = 256 * 32 * sizeof(uint32_t) + (size_t)(pt / 32) * 2 * 32 * PIGEON_ROW;
             if (transpose) {
                 TA_CUDA(ctx, cudaFuncSetAttribute(search_pigeon_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                search_pigeon_staged_kernel<true><<<blocks, pt, smem, st>>>(needle_dev, needle_len, hay, hay_off, n, k, pieces, (uint32_t)subs, (uint32_t)segs, idx_out, counter);
+                search_pigeon_staged_kernel<true><<<blocks, pt, smem, st>>>(needle_dev, needle_len, hay, hay_off, n, k, pieces, (uint32_t)subs, (uint32_t)segs, idx_out, counter, only_if);
             } else {
                 TA_CUDA(ctx, cudaFuncSetAttribute(search_pigeon_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                search_pigeon_staged_kernel<false><<<blocks, pt, smem, st>>>(needle_dev, needle_len, hay, hay_off, n, k, pieces, (uint32_t)subs, (uint32_t)segs, idx_out, counter);
+                search_pigeon_staged_kernel<false><<<blocks, pt, smem, st>>>(needle_dev, needle_len, hay, hay_off, n, k, pieces, (uint32_t)subs, (uint32_t)segs, idx_out, counter, only_if);
             }
             ctx->launches++;
             TA_CUDA(ctx, cudaGetLastError());

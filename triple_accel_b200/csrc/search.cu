@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "ta_common.cuh"
+#include "search_emit.hpp"  // Hit, sort_hits, emit_matches: the host phase (plain C++, also compiled by the CPU tests)
 
 // implemented in lev_bitpar.cu: flags[i] = 1 iff haystack i has an end position with unit-cost distance <= k
 int ta_launch_search_filter(ta_ctx *ctx, const uint8_t *needle_dev, uint32_t needle_len, const uint8_t *hay,
@@ -28,10 +29,6 @@ int ta_launch_search_filter(ta_ctx *ctx, const uint8_t *needle_dev, uint32_t nee
                             uint32_t *idx_out, uint32_t *counter, uint32_t *segs_out, cudaStream_t st);
 
 namespace {
-
-struct Hit {  // one reported end position (string lengths are < 2^22, TA_MAX_STRING_LEN)
-    uint32_t hay, end, len, cost;
-};
 
 struct SearchArgs {
     const uint8_t *needle;  // device copy
@@ -238,24 +235,25 @@ __global__ void __launch_bounds__(128) search_wave_kernel(const SearchArgs args)
     const uint32_t mism = args.mism, gap = args.gap, sgap = args.sgap, tcost = args.tcost, k = args.k;
     const uint32_t open = sgap + gap;
     const bool anchored = args.anchored != 0;
-    // Segment mode (unanchored only): the column state at x depends on at most 2N + start_gap/gap + 2 earlier
-    // haystack bytes (an optimal alignment of a needle prefix of length j ending at x costs <= j*gap + start_gap,
-    // so it consumes <= 2j + start_gap/gap haystack bytes, and every tied candidate of the reference's length
-    // tie-breaks lies on such a path); a fresh start `warm` bytes before the segment therefore reproduces the
-    // reference's (cost, length) for every end position inside the segment.
-    uint64_t col0 = 0, emit_from = 0;  // columns are numbered from col0; hits are reported for x > emit_from
+    // Segment mode (unanchored only): only cells of cost <= k are reported, a cell of cost c is decided by
+    // predecessors of cost <= c (costs are non-negative), and a path of cost c to needle row j consumes at most
+    // j + c/gap haystack bytes -- so every candidate that wins or ties in the reference's length tie-breaks lies
+    // within N + k/gap bytes of the end position, and the candidates a restarted DP sees too expensively lose in both
+    // runs: a fresh start `warm` = N + k/gap + 2 bytes before the segment reproduces the reference's (cost, length)
+    // for every reported end position inside it (tests/test_search_restart_model.py pins the margin on the CPU).
+    uint32_t col0 = 0, emit_from = 0;  // columns are numbered from col0; hits are reported for x + col0 > emit_from
     if (args.segs) {
-        const uint64_t seg = code % args.segs;
-        emit_from = seg * TA_SEARCH_SUB;
-        const uint64_t seg_end = emit_from + TA_SEARCH_SUB < H ? emit_from + TA_SEARCH_SUB : H;
+        const uint32_t seg = code % args.segs;
+        emit_from = seg * (uint32_t)TA_SEARCH_SUB;
+        const uint64_t seg_end = (uint64_t)emit_from + TA_SEARCH_SUB < H ? (uint64_t)emit_from + TA_SEARCH_SUB : H;
         col0 = emit_from > args.warm ? emit_from - args.warm : 0;
         hay += col0;
         H = seg_end - col0;
     }
-    uint64_t iter_len = H;  // src/levenshtein.rs:1650-1661
+    uint32_t iter_len = (uint32_t)H;  // src/levenshtein.rs:1650-1661 (H <= 0xFFFFFF00: checked by the host)
     if (anchored) {
         const uint64_t lim = (uint64_t)N + (uint64_t)((k > sgap ? k - sgap : 0u) / gap);
-        iter_len = H < lim ? H : lim;
+        iter_len = H < lim ? (uint32_t)H : (uint32_t)lim;
     }
 
     // rows owned by this lane: j = t*C + c + 1
@@ -283,24 +281,25 @@ __global__ void __launch_bounds__(128) search_wave_kernel(const SearchArgs args)
     uint32_t hc_prev = 0x200u;
 
     const int last_t = (int)((N - 1) / C), last_c = (int)((N - 1) % C);
-    const uint64_t steps = iter_len + 31;
+    const uint32_t steps = iter_len + 31;  // 32-bit counters: the step is one serial chain, every instruction counts
     // haystack bytes go through registers: chunk q = bytes [32q, 32q + 32), one per lane, fetched a chunk ahead.  At step
     // s the lanes read bytes s-1-t, which lie in chunk (s-1)/32 or the one before -- two shuffles instead of a dependent
     // one-byte global load in every step of the serial chain (that load was 80 % of the step: 48 -> ~10 us per launch).
-    auto ld_chunk = [&](const uint64_t q) {
-        const uint64_t i = q * 32 + (uint64_t)t;
+    auto ld_chunk = [&](const uint32_t q) {
+        const uint32_t i = q * 32 + (uint32_t)t;
         return i < iter_len ? (uint32_t)__ldg(hay + i) : 0u;
     };
     uint32_t hb_prev = 0, hb_cur = ld_chunk(0), hb_next = ld_chunk(1);
-    for (uint64_t s = 1; s <= steps; s++) {
+    for (uint32_t s = 1; s <= steps; s++) {
         if (s > 1 && ((s - 1) & 31) == 0) {
             hb_prev = hb_cur;
             hb_cur = hb_next;
             hb_next = ld_chunk(((s - 1) >> 5) + 1);
         }
-        const int64_t bi = (int64_t)s - 1 - t;  // byte index of column x
-        const uint32_t hb_a = __shfl_sync(full, hb_cur, (int)(bi & 31)), hb_b = __shfl_sync(full, hb_prev, (int)(bi & 31));
-        const uint32_t hc = (bi >> 5) == (int64_t)((s - 1) >> 5) ? hb_a : hb_b;
+        // byte index of column x is s - 1 - t: in the current chunk iff t <= (s - 1) mod 32
+        const int src_lane = (int)((s - 1 - (uint32_t)t) & 31u);
+        const uint32_t hb_a = __shfl_sync(full, hb_cur, src_lane), hb_b = __shfl_sync(full, hb_prev, src_lane);
+        const uint32_t hc = (uint32_t)t <= ((s - 1) & 31u) ? hb_a : hb_b;
         // neighbour state for column x = s - t, produced by lane t-1 at step s-1
         uint32_t Ldp = __shfl_up_sync(full, out_dp, 1);
         uint32_t Llen = __shfl_up_sync(full, out_len, 1);
@@ -311,8 +310,8 @@ __global__ void __launch_bounds__(128) search_wave_kernel(const SearchArgs args)
             Tdp = __shfl_up_sync(full, out_tdp, 1);
             Tlen = __shfl_up_sync(full, out_tlen, 1);
         }
-        const int64_t x = (int64_t)s - t;
-        const bool active = x >= 1 && (uint64_t)x <= iter_len;
+        const uint32_t x = s - (uint32_t)t;  // meaningful when s > t
+        const bool active = s > (uint32_t)t && x <= iter_len;
         if (t == 0) {  // row 0 (:1710-1721)
             Ldp = anchored ? (uint32_t)x * gap + sgap : 0u;
             Llen = 0;
@@ -396,13 +395,13 @@ __global__ void __launch_bounds__(128) search_wave_kernel(const SearchArgs args)
                 left_dp = dp;
                 left_len = len;
                 nprev = nc[c];
-                if (c == last_c && t == last_t && dp <= k && (uint64_t)x + col0 > emit_from) {
+                if (c == last_c && t == last_t && dp <= k && x + col0 > emit_from) {
                     const unsigned long long slot = atomicAdd(args.hit_count, 1ull);  // :1792-1806 (All threshold)
                     if (slot < args.hit_cap) {
                         Hit h;
                         h.hay = hidx;
                         h.cost = dp;
-                        h.end = (uint32_t)((uint64_t)x + col0);
+                        h.end = x + col0;
                         h.len = (uint32_t)len;
                         args.hits[slot] = h;
                     }
@@ -448,7 +447,7 @@ static int search_device(ta_ctx *ctx, cudaStream_t st, const uint8_t *d_needle, 
                          const uint8_t *d_hay, const uint64_t *d_off, size_t n, uint64_t max_hay, uint32_t k,
                          ta_costs costs, int anchored, std::vector<Hit> &hits) {
     int rc;
-    if (max_hay > 0xFFFFFFF0ull) return TA_ERR_TOO_LARGE;  // hit records carry 32-bit end positions and lengths
+    if (max_hay > 0xFFFFFF00ull) return TA_ERR_TOO_LARGE;  // hit records and the kernels' column counters are 32-bit
     constexpr size_t SPEC_HITS = 16384;  // hits copied back speculatively with the counters (384 KB, pinned)
     const bool unit = costs.mismatch == 1 && costs.gap == 1 && costs.start_gap == 0 && costs.transpose <= 1;
     const uint32_t *d_idx = nullptr;
@@ -540,7 +539,7 @@ static int search_device(ta_ctx *ctx, cudaStream_t st, const uint8_t *d_needle, 
         if (attempt) TA_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st));
         SearchArgs sa;
         sa.needle = d_needle, sa.hay = d_hay, sa.hay_off = d_off, sa.idx = d_idx, sa.n = work_n, sa.n_dev = d_work_n;
-        sa.segs = segs, sa.warm = 2u * (uint32_t)needle_len + costs.start_gap / costs.gap + 2u;
+        sa.segs = segs, sa.warm = (uint32_t)needle_len + k / costs.gap + 2u;
         sa.needle_len = (uint32_t)needle_len, sa.k = k;
         sa.mism = costs.mismatch, sa.gap = costs.gap, sa.sgap = costs.start_gap, sa.tcost = costs.transpose;
         sa.anchored = anchored, sa.hits = (Hit *)ctx->d_work[1].p, sa.hit_count = d_count, sa.hit_cap = cap;
@@ -572,107 +571,6 @@ static int search_device(ta_ctx *ctx, cudaStream_t st, const uint8_t *d_needle, 
         cap = got;  // exact size known now: rerun once
     }
     return TA_ERR_TOO_LARGE;
-}
-
-// orders the hits by (haystack, end): LSD radix sort on the haystack index alone (11 bits per pass, only over the bits
-// in use: two passes for up to 4 M haystacks), then each haystack's run -- a handful of hits as a rule -- by end position.
-// (A comparison sort of a few thousand 16-byte records costs more than the exact kernel that produced them; sorting
-// the full 64-bit key took three passes over 2048 counters and was a quarter of the search step.)
-static void sort_hits(std::vector<Hit> &hits) {
-    const size_t n = hits.size();
-    if (n < 2) return;
-    auto by_end = [](const Hit &x, const Hit &y) { return x.end < y.end; };
-    if (n < 64) {
-        std::sort(hits.begin(), hits.end(), [](const Hit &x, const Hit &y) {
-            return x.hay != y.hay ? x.hay < y.hay : x.end < y.end;
-        });
-        return;
-    }
-    uint32_t max_hay = 0;
-    for (const Hit &h : hits) max_hay = std::max(max_hay, h.hay);
-    int hay_bits = 1;
-    while (hay_bits < 32 && (max_hay >> hay_bits)) hay_bits++;
-    std::vector<Hit> tmp(n);
-    Hit *src = hits.data(), *dst = tmp.data();
-    constexpr int RB = 11;
-    uint32_t count[1 << RB];
-    for (int shift = 0; shift < hay_bits; shift += RB) {
-        memset(count, 0, sizeof count);
-        for (size_t i = 0; i < n; i++) count[(src[i].hay >> shift) & ((1u << RB) - 1)]++;
-        uint32_t sum = 0;
-        for (int b = 0; b < (1 << RB); b++) {
-            const uint32_t c = count[b];
-            count[b] = sum;
-            sum += c;
-        }
-        for (size_t i = 0; i < n; i++) dst[count[(src[i].hay >> shift) & ((1u << RB) - 1)]++] = src[i];
-        std::swap(src, dst);
-    }
-    if (src != hits.data()) memcpy(hits.data(), src, n * sizeof(Hit));
-    for (size_t i = 0; i < n;) {  // runs of one haystack
-        size_t j = i + 1;
-        while (j < n && hits[j].hay == hits[i].hay) j++;
-        if (j - i > 16) {
-            std::sort(hits.begin() + i, hits.begin() + j, by_end);
-        } else {
-            for (size_t x = i + 1; x < j; x++) {  // insertion sort
-                const Hit h = hits[x];
-                size_t y = x;
-                for (; y > i && hits[y - 1].end > h.end; y--) hits[y] = hits[y - 1];
-                hits[y] = h;
-            }
-        }
-        i = j;
-    }
-}
-
-// Host phase: order the hits by (haystack, end) and apply the reference's emission rules -- the row-0 match
-// (src/levenshtein.rs:1686-1707), the running Best threshold (:1792-1806) and the Best post-pass (:1812-1835).
-static void emit_matches(size_t n, size_t needle_len, uint32_t k, bool best, ta_costs costs, std::vector<Hit> &hits,
-                         uint64_t *moff, std::vector<ta_match> &result) {
-    sort_hits(hits);
-    const uint32_t row0 = (uint32_t)needle_len * costs.gap + costs.start_gap;
-    size_t hp = 0;
-    std::vector<ta_match> cur;
-    result.reserve(hits.size() + (row0 <= k ? n : 0));
-    for (size_t i = 0; i < n; i++) {
-        if (row0 > k && (hp >= hits.size() || hits[hp].hay != i)) {  // a run of haystacks with nothing to report
-            const size_t stop = hp < hits.size() ? (size_t)hits[hp].hay : n;
-            std::fill(moff + i + 1, moff + stop + 1, (uint64_t)result.size());
-            i = stop - 1;
-            continue;
-        }
-        cur.clear();
-        uint32_t curr_k = k;
-        if (row0 <= curr_k) {
-            if (best) curr_k = row0;
-            cur.push_back(ta_match{0, 0, row0, 0});
-        }
-        for (; hp < hits.size() && hits[hp].hay == i; hp++) {
-            const Hit &h = hits[hp];
-            if (h.cost <= curr_k) {
-                if (best) curr_k = h.cost;
-                cur.push_back(ta_match{h.end - h.len, h.end, h.cost, 0});
-            }
-        }
-        if (best && !cur.empty()) {
-            size_t wpos = 0;
-            for (size_t r = 0; r < cur.size(); r++) {
-                if (wpos == 0)
-                    cur[wpos++] = cur[r];
-                else if (cur[r].start <= cur[wpos - 1].start)
-                    cur[wpos - 1] = cur[r];  // replace previous if fully overlapping
-                else
-                    cur[wpos++] = cur[r];
-            }
-            size_t f = 0;
-            for (size_t r = 0; r < wpos; r++)
-                if (cur[r].k == curr_k) cur[f++] = cur[r];
-            cur.resize(f);
-        }
-        result.insert(result.end(), cur.begin(), cur.end());
-        moff[i + 1] = result.size();
-    }
 }
 
 static int export_matches(const std::vector<ta_match> &result, uint64_t *moff, ta_match **out_matches,
