@@ -815,9 +815,18 @@ struct QCand {
 constexpr uint32_t QG_LOG = 18;  // 256 Kbit = 32 KB of shared memory
 constexpr uint32_t QG_BITS = 1u << QG_LOG;
 constexpr int QG_MAX = 64;
-constexpr int QG_UNROLL = 4;
+constexpr uint32_t QG_CHUNK = 512;  // vectors per chunk: 8 KB
 
 __device__ __forceinline__ uint32_t qg_mul(uint32_t x) { return x * 0x9E3779B1u; }  // hash = top QG_LOG bits
+
+// the chunk counter: a bare atom.add whose result is first read a chunk later.  (atomicAdd() by one lane is turned into
+// the warp-aggregation sequence -- elect, ATOMG, SHFL of the returned value -- and the SHFL waits for the round trip on
+// the spot: 36 % of the scan's stall samples.)
+__device__ __forceinline__ uint32_t qg_next_chunk(uint32_t *ctr) {
+    uint32_t r;
+    asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(r) : "l"(ctr) : "memory");
+    return r;
+}
 
 // the 4-grams of every piece, in a fixed order (both kernels build the same list); returns their number
 __device__ __forceinline__ uint32_t qg_build(const uint8_t *nd, uint32_t N, uint32_t pieces, QGram *grams) {
@@ -864,12 +873,14 @@ __device__ __noinline__ bool qgram_push(const QGramShared &sh, const uint32_t wo
     return true;
 }
 
-__global__ void __launch_bounds__(256, 6) search_qgram_kernel(const uint8_t *__restrict__ needle, uint32_t N,
+template <int U, int OCC>  // U 16-byte loads per thread and round, OCC resident CTAs per SM
+__global__ void __launch_bounds__(256, OCC) search_qgram_kernel(const uint8_t *__restrict__ needle, uint32_t N,
                                                               const uint8_t *__restrict__ hay,
                                                               const uint64_t *__restrict__ hay_off, size_t n,
                                                               uint32_t pieces, QCand *__restrict__ queue,
                                                               uint32_t *__restrict__ qcount, uint32_t qcap,
-                                                              uint32_t *__restrict__ gave_up) {
+                                                              uint32_t *__restrict__ gave_up,
+                                                              uint32_t *__restrict__ chunk_ctr) {
     __shared__ QGramShared sh;
     for (uint32_t q = threadIdx.x; q < QG_BITS / 32; q += blockDim.x) sh.bitmap[q] = 0;
     if (threadIdx.x < 32) sh.needle[threadIdx.x] = threadIdx.x < N ? needle[threadIdx.x] : 0;
@@ -903,35 +914,81 @@ __global__ void __launch_bounds__(256, 6) search_qgram_kernel(const uint8_t *__r
         return true;
     };
 
-    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (uint64_t)gridDim.x * blockDim.x;
-    // body: 16-byte vectors [v0, v1), each four aligned words; head and tail words one by one.  QG_UNROLL independent
-    // 16-byte loads are in flight per thread and their 16 bitmap tests are OR-ed into one flag: one branch per 64 bytes.
+    // body: 16-byte vectors [v0, v1), each four aligned words; the (at most three) words before and after it one by one.
+    // The vectors are handed out in chunks of QG_CHUNK (8 KB) through a device counter, a warp at a time: with a fixed
+    // share per warp the scan ran at ~5.4 TB/s until the fastest warps were done and then waited as long again for the
+    // slowest ones (SM active cycles min 151 k / max 282 k).  A warp asks for its next chunk before it works on the
+    // current one, so the counter's round trip is never waited for.  Within a round U independent 16-byte
+    // loads are in flight per thread and their 16 bitmap tests are OR-ed into one flag: one branch per 64 bytes.
     const uint64_t v0 = (first_w + 3) >> 2, v1 = end_w >> 2;
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool go = true;
-    if (v0 < v1) {
-        uint64_t v = v0 + tid;
-        for (; go && v + (QG_UNROLL - 1) * nthreads < v1; v += QG_UNROLL * nthreads) {
-            uint4 x[QG_UNROLL];
-#pragma unroll
-            for (int u = 0; u < QG_UNROLL; u++) x[u] = ldv(v + u * nthreads);
-            uint32_t any = 0;
-#pragma unroll
-            for (int u = 0; u < QG_UNROLL; u++) any |= test(x[u].x) | test(x[u].y) | test(x[u].z) | test(x[u].w);
-            if (any & 1u) {
-#pragma unroll 1
-                for (int u = 0; u < QG_UNROLL; u++)
-#pragma unroll 1
-                    for (int i = 0; i < 4; i++) go = go && slow(4 * (v + u * nthreads) + i);
-            }
-        }
-        for (; go && v < v1; v += nthreads)
+    if (v0 >= v1) {  // no whole vector: a handful of words
+        if (tid == 0)
+            for (uint64_t wi = first_w; go && wi < end_w; wi++) go = slow(wi);
+        return;
+    }
+    if (tid < 8) {
+        for (uint64_t wi = first_w + tid; go && wi < 4 * v0; wi += 8) go = slow(wi);
+        for (uint64_t wi = 4 * v1 + tid; go && wi < end_w; wi += 8) go = slow(wi);
+    }
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t n_chunks = (v1 - v0 + QG_CHUNK - 1) / QG_CHUNK;
+    constexpr uint32_t ROUND = 32 * U, ROUNDS = QG_CHUNK / ROUND;  // vectors per round of the warp, rounds per chunk
+    uint32_t c = 0, c_next = 0;
+    if (lane == 0) c = qg_next_chunk(chunk_ctr);
+    c = __shfl_sync(0xffffffffu, c, 0);
+    if (c >= n_chunks) return;
+    if (lane == 0) c_next = qg_next_chunk(chunk_ctr);
+    // software pipeline over rounds, across chunk boundaries: the loads of round r + 1 are issued before round r is
+    // tested, so a warp always has U to 2U loads in flight (with load -> test -> load the scan was latency-bound at
+    // 4.2 TB/s: most warps waiting on their loads, issue slots 35 % busy)
+    auto full_chunk = [&](uint32_t cc) { return v0 + ((uint64_t)cc + 1) * QG_CHUNK <= v1; };
+    auto partial = [&](uint32_t cc) {  // the last chunk when it is not whole: word by word
+        for (uint64_t v = v0 + (uint64_t)cc * QG_CHUNK + lane; go && v < v1; v += 32)
 #pragma unroll 1
             for (int i = 0; i < 4; i++) go = go && slow(4 * v + i);
-        for (uint64_t wi = first_w + tid; go && wi < 4 * v0; wi += nthreads) go = slow(wi);
-        for (uint64_t wi = 4 * v1 + tid; go && wi < end_w; wi += nthreads) go = slow(wi);
-    } else {
-        for (uint64_t wi = first_w + tid; go && wi < end_w; wi += nthreads) go = slow(wi);
+    };
+    if (!full_chunk(c)) {  // c is the last chunk, nothing follows it
+        partial(c);
+        return;
     }
+    uint32_t it = 0;
+    uint64_t vcur = v0 + (uint64_t)c * QG_CHUNK + lane;
+    uint4 x[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) x[u] = ldv(vcur + u * 32);
+    while (true) {
+        // where the next round is
+        bool have_next = true;
+        if (++it == ROUNDS) {
+            it = 0;
+            c = __shfl_sync(0xffffffffu, c_next, 0);
+            have_next = c < n_chunks && full_chunk(c);
+            if (have_next && lane == 0) c_next = qg_next_chunk(chunk_ctr);
+        }
+        const uint64_t vnext = v0 + (uint64_t)c * QG_CHUNK + it * ROUND + lane;
+        uint4 y[U];
+        if (have_next) {
+#pragma unroll
+            for (int u = 0; u < U; u++) y[u] = ldv(vnext + u * 32);
+        }
+        uint32_t any = 0;
+#pragma unroll
+        for (int u = 0; u < U; u++) any |= test(x[u].x) | test(x[u].y) | test(x[u].z) | test(x[u].w);
+        if (any & 1u) {
+#pragma unroll 1
+            for (int u = 0; u < U; u++)
+#pragma unroll 1
+                for (int i = 0; i < 4; i++) go = go && slow(4 * (vcur + u * 32) + i);
+        }
+        if (__any_sync(0xffffffffu, !go)) return;  // the queue is full: the fallback kernel takes over
+        if (!have_next) break;
+#pragma unroll
+        for (int u = 0; u < U; u++) x[u] = y[u];
+        vcur = vnext;
+    }
+    if (c < n_chunks) partial(c);  // this warp drew the partial last chunk
 }
 
 // one queued word per thread: which haystack, which pieces, and what the occurrence allows
@@ -959,13 +1016,14 @@ __global__ void __launch_bounds__(128) search_qgram_resolve_kernel(const uint8_t
     __syncthreads();
     const uint32_t total = *qcount, ng = n_grams;
     const uint64_t B0 = hay_off[0], span = hay_off[n] - B0;
+    const uint64_t avg_len = span / n ? span / n : 1;
     for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
         const uint64_t g = queue[e].g;
         const uint32_t word = queue[e].word;
         // the haystack that holds byte g (largest h with hay_off[h] <= g): interpolate, then bisect what is left
         size_t lo = 0, hi = n;
         {
-            const size_t est = (size_t)(((unsigned __int128)(g - B0) * n) / (span ? span : 1));
+            const size_t est = (size_t)((g - B0) / avg_len);  // exact for equal-length haystacks
             const size_t e0 = est < n ? est : n - 1;
             if (hay_off[e0] <= g) {
                 lo = e0;
@@ -985,8 +1043,12 @@ __global__ void __launch_bounds__(128) search_qgram_resolve_kernel(const uint8_t
         const uint64_t h0 = hay_off[h], H = hay_off[h + 1] - h0;
         const uint8_t *p = hay + h0;
         const uint64_t x = g - h0;
-        for (uint32_t j = 0; j < ng; j++) {
-            if (grams[j].gram != word) continue;
+        // Find the matching 4-gram FIRST and do the work after the search loop: with the work inside `for j`, lanes whose
+        // words are different grams ran their verifications one after the other (ncu: 1 active thread per instruction,
+        // 128 us for 2 400 entries).  A word can equal several grams only if the needle repeats itself: outer loop.
+        for (uint32_t j = 0;; j++) {
+            while (j < ng && grams[j].gram != word) j++;
+            if (j >= ng) break;
             const uint32_t off = grams[j].off, len = grams[j].len, fin = grams[j].fin;
             if (x < off) continue;            // the piece would start before the haystack
             const uint64_t q = x - off + len - 1;  // haystack index of the piece's last byte
@@ -1071,16 +1133,17 @@ int ta_launch_search_filter(ta_ctx *ctx, const uint8_t *needle_dev, uint32_t nee
         QCand *queue = (QCand *)((uint8_t *)ctx->d_work[2].p + flag_bytes);
         uint32_t *qcount = ctx->d_flags + 16, *gave_up = ctx->d_flags + 17;
         TA_CUDA(ctx, cudaMemsetAsync(sub_flags, 0, words * sizeof(uint32_t), st));
-        TA_CUDA(ctx, cudaMemsetAsync(qcount, 0, 2 * sizeof(uint32_t), st));
-        static int occ = 0;  // one wave of resident CTAs: the scan is a grid-stride loop
-        if (!occ) {
-            int o = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, search_qgram_kernel, 256, 0);
-            occ = o > 0 ? o : 1;
-        }
+        TA_CUDA(ctx, cudaMemsetAsync(qcount, 0, 3 * sizeof(uint32_t), st));  // queue length, gave-up flag, chunk counter
+        // one wave of resident CTAs, chunks handed out dynamically; TA_QGRAM_U=2 picks the 2-load, 5-CTA variant (testing)
+        static const int env_u = getenv("TA_QGRAM_U") ? atoi(getenv("TA_QGRAM_U")) : 0;
         static const int env_ctas = getenv("TA_QGRAM_CTAS") ? atoi(getenv("TA_QGRAM_CTAS")) : 0;
-        const unsigned blocks = (unsigned)ctx->sm_count * (unsigned)(env_ctas > 0 ? env_ctas : occ);
-        search_qgram_kernel<<<blocks, 256, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, pieces, queue, qcount, qcap, gave_up);
+        if (env_u == 2) {
+            const unsigned blocks = (unsigned)ctx->sm_count * (unsigned)(env_ctas > 0 ? env_ctas : 5);
+            search_qgram_kernel<2, 5><<<blocks, 256, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, pieces, queue, qcount, qcap, gave_up, ctx->d_flags + 18);
+        } else {
+            const unsigned blocks = (unsigned)ctx->sm_count * (unsigned)(env_ctas > 0 ? env_ctas : 4);
+            search_qgram_kernel<4, 4><<<blocks, 256, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, pieces, queue, qcount, qcap, gave_up, ctx->d_flags + 18);
+        }
         ctx->launches++;
         TA_CUDA(ctx, cudaGetLastError());
         const unsigned rblocks = (unsigned)std::min<uint64_t>(((uint64_t)qcap + 127) / 128, (uint64_t)ctx->sm_count * 8);

@@ -38,6 +38,7 @@ struct SearchArgs {
     uint32_t segs;        // 0: idx holds haystack indices.  > 0: idx holds haystack * segs + segment codes and the
                           // item covers only that TA_SEARCH_SUB-byte segment after a warm-up of `warm` bytes
     uint32_t warm;
+    uint32_t split;       // segment items are cut into `split` parts of TA_SEARCH_SUB / split end positions, a warp each
     size_t n;
     const uint32_t *n_dev;  // optional: the number of work items lives on the device (written by the pre-filter)
     uint32_t needle_len;
@@ -223,10 +224,15 @@ __global__ void __launch_bounds__(128) search_wave_kernel(const SearchArgs args)
     const int t = threadIdx.x & 31;
     // persistent warps: the item count may only exist on the device (pre-filter output), so the grid is sized from an
     // upper bound and every warp strides over the items
-    const size_t n_items = args.n_dev ? (size_t)*args.n_dev : args.n;
+    // A warp's item is ONE serial chain of warm + end positions + 31 steps (~75 dependent instructions each), and after
+    // a pre-filter there are far fewer items than the GPU has warps -- so a flagged sub-segment is cut into `split`
+    // parts, each restarted on its own: more total work, a shorter chain (37 + 32 + 31 steps instead of 37 + 128 + 31).
+    const uint32_t split = args.segs ? args.split : 1u;
+    const size_t n_items = (args.n_dev ? (size_t)*args.n_dev : args.n) * split;
     const size_t n_warps = (size_t)gridDim.x * (blockDim.x >> 5);
     for (size_t w = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < n_items; w += n_warps) {
-    const uint32_t code = args.idx ? args.idx[w] : (uint32_t)w;
+    const uint32_t part = (uint32_t)(w % split);
+    const uint32_t code = args.idx ? args.idx[w / split] : (uint32_t)w;
     const uint32_t hidx = args.segs ? code / args.segs : code;
     const uint64_t h0 = args.hay_off[hidx], h1 = args.hay_off[hidx + 1];
     const uint8_t *hay = args.hay + h0;
@@ -243,9 +249,10 @@ __global__ void __launch_bounds__(128) search_wave_kernel(const SearchArgs args)
     // for every reported end position inside it (tests/test_search_restart_model.py pins the margin on the CPU).
     uint32_t col0 = 0, emit_from = 0;  // columns are numbered from col0; hits are reported for x + col0 > emit_from
     if (args.segs) {
-        const uint32_t seg = code % args.segs;
-        emit_from = seg * (uint32_t)TA_SEARCH_SUB;
-        const uint64_t seg_end = (uint64_t)emit_from + TA_SEARCH_SUB < H ? (uint64_t)emit_from + TA_SEARCH_SUB : H;
+        const uint32_t seg = code % args.segs, span = (uint32_t)TA_SEARCH_SUB / split;
+        emit_from = seg * (uint32_t)TA_SEARCH_SUB + part * span;
+        if (emit_from >= H) continue;  // this part lies past the haystack's end
+        const uint64_t seg_end = (uint64_t)emit_from + span < H ? (uint64_t)emit_from + span : H;
         col0 = emit_from > args.warm ? emit_from - args.warm : 0;
         hay += col0;
         H = seg_end - col0;
@@ -540,12 +547,14 @@ static int search_device(ta_ctx *ctx, cudaStream_t st, const uint8_t *d_needle, 
         SearchArgs sa;
         sa.needle = d_needle, sa.hay = d_hay, sa.hay_off = d_off, sa.idx = d_idx, sa.n = work_n, sa.n_dev = d_work_n;
         sa.segs = segs, sa.warm = (uint32_t)needle_len + k / costs.gap + 2u;
+        static const int env_split = getenv("TA_WAVE_SPLIT") ? atoi(getenv("TA_WAVE_SPLIT")) : 0;  // 1, 2, 4, 8 (testing)
+        sa.split = (env_split == 1 || env_split == 2 || env_split == 4 || env_split == 8) ? (uint32_t)env_split : 2u;
         sa.needle_len = (uint32_t)needle_len, sa.k = k;
         sa.mism = costs.mismatch, sa.gap = costs.gap, sa.sgap = costs.start_gap, sa.tcost = costs.transpose;
         sa.anchored = anchored, sa.hits = (Hit *)ctx->d_work[1].p, sa.hit_count = d_count, sa.hit_cap = cap;
         sa.rows_ws = use_global ? (uint32_t *)ctx->d_work[3].p : nullptr;
         const size_t per_block = use_wave ? (size_t)threads / 32 : (size_t)threads;
-        size_t blocks = (work_n + per_block - 1) / per_block;
+        size_t blocks = (work_n * (segs ? sa.split : 1u) + per_block - 1) / per_block;
         if (use_wave) blocks = std::min<size_t>(blocks, (size_t)ctx->sm_count * 16);  // persistent warps
         if (use_global) blocks = global_blocks;
         kern<<<(unsigned)blocks, threads, smem, st>>>(sa);

@@ -57,6 +57,23 @@ static inline void sort_hits(std::vector<Hit> &hits, size_t n_hay) {
     hits.swap(tmp);
 }
 
+// moff[a .. b) = v.  The offsets of the haystacks without a match are ~1000 runs of ~100 equal values per call; std::fill
+// pays its alignment prologue / remainder epilogue on every run and was 3x slower than one flat fill of the same bytes.
+// Here: groups of eight stores, and the last group overlaps the one before it instead of a scalar tail.
+static inline void fill_run(uint64_t *a, uint64_t *b, uint64_t v) {
+    if (b - a < 8) {
+        for (; a < b; a++) *a = v;
+        return;
+    }
+    for (; a + 8 <= b; a += 8) {
+        a[0] = v, a[1] = v, a[2] = v, a[3] = v;
+        a[4] = v, a[5] = v, a[6] = v, a[7] = v;
+    }
+    a = b - 8;
+    a[0] = v, a[1] = v, a[2] = v, a[3] = v;
+    a[4] = v, a[5] = v, a[6] = v, a[7] = v;
+}
+
 // Host phase: order the hits by (haystack, end) and apply the reference's emission rules -- the row-0 match
 // (src/levenshtein.rs:1686-1707), the running Best threshold (:1792-1806) and the Best post-pass (:1812-1835).
 // moff[0] is set by the caller; moff[1 .. n] and `result` are filled here.
@@ -77,7 +94,7 @@ static inline void emit_matches(size_t n, size_t needle_len, uint32_t k, bool be
         if (row0 > k) {  // a run of haystacks with nothing to report: filled at memset speed
             const size_t stop = hp < nh ? (size_t)hv[hp].hay : n;
             if (stop > i) {
-                std::fill(moff + i + 1, moff + stop + 1, (uint64_t)result.size());
+                fill_run(moff + i + 1, moff + stop + 1, (uint64_t)result.size());
                 i = stop;
                 if (i >= n) break;
             }
