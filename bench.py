@@ -62,7 +62,7 @@ WORKLOADS = {
     "search_all_n32_h4096": ("search", 100_000, 4096, 3, (1, 1, 0, 0), "strong",
                              "levenshtein_search SearchType::All, needle len=32, 100k haystacks len=4096, k=3, 1% planted hits"),
     "search_n64_h4096": ("search", 100_000, 4096, 6, (1, 1, 0, 0), "strong",
-                         "levenshtein_search needle len=64 (Myers pre-filter), 100k haystacks len=4096, k=6, Best, 1% planted hits"),
+                         "levenshtein_search needle len=64 (seven pieces of 9), 100k haystacks len=4096, k=6, Best, 1% planted hits"),
     "search_affine_n32_h4096": ("search", 20_000, 4096, 6, (2, 1, 3, 0), "strong",
                                 "levenshtein_search EditCosts(2,1,3,None): no pre-filter, exact (cost, length) kernel over whole "
                                 "haystacks; needle len=32, 20k haystacks len=4096, k=6, Best"),
@@ -168,7 +168,7 @@ def dominant_kernel(op, k, costs, length):
         nlen = SEARCH_NEEDLE[0]
         pieces = (2 * k + 1) if costs[3] else (k + 1)
         forced = os.environ.get("TA_SEARCH_FILTER", "")
-        if nlen <= 32 and pieces <= nlen and nlen // pieces >= 7 and forced in ("", "qgram"):
+        if nlen <= 64 and pieces <= nlen and nlen // pieces >= 7 and forced in ("", "qgram"):
             return "search_qgram_kernel (+ search_qgram_resolve_kernel, search_wave_kernel on the flagged 128-byte sub-segments)"
         if nlen <= 32 and pieces <= nlen and nlen // pieces >= 4 and forced != "myers":
             return "search_pigeon_staged_kernel (+ search_wave_kernel on the flagged 128-byte sub-segments)"

@@ -535,13 +535,15 @@ def test_search_filter_long_needles_and_transpositions(eng):
 
 
 def test_search_qgram_filter(eng):
-    """the aligned-word (4-gram) pre-filter: needles whose k + 1 (2k + 1) pieces are >= 7 bytes.  Alphabets of 2 / 4
+    """the aligned-word (4-gram) pre-filter: needles of up to 64 bytes whose k + 1 (2k + 1) pieces are >= 7 bytes.  Alphabets of 2 / 4
     symbols make every word a candidate (the queue, the whole-piece compare and the verification do the work; big
     batches overflow the queue and take the shift-and fallback), 256 symbols is the case it is built for; haystacks
     are ragged, start at every alignment, and include empty and shorter-than-a-word ones."""
     rng = random.Random(1717)
     for nlen, k, costs in ((14, 1, (1, 1, 0, 0)), (21, 2, (1, 1, 0, 0)), (32, 3, (1, 1, 0, 0)), (28, 3, (1, 1, 0, 0)),
-                           (32, 1, (1, 1, 0, 1)), (21, 1, (1, 1, 0, 1)), (32, 6, (2, 2, 0, 0)), (30, 0, (1, 1, 0, 0))):
+                           (32, 1, (1, 1, 0, 1)), (21, 1, (1, 1, 0, 1)), (32, 6, (2, 2, 0, 0)), (30, 0, (1, 1, 0, 0)),
+                           (64, 6, (1, 1, 0, 0)), (48, 5, (1, 1, 0, 0)), (33, 3, (1, 1, 0, 0)), (64, 3, (1, 1, 0, 1)),
+                           (57, 0, (1, 1, 0, 1))):
         for alpha in (2, 4, 256):
             needle = bytes(rng.randrange(alpha) for _ in range(nlen))
             hays = [b"", b"ab", needle, needle[1:], needle + needle]

@@ -385,7 +385,9 @@ __global__ void __launch_bounds__(128) search_filter_kernel(const uint8_t *__res
                                                             const uint8_t *__restrict__ hay,
                                                             const uint64_t *__restrict__ hay_off, size_t n, uint32_t k,
                                                             uint32_t subs, uint32_t *__restrict__ idx_out,
-                                                            uint32_t *__restrict__ counter) {
+                                                            uint32_t *__restrict__ counter,
+                                                            const uint32_t *__restrict__ only_if) {
+    if (only_if && *only_if == 0) return;  // queued as the q-gram scan's fallback: runs only if that kernel gave up
     __shared__ W peq[256];
     for (int c = threadIdx.x; c < 256; c += blockDim.x) peq[c] = 0;
     __syncthreads();
@@ -816,12 +818,11 @@ constexpr uint32_t QG_LOG = 18;  // 256 Kbit = 32 KB of shared memory
 constexpr uint32_t QG_BITS = 1u << QG_LOG;
 constexpr int QG_MAX = 64;
 constexpr uint32_t QG_CHUNK = 512;  // vectors per chunk: 8 KB
+constexpr uint32_t QG_REGIONS = 8;  // chunk counters (one 128-byte line each)
 
 __device__ __forceinline__ uint32_t qg_mul(uint32_t x) { return x * 0x9E3779B1u; }  // hash = top QG_LOG bits
 
-// the chunk counter: a bare atom.add whose result is first read a chunk later.  (atomicAdd() by one lane is turned into
-// the warp-aggregation sequence -- elect, ATOMG, SHFL of the returned value -- and the SHFL waits for the round trip on
-// the spot: 36 % of the scan's stall samples.)
+// the chunk counter (see the note at its use in the scan loop)
 __device__ __forceinline__ uint32_t qg_next_chunk(uint32_t *ctr) {
     uint32_t r;
     asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(r) : "l"(ctr) : "memory");
@@ -849,7 +850,7 @@ struct QGramShared {
     uint32_t bitmap[QG_BITS / 32];
     QGram grams[QG_MAX];
     uint32_t n_grams;
-    uint8_t needle[32];
+    uint8_t needle[64];
 };
 
 // a word that hit the bitmap: if it really is one of the 4-grams, queue it.  Out of line: it runs for one word in ~10^4
@@ -883,7 +884,7 @@ __global__ void __launch_bounds__(256, OCC) search_qgram_kernel(const uint8_t *_
                                                               uint32_t *__restrict__ chunk_ctr) {
     __shared__ QGramShared sh;
     for (uint32_t q = threadIdx.x; q < QG_BITS / 32; q += blockDim.x) sh.bitmap[q] = 0;
-    if (threadIdx.x < 32) sh.needle[threadIdx.x] = threadIdx.x < N ? needle[threadIdx.x] : 0;
+    if (threadIdx.x < 64) sh.needle[threadIdx.x] = threadIdx.x < N ? needle[threadIdx.x] : 0;
     __syncthreads();
     if (threadIdx.x == 0) {  // a few dozen entries: one thread, needle bytes from shared memory
         const uint32_t cnt = qg_build(sh.needle, N, pieces, sh.grams);
@@ -935,44 +936,73 @@ __global__ void __launch_bounds__(256, OCC) search_qgram_kernel(const uint8_t *_
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t n_chunks = (v1 - v0 + QG_CHUNK - 1) / QG_CHUNK;
     constexpr uint32_t ROUND = 32 * U, ROUNDS = QG_CHUNK / ROUND;  // vectors per round of the warp, rounds per chunk
-    uint32_t c = 0, c_next = 0;
-    if (lane == 0) c = qg_next_chunk(chunk_ctr);
-    c = __shfl_sync(0xffffffffu, c, 0);
-    if (c >= n_chunks) return;
-    if (lane == 0) c_next = qg_next_chunk(chunk_ctr);
-    // software pipeline over rounds, across chunk boundaries: the loads of round r + 1 are issued before round r is
-    // tested, so a warp always has U to 2U loads in flight (with load -> test -> load the scan was latency-bound at
-    // 4.2 TB/s: most warps waiting on their loads, issue slots 35 % busy)
-    auto full_chunk = [&](uint32_t cc) { return v0 + ((uint64_t)cc + 1) * QG_CHUNK <= v1; };
-    auto partial = [&](uint32_t cc) {  // the last chunk when it is not whole: word by word
-        for (uint64_t v = v0 + (uint64_t)cc * QG_CHUNK + lane; go && v < v1; v += 32)
+    // Chunk hand-out: the chunks are cut into QG_REGIONS contiguous regions, each with its own counter in its own
+    // 128-byte line; a warp works its way through region (warp id mod QG_REGIONS) and, when that is used up, through
+    // the others.  (ONE counter for all 50 k chunks was the bottleneck of the scan: an L2 atomic unit serves one address
+    // at ~2 ns per request, whatever the number of warps -- 2 to 6 CTAs per SM all ran at 110 us, a third of the stall
+    // samples on the counter's reply.)
+    const uint64_t cpr = (n_chunks + QG_REGIONS - 1) / QG_REGIONS;  // chunks per region
+    uint32_t region = (uint32_t)((tid >> 5) % QG_REGIONS), tried = 0;
+    auto region_size = [&](uint32_t r) -> uint64_t {
+        const uint64_t lo = (uint64_t)r * cpr;
+        return lo >= n_chunks ? 0 : (n_chunks - lo < cpr ? n_chunks - lo : cpr);
+    };
+    auto request = [&]() -> uint32_t { return lane == 0 ? qg_next_chunk(chunk_ctr + region * 32u) : 0u; };
+    // ticket (lane 0) -> chunk index, or n_chunks when everything has been handed out; moves on to the next region
+    // (one exposed round trip each) when the ticket is past the end of the current one
+    auto resolve = [&](uint32_t ticket) -> uint64_t {
+        uint32_t li = __shfl_sync(0xffffffffu, ticket, 0);
+        while ((uint64_t)li >= region_size(region)) {
+            if (++tried == QG_REGIONS) return n_chunks;
+            region = region + 1 == QG_REGIONS ? 0 : region + 1;
+            li = __shfl_sync(0xffffffffu, request(), 0);
+        }
+        return (uint64_t)region * cpr + li;
+    };
+    auto full_chunk = [&](uint64_t cc) { return v0 + (cc + 1) * QG_CHUNK <= v1; };
+    auto partial = [&](uint64_t cc) {  // the last chunk when it is not whole: word by word
+        for (uint64_t v = v0 + cc * QG_CHUNK + lane; go && v < v1; v += 32)
 #pragma unroll 1
             for (int i = 0; i < 4; i++) go = go && slow(4 * v + i);
     };
-    if (!full_chunk(c)) {  // c is the last chunk, nothing follows it
+    // software pipeline over rounds, across chunk boundaries: the loads of round r + 1 are issued before round r is
+    // tested, so a warp always has U to 2U loads in flight (with load -> test -> load the scan was latency-bound at
+    // 4.2 TB/s: most warps waiting on their loads, issue slots 35 % busy)
+    uint64_t c = resolve(request());
+    while (c < n_chunks && !full_chunk(c)) {  // drew the partial last chunk first: do it and draw again
         partial(c);
-        return;
+        c = resolve(request());
     }
+    if (c >= n_chunks) return;
+    uint32_t ticket = request();
     uint32_t it = 0;
-    uint64_t vcur = v0 + (uint64_t)c * QG_CHUNK + lane;
+    uint64_t vcur = v0 + c * QG_CHUNK + lane;
     uint4 x[U];
 #pragma unroll
     for (int u = 0; u < U; u++) x[u] = ldv(vcur + u * 32);
     while (true) {
         // where the next round is
-        bool have_next = true;
+        bool have_next = true, new_chunk = false;
         if (++it == ROUNDS) {
             it = 0;
-            c = __shfl_sync(0xffffffffu, c_next, 0);
-            have_next = c < n_chunks && full_chunk(c);
-            if (have_next && lane == 0) c_next = qg_next_chunk(chunk_ctr);
+            c = resolve(ticket);
+            while (c < n_chunks && !full_chunk(c)) {
+                partial(c);
+                c = resolve(request());
+            }
+            have_next = c < n_chunks;
+            new_chunk = have_next;
         }
-        const uint64_t vnext = v0 + (uint64_t)c * QG_CHUNK + it * ROUND + lane;
+        const uint64_t vnext = v0 + c * QG_CHUNK + it * ROUND + lane;
         uint4 y[U];
         if (have_next) {
 #pragma unroll
             for (int u = 0; u < U; u++) y[u] = ldv(vnext + u * 32);
         }
+        // the request for the chunk after this one goes out AFTER the loads: ptxas turns a one-lane atom.add (atomicAdd()
+        // or inline PTX, atom.inc too) into its warp-aggregation sequence -- elect, ATOMG, SHFL of the returned value --
+        // and that SHFL waits for the round trip on the spot
+        if (new_chunk) ticket = request();
         uint32_t any = 0;
 #pragma unroll
         for (int u = 0; u < U; u++) any |= test(x[u].x) | test(x[u].y) | test(x[u].z) | test(x[u].w);
@@ -988,11 +1018,10 @@ __global__ void __launch_bounds__(256, OCC) search_qgram_kernel(const uint8_t *_
         for (int u = 0; u < U; u++) x[u] = y[u];
         vcur = vnext;
     }
-    if (c < n_chunks) partial(c);  // this warp drew the partial last chunk
 }
 
 // one queued word per thread: which haystack, which pieces, and what the occurrence allows
-template <bool TRANS>
+template <typename W, bool TRANS>  // W: the verification's bit-vector word (uint32_t for needles <= 32, else uint64_t)
 __global__ void __launch_bounds__(128) search_qgram_resolve_kernel(const uint8_t *__restrict__ needle, uint32_t N,
                                                                    const uint8_t *__restrict__ hay,
                                                                    const uint64_t *__restrict__ hay_off, size_t n,
@@ -1004,14 +1033,19 @@ __global__ void __launch_bounds__(128) search_qgram_resolve_kernel(const uint8_t
                                                                    uint32_t *__restrict__ idx_out,
                                                                    uint32_t *__restrict__ counter) {
     if (*gave_up) return;
-    __shared__ uint32_t peq[256];
+    __shared__ W peq[256];
     __shared__ QGram grams[QG_MAX];
-    __shared__ uint8_t nd[32];
+    __shared__ uint8_t nd[64];
     __shared__ uint32_t n_grams;
     for (uint32_t q = threadIdx.x; q < 256; q += blockDim.x) peq[q] = 0;
-    if (threadIdx.x < 32) nd[threadIdx.x] = threadIdx.x < N ? needle[threadIdx.x] : 0;
+    if (threadIdx.x < 64) nd[threadIdx.x] = threadIdx.x < N ? needle[threadIdx.x] : 0;
     __syncthreads();
-    if (threadIdx.x < N) atomicOr(&peq[nd[threadIdx.x]], 1u << threadIdx.x);
+    if (threadIdx.x < N) {
+        if (sizeof(W) == 4)
+            atomicOr((unsigned int *)&peq[nd[threadIdx.x]], 1u << threadIdx.x);
+        else
+            atomicOr((unsigned long long *)&peq[nd[threadIdx.x]], 1ull << threadIdx.x);
+    }
     if (threadIdx.x == 0) n_grams = qg_build(nd, N, pieces, grams);
     __syncthreads();
     const uint32_t total = *qcount, ng = n_grams;
@@ -1063,18 +1097,19 @@ __global__ void __launch_bounds__(128) search_qgram_resolve_kernel(const uint8_t
             if (ehi > H - 1) ehi = H - 1;
             if (elo > ehi) continue;
             const uint64_t st = q + 1 > (uint64_t)fin + 1 + k ? q + 1 - (fin + 1 + k) : 0;
-            uint32_t VP = 0xffffffffu, VN = 0, D0prev = 0xffffffffu, Eqprev = 0, score = N;
-            const uint32_t top = 1u << (N - 1);
+            W VP = ~(W)0, VN = 0, D0prev = ~(W)0, Eqprev = 0;
+            uint32_t score = N;
+            const W top = (W)1 << (N - 1);
             for (uint64_t t = st; t <= ehi; t++) {
-                const uint32_t Eq = peq[p[t]];
-                uint32_t D0 = (((Eq & VP) + VP) ^ VP) | Eq | VN;
+                const W Eq = peq[p[t]];
+                W D0 = (((Eq & VP) + VP) ^ VP) | Eq | VN;
                 if (TRANS) {
                     D0 |= ((~D0prev & Eq) << 1) & Eqprev;
                     D0prev = D0;
                     Eqprev = Eq;
                 }
-                uint32_t HP = VN | ~(D0 | VP);
-                uint32_t HN = D0 & VP;
+                W HP = VN | ~(D0 | VP);
+                W HN = D0 & VP;
                 score += (HP & top) ? 1u : 0u;
                 score -= (HN & top) ? 1u : 0u;
                 HP <<= 1;
@@ -1114,7 +1149,7 @@ int ta_launch_search_filter(ta_ctx *ctx, const uint8_t *needle_dev, uint32_t nee
     if (force && force[0] == 'm') pigeon = false;
     if (force && force[0] == 'p' && needle_len <= 32 && pieces <= needle_len) pigeon = true;
     // pieces of >= 7 bytes: aligned-word sampling at memory speed (TA_SEARCH_FILTER=pigeon|myers keep the others testable)
-    bool qgram = needle_len <= 32 && pieces <= needle_len && needle_len / pieces >= 7 &&
+    bool qgram = needle_len <= 64 && pieces <= needle_len && needle_len / pieces >= 7 &&
                  pieces * (needle_len / pieces + 1 - 3) <= (uint32_t)QG_MAX;
     if (force && force[0] != 'q') qgram = false;
     const uint32_t *only_if = nullptr;  // set when the shift-and kernel below is only the q-gram scan's fallback
@@ -1126,35 +1161,50 @@ int ta_launch_search_filter(ta_ctx *ctx, const uint8_t *needle_dev, uint32_t nee
         static const long env_cap = getenv("TA_QGRAM_QCAP") ? atol(getenv("TA_QGRAM_QCAP")) : 0;  // testing: force the fallback
         const uint64_t total_bytes = (uint64_t)n * max_hay;  // upper bound of the flat range
         const uint32_t qcap = env_cap > 0 ? (uint32_t)env_cap : (uint32_t)std::min<uint64_t>(total_bytes / 4096 + 4096, 1u << 24);
-        const size_t flag_bytes = (words * sizeof(uint32_t) + 15) & ~(size_t)15;
-        int rc = ta_dev_reserve(ctx, ctx->d_work[2], flag_bytes + (size_t)qcap * sizeof(QCand));
+        // workspace: [sub-segment flags | chunk counters, one 128-byte line each | queue]; one memset clears the first two
+        const size_t flag_bytes = (words * sizeof(uint32_t) + 127) & ~(size_t)127;
+        const size_t ctr_bytes = (size_t)QG_REGIONS * 128;
+        int rc = ta_dev_reserve(ctx, ctx->d_work[2], flag_bytes + ctr_bytes + (size_t)qcap * sizeof(QCand));
         if (rc != TA_OK) return rc;
         uint32_t *sub_flags = (uint32_t *)ctx->d_work[2].p;
-        QCand *queue = (QCand *)((uint8_t *)ctx->d_work[2].p + flag_bytes);
+        uint32_t *chunk_ctr = (uint32_t *)((uint8_t *)ctx->d_work[2].p + flag_bytes);
+        QCand *queue = (QCand *)((uint8_t *)ctx->d_work[2].p + flag_bytes + ctr_bytes);
         uint32_t *qcount = ctx->d_flags + 16, *gave_up = ctx->d_flags + 17;
-        TA_CUDA(ctx, cudaMemsetAsync(sub_flags, 0, words * sizeof(uint32_t), st));
-        TA_CUDA(ctx, cudaMemsetAsync(qcount, 0, 3 * sizeof(uint32_t), st));  // queue length, gave-up flag, chunk counter
+        TA_CUDA(ctx, cudaMemsetAsync(sub_flags, 0, flag_bytes + ctr_bytes, st));
+        TA_CUDA(ctx, cudaMemsetAsync(qcount, 0, 2 * sizeof(uint32_t), st));  // queue length, gave-up flag
         // one wave of resident CTAs, chunks handed out dynamically; TA_QGRAM_U=2 picks the 2-load, 5-CTA variant (testing)
         static const int env_u = getenv("TA_QGRAM_U") ? atoi(getenv("TA_QGRAM_U")) : 0;
         static const int env_ctas = getenv("TA_QGRAM_CTAS") ? atoi(getenv("TA_QGRAM_CTAS")) : 0;
         if (env_u == 2) {
             const unsigned blocks = (unsigned)ctx->sm_count * (unsigned)(env_ctas > 0 ? env_ctas : 5);
-            search_qgram_kernel<2, 5><<<blocks, 256, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, pieces, queue, qcount, qcap, gave_up, ctx->d_flags + 18);
+            search_qgram_kernel<2, 5><<<blocks, 256, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, pieces, queue, qcount, qcap, gave_up, chunk_ctr);
         } else {
             const unsigned blocks = (unsigned)ctx->sm_count * (unsigned)(env_ctas > 0 ? env_ctas : 4);
-            search_qgram_kernel<4, 4><<<blocks, 256, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, pieces, queue, qcount, qcap, gave_up, ctx->d_flags + 18);
+            search_qgram_kernel<4, 4><<<blocks, 256, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, pieces, queue, qcount, qcap, gave_up, chunk_ctr);
         }
         ctx->launches++;
         TA_CUDA(ctx, cudaGetLastError());
         const unsigned rblocks = (unsigned)std::min<uint64_t>(((uint64_t)qcap + 127) / 128, (uint64_t)ctx->sm_count * 8);
-        if (transpose)
-            search_qgram_resolve_kernel<true><<<rblocks, 128, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, k, pieces, (uint32_t)subs, queue, qcount, gave_up, sub_flags, idx_out, counter);
-        else
-            search_qgram_resolve_kernel<false><<<rblocks, 128, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, k, pieces, (uint32_t)subs, queue, qcount, gave_up, sub_flags, idx_out, counter);
+#define TA_RESOLVE(W, T)                                                                                                      \
+    search_qgram_resolve_kernel<W, T><<<rblocks, 128, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, k, pieces, (uint32_t)subs, \
+                                                               queue, qcount, gave_up, sub_flags, idx_out, counter)
+        if (needle_len <= 32) {
+            if (transpose)
+                TA_RESOLVE(uint32_t, true);
+            else
+                TA_RESOLVE(uint32_t, false);
+        } else {
+            if (transpose)
+                TA_RESOLVE(uint64_t, true);
+            else
+                TA_RESOLVE(uint64_t, false);
+        }
+#undef TA_RESOLVE
         ctx->launches++;
         TA_CUDA(ctx, cudaGetLastError());
-        only_if = gave_up;  // the staged shift-and kernel below runs only if the scan gave up
-        pigeon = true;
+        // the filter launched below (shift-and for needles <= 32, else Myers) runs only if the scan gave up
+        only_if = gave_up;
+        pigeon = needle_len <= 32;
     }
     if (pigeon) {
         // 256-thread blocks: the 32 KB bank-replicated table is shared by 8 warps (TA_PIGEON_THREADS overrides)
@@ -1188,14 +1238,14 @@ int ta_launch_search_filter(ta_ctx *ctx, const uint8_t *needle_dev, uint32_t nee
         }
     } else if (needle_len <= 32) {
         if (transpose)
-            search_filter_kernel<uint32_t, true><<<grid, 128, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, k, (uint32_t)subs, idx_out, counter);
+            search_filter_kernel<uint32_t, true><<<grid, 128, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, k, (uint32_t)subs, idx_out, counter, only_if);
         else
-            search_filter_kernel<uint32_t, false><<<grid, 128, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, k, (uint32_t)subs, idx_out, counter);
+            search_filter_kernel<uint32_t, false><<<grid, 128, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, k, (uint32_t)subs, idx_out, counter, only_if);
     } else {
         if (transpose)
-            search_filter_kernel<uint64_t, true><<<grid, 128, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, k, (uint32_t)subs, idx_out, counter);
+            search_filter_kernel<uint64_t, true><<<grid, 128, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, k, (uint32_t)subs, idx_out, counter, only_if);
         else
-            search_filter_kernel<uint64_t, false><<<grid, 128, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, k, (uint32_t)subs, idx_out, counter);
+            search_filter_kernel<uint64_t, false><<<grid, 128, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, k, (uint32_t)subs, idx_out, counter, only_if);
     }
     ctx->launches++;
     TA_CUDA(ctx, cudaGetLastError());
