@@ -19,7 +19,7 @@ CAPTURES = {
     "lev_k16_len4096": ("gpurun_out/prof_fr6_lev_k16_len4096.ncu-rep", 262_144),
     "exp_len1024": ("gpurun_out/prof_fr6_exp_len1024.ncu-rep", 1_000_000),
     "affine_k16_len128": ("gpurun_out/prof_diag16v3_affine_k16_len128.ncu-rep", 1_000_000),
-    "search_n32_h4096": ("gpurun_out/prof_search_n32_h4096_staged.ncu-rep", 100_000),
+    "search_n32_h4096": ("gpurun_out/prof_search_qgram_n32_h4096.ncu-rep", 100_000),
 }
 
 

@@ -1033,6 +1033,7 @@ __global__ void __launch_bounds__(128) search_qgram_resolve_kernel(const uint8_t
                                                                    uint32_t *__restrict__ idx_out,
                                                                    uint32_t *__restrict__ counter) {
     if (*gave_up) return;
+    if ((uint64_t)blockIdx.x * blockDim.x >= *qcount) return;  // the grid is sized for a full queue; most blocks have nothing
     __shared__ W peq[256];
     __shared__ QGram grams[QG_MAX];
     __shared__ uint8_t nd[64];
@@ -1098,7 +1099,8 @@ __global__ void __launch_bounds__(128) search_qgram_resolve_kernel(const uint8_t
             if (elo > ehi) continue;
             const uint64_t st = q + 1 > (uint64_t)fin + 1 + k ? q + 1 - (fin + 1 + k) : 0;
             W VP = ~(W)0, VN = 0, D0prev = ~(W)0, Eqprev = 0;
-            uint32_t score = N;
+            uint32_t score = N, hit_subs = 0;
+            const uint64_t sub0 = elo / TA_SEARCH_SUB;
             const W top = (W)1 << (N - 1);
             for (uint64_t t = st; t <= ehi; t++) {
                 const W Eq = peq[p[t]];
@@ -1116,11 +1118,14 @@ __global__ void __launch_bounds__(128) search_qgram_resolve_kernel(const uint8_t
                 HN <<= 1;
                 VP = HN | ~(D0 | HP);
                 VN = D0 & HP;
-                if (t >= elo && score <= k) {
-                    const uint64_t code = (uint64_t)h * subs + t / TA_SEARCH_SUB;
-                    const uint32_t bit = 1u << (code & 31u);
-                    if (!(atomicOr(&sub_flags[code >> 5], bit) & bit)) idx_out[atomicAdd(counter, 1u)] = (uint32_t)code;
-                }
+                // ends elo .. ehi span at most two sub-segments (2k < TA_SEARCH_SUB): note which, flag after the loop
+                if (t >= elo && score <= k) hit_subs |= t / TA_SEARCH_SUB == sub0 ? 1u : 2u;
+            }
+            for (uint32_t w = 0; w < 2; w++) {
+                if (!(hit_subs >> w & 1u)) continue;
+                const uint64_t code = (uint64_t)h * subs + sub0 + w;
+                const uint32_t bit = 1u << (code & 31u);
+                if (!(atomicOr(&sub_flags[code >> 5], bit) & bit)) idx_out[atomicAdd(counter, 1u)] = (uint32_t)code;
             }
         }
     }
@@ -1172,16 +1177,12 @@ int ta_launch_search_filter(ta_ctx *ctx, const uint8_t *needle_dev, uint32_t nee
         uint32_t *qcount = ctx->d_flags + 16, *gave_up = ctx->d_flags + 17;
         TA_CUDA(ctx, cudaMemsetAsync(sub_flags, 0, flag_bytes + ctr_bytes, st));
         TA_CUDA(ctx, cudaMemsetAsync(qcount, 0, 2 * sizeof(uint32_t), st));  // queue length, gave-up flag
-        // one wave of resident CTAs, chunks handed out dynamically; TA_QGRAM_U=2 picks the 2-load, 5-CTA variant (testing)
-        static const int env_u = getenv("TA_QGRAM_U") ? atoi(getenv("TA_QGRAM_U")) : 0;
+        // one wave of resident CTAs, chunks handed out dynamically.  Four loads per thread and round, 4 CTAs/SM (64
+        // registers): measured against 2 loads x 5 CTAs, 8 x 3 and 4 x 5 (spills) -- 0.302 / 0.308 / 0.315 / 0.346 ms
+        // for the whole search step; TA_QGRAM_CTAS changes the grid (2 and 3 CTAs/SM: 0.316 / 0.310 ms)
         static const int env_ctas = getenv("TA_QGRAM_CTAS") ? atoi(getenv("TA_QGRAM_CTAS")) : 0;
-        if (env_u == 2) {
-            const unsigned blocks = (unsigned)ctx->sm_count * (unsigned)(env_ctas > 0 ? env_ctas : 5);
-            search_qgram_kernel<2, 5><<<blocks, 256, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, pieces, queue, qcount, qcap, gave_up, chunk_ctr);
-        } else {
-            const unsigned blocks = (unsigned)ctx->sm_count * (unsigned)(env_ctas > 0 ? env_ctas : 4);
-            search_qgram_kernel<4, 4><<<blocks, 256, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, pieces, queue, qcount, qcap, gave_up, chunk_ctr);
-        }
+        const unsigned blocks = (unsigned)ctx->sm_count * (unsigned)(env_ctas > 0 && env_ctas <= 4 ? env_ctas : 4);
+        search_qgram_kernel<4, 4><<<blocks, 256, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, pieces, queue, qcount, qcap, gave_up, chunk_ctr);
         ctx->launches++;
         TA_CUDA(ctx, cudaGetLastError());
         const unsigned rblocks = (unsigned)std::min<uint64_t>(((uint64_t)qcap + 127) / 128, (uint64_t)ctx->sm_count * 8);
