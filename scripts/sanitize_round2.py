@@ -34,6 +34,25 @@ for costs in ((2, 1, 3, 0), (2, 2, 1, 3)):
     got, goff = eng.levenshtein_search_batch(needle, hay, hoff, 6, 1, costs)
     want, woff = orc.levenshtein_search_batch(needle, hay, hoff, 6, 1, costs, threads=4)
     assert np.array_equal(goff, woff) and np.array_equal(got, want), ("search weighted", costs)
+# aligned-word 4-gram scan + resolve kernel + split wave items: needles 32 and 64, unaligned ragged haystacks (tight array),
+# 256-letter alphabet (the scan's own path) and a 4-letter one (queue overflow -> device-side fallback kernel)
+for alpha, nlen, k in ((256, 32, 3), (256, 64, 6), (4, 32, 3), (4, 57, 2)):
+    rs = np.random.default_rng(alpha + nlen)
+    nd = rs.integers(0, alpha, size=nlen, dtype=np.uint8)
+    lens = rs.integers(0, 900, size=400)
+    lens[:3] = (0, 3, nlen)
+    hoff2 = np.zeros(401, dtype=np.uint64)
+    hoff2[1:] = np.cumsum(lens)
+    hay2 = rs.integers(0, alpha, size=int(hoff2[-1]), dtype=np.uint8)
+    for i in range(3, 400, 5):
+        if lens[i] > nlen + 4:
+            pos = int(hoff2[i]) + int(rs.integers(0, lens[i] - nlen))
+            hay2[pos:pos + nlen] = nd
+            hay2[pos + int(rs.integers(0, nlen))] ^= 1
+    for st in (0, 1):
+        got, goff = eng.levenshtein_search_batch(nd, hay2, hoff2, k, st)
+        want, woff = orc.levenshtein_search_batch(nd, hay2, hoff2, k, st, threads=4)
+        assert np.array_equal(goff, woff) and np.array_equal(got, want), ("search qgram", alpha, nlen, k, st)
 rng = np.random.default_rng(3)
 long_needle = rng.integers(1, 5, size=500, dtype=np.uint8)
 hay = rng.integers(1, 5, size=40 * 1500, dtype=np.uint8)
