@@ -819,6 +819,7 @@ constexpr uint32_t QG_BITS = 1u << QG_LOG;
 constexpr int QG_MAX = 64;
 constexpr uint32_t QG_CHUNK = 512;  // vectors per chunk: 8 KB
 constexpr uint32_t QG_REGIONS = 8;  // chunk counters (one 128-byte line each)
+constexpr uint32_t QG_GRAN = 16;    // bytes of end positions per flagged granule
 
 __device__ __forceinline__ uint32_t qg_mul(uint32_t x) { return x * 0x9E3779B1u; }  // hash = top QG_LOG bits
 
@@ -1026,7 +1027,7 @@ __global__ void __launch_bounds__(128) search_qgram_resolve_kernel(const uint8_t
                                                                    const uint8_t *__restrict__ hay,
                                                                    const uint64_t *__restrict__ hay_off, size_t n,
                                                                    uint32_t k, uint32_t pieces, uint32_t subs,
-                                                                   const QCand *__restrict__ queue,
+                                                                   uint32_t gran, const QCand *__restrict__ queue,
                                                                    const uint32_t *__restrict__ qcount,
                                                                    const uint32_t *__restrict__ gave_up,
                                                                    uint32_t *__restrict__ sub_flags,
@@ -1100,7 +1101,7 @@ __global__ void __launch_bounds__(128) search_qgram_resolve_kernel(const uint8_t
             const uint64_t st = q + 1 > (uint64_t)fin + 1 + k ? q + 1 - (fin + 1 + k) : 0;
             W VP = ~(W)0, VN = 0, D0prev = ~(W)0, Eqprev = 0;
             uint32_t score = N, hit_subs = 0;
-            const uint64_t sub0 = elo / TA_SEARCH_SUB;
+            const uint64_t sub0 = elo / gran;
             const W top = (W)1 << (N - 1);
             for (uint64_t t = st; t <= ehi; t++) {
                 const W Eq = peq[p[t]];
@@ -1118,10 +1119,10 @@ __global__ void __launch_bounds__(128) search_qgram_resolve_kernel(const uint8_t
                 HN <<= 1;
                 VP = HN | ~(D0 | HP);
                 VN = D0 & HP;
-                // ends elo .. ehi span at most two sub-segments (2k < TA_SEARCH_SUB): note which, flag after the loop
-                if (t >= elo && score <= k) hit_subs |= t / TA_SEARCH_SUB == sub0 ? 1u : 2u;
+                // ends elo .. ehi span a few granules (2k + 1 <= 19 positions): note which, flag after the loop
+                if (t >= elo && score <= k) hit_subs |= 1u << (uint32_t)(t / gran - sub0);
             }
-            for (uint32_t w = 0; w < 2; w++) {
+            for (uint32_t w = 0; hit_subs >> w; w++) {
                 if (!(hit_subs >> w & 1u)) continue;
                 const uint64_t code = (uint64_t)h * subs + sub0 + w;
                 const uint32_t bit = 1u << (code & 31u);
@@ -1140,11 +1141,12 @@ __global__ void __launch_bounds__(128) search_qgram_resolve_kernel(const uint8_t
 // the rest Myers' recurrence over the whole haystack (search_filter_kernel); TA_SEARCH_FILTER=myers|pigeon forces one.
 int ta_launch_search_filter(ta_ctx *ctx, const uint8_t *needle_dev, uint32_t needle_len, const uint8_t *hay,
                             const uint64_t *hay_off, size_t n, uint64_t max_hay, uint32_t k, bool transpose,
-                            uint32_t *idx_out, uint32_t *counter, uint32_t *subs_out, cudaStream_t st) {
+                            uint32_t *idx_out, uint32_t *counter, ta_filter_out *fo, cudaStream_t st) {
     if (needle_len == 0 || needle_len > 64) return TA_ERR_TOO_LARGE;
     const uint64_t subs = max_hay ? (max_hay + TA_SEARCH_SUB - 1) / TA_SEARCH_SUB : 1;
     const uint64_t segs = max_hay ? (max_hay + FILTER_SEG - 1) / FILTER_SEG : 1;
-    *subs_out = (uint32_t)subs;
+    *fo = ta_filter_out();
+    fo->segs = (uint32_t)subs, fo->gran = TA_SEARCH_SUB;
     if (n == 0 || max_hay == 0) return TA_OK;
     if (segs > 65535 || (uint64_t)n * subs > 0xFFFFFFF0ull) return TA_ERR_TOO_LARGE;
     const dim3 grid((unsigned)((n + 127) / 128), (unsigned)segs);
@@ -1159,7 +1161,13 @@ int ta_launch_search_filter(ta_ctx *ctx, const uint8_t *needle_dev, uint32_t nee
     if (force && force[0] != 'q') qgram = false;
     const uint32_t *only_if = nullptr;  // set when the shift-and kernel below is only the q-gram scan's fallback
     if (qgram) {
-        const uint64_t nbits = (uint64_t)n * subs;
+        // the resolve kernel confirms END POSITIONS, so it can flag much finer granules than the scanning filters: 16
+        // bytes instead of TA_SEARCH_SUB -- the exact kernel's serial chain per item is margin + granule + 31 steps
+        const uint64_t subs16 = (max_hay + QG_GRAN - 1) / QG_GRAN;
+        const bool fine = (uint64_t)n * subs16 <= 0xFFFFFFF0ull;
+        const uint64_t qsubs = fine ? subs16 : subs;
+        const uint32_t qgran = fine ? QG_GRAN : (uint32_t)TA_SEARCH_SUB;
+        const uint64_t nbits = (uint64_t)n * qsubs;
         const size_t words = (size_t)((nbits + 31) / 32);
         // queue: one entry per exact 4-gram match; a few per real occurrence on high-entropy input.  More than one per
         // 1024 haystack words means common 4-grams (text, DNA): give up and let the shift-and kernel do it.
@@ -1187,8 +1195,8 @@ int ta_launch_search_filter(ta_ctx *ctx, const uint8_t *needle_dev, uint32_t nee
         TA_CUDA(ctx, cudaGetLastError());
         const unsigned rblocks = (unsigned)std::min<uint64_t>(((uint64_t)qcap + 127) / 128, (uint64_t)ctx->sm_count * 8);
 #define TA_RESOLVE(W, T)                                                                                                      \
-    search_qgram_resolve_kernel<W, T><<<rblocks, 128, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, k, pieces, (uint32_t)subs, \
-                                                               queue, qcount, gave_up, sub_flags, idx_out, counter)
+    search_qgram_resolve_kernel<W, T><<<rblocks, 128, 0, st>>>(needle_dev, needle_len, hay, hay_off, n, k, pieces, (uint32_t)qsubs, \
+                                                               qgran, queue, qcount, gave_up, sub_flags, idx_out, counter)
         if (needle_len <= 32) {
             if (transpose)
                 TA_RESOLVE(uint32_t, true);
@@ -1206,6 +1214,8 @@ int ta_launch_search_filter(ta_ctx *ctx, const uint8_t *needle_dev, uint32_t nee
         // the filter launched below (shift-and for needles <= 32, else Myers) runs only if the scan gave up
         only_if = gave_up;
         pigeon = needle_len <= 32;
+        fo->segs = (uint32_t)qsubs, fo->gran = qgran;
+        fo->alt_flag = gave_up, fo->alt_segs = (uint32_t)subs, fo->alt_gran = TA_SEARCH_SUB;
     }
     if (pigeon) {
         // 256-thread blocks: the 32 KB bank-replicated table is shared by 8 warps (TA_PIGEON_THREADS overrides)

@@ -26,7 +26,7 @@
 // implemented in lev_bitpar.cu: flags[i] = 1 iff haystack i has an end position with unit-cost distance <= k
 int ta_launch_search_filter(ta_ctx *ctx, const uint8_t *needle_dev, uint32_t needle_len, const uint8_t *hay,
                             const uint64_t *hay_off, size_t n, uint64_t max_hay, uint32_t k, bool transpose,
-                            uint32_t *idx_out, uint32_t *counter, uint32_t *segs_out, cudaStream_t st);
+                            uint32_t *idx_out, uint32_t *counter, ta_filter_out *fo, cudaStream_t st);
 
 namespace {
 
@@ -37,6 +37,9 @@ struct SearchArgs {
     const uint32_t *idx;  // optional: work item w -> haystack idx[w] (or a segment code, see segs)
     uint32_t segs;        // 0: idx holds haystack indices.  > 0: idx holds haystack * segs + segment codes and the
                           // item covers only that TA_SEARCH_SUB-byte segment after a warm-up of `warm` bytes
+    uint32_t gran;        // bytes of end positions per segment code
+    const uint32_t *alt_flag;  // if set on the device: the list holds alt_segs / alt_gran codes (the fallback filter ran)
+    uint32_t alt_segs, alt_gran;
     uint32_t warm;
     uint32_t split;       // segment items are cut into `split` parts of TA_SEARCH_SUB / split end positions, a warp each
     size_t n;
@@ -227,13 +230,15 @@ __global__ void __launch_bounds__(128) search_wave_kernel(const SearchArgs args)
     // A warp's item is ONE serial chain of warm + end positions + 31 steps (~75 dependent instructions each), and after
     // a pre-filter there are far fewer items than the GPU has warps -- so a flagged sub-segment is cut into `split`
     // parts, each restarted on its own: more total work, a shorter chain (37 + 32 + 31 steps instead of 37 + 128 + 31).
-    const uint32_t split = args.segs ? args.split : 1u;
+    uint32_t segs = args.segs, gran = args.gran;
+    if (segs && args.alt_flag && *args.alt_flag) segs = args.alt_segs, gran = args.alt_gran;
+    const uint32_t split = segs && gran >= (uint32_t)TA_SEARCH_SUB ? args.split : 1u;
     const size_t n_items = (args.n_dev ? (size_t)*args.n_dev : args.n) * split;
     const size_t n_warps = (size_t)gridDim.x * (blockDim.x >> 5);
     for (size_t w = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < n_items; w += n_warps) {
     const uint32_t part = (uint32_t)(w % split);
     const uint32_t code = args.idx ? args.idx[w / split] : (uint32_t)w;
-    const uint32_t hidx = args.segs ? code / args.segs : code;
+    const uint32_t hidx = segs ? code / segs : code;
     const uint64_t h0 = args.hay_off[hidx], h1 = args.hay_off[hidx + 1];
     const uint8_t *hay = args.hay + h0;
     uint64_t H = h1 - h0;
@@ -248,9 +253,9 @@ __global__ void __launch_bounds__(128) search_wave_kernel(const SearchArgs args)
     // runs: a fresh start `warm` = N + k/gap + 2 bytes before the segment reproduces the reference's (cost, length)
     // for every reported end position inside it (tests/test_search_restart_model.py pins the margin on the CPU).
     uint32_t col0 = 0, emit_from = 0;  // columns are numbered from col0; hits are reported for x + col0 > emit_from
-    if (args.segs) {
-        const uint32_t seg = code % args.segs, span = (uint32_t)TA_SEARCH_SUB / split;
-        emit_from = seg * (uint32_t)TA_SEARCH_SUB + part * span;
+    if (segs) {
+        const uint32_t seg = code % segs, span = gran / split;
+        emit_from = seg * gran + part * span;
         if (emit_from >= H) continue;  // this part lies past the haystack's end
         const uint64_t seg_end = (uint64_t)emit_from + span < H ? (uint64_t)emit_from + span : H;
         col0 = emit_from > args.warm ? emit_from - args.warm : 0;
@@ -461,6 +466,7 @@ static int search_device(ta_ctx *ctx, cudaStream_t st, const uint8_t *d_needle, 
     const uint32_t *d_work_n = nullptr;  // device-side item count (pre-filter path)
     size_t work_n = n;                   // items, or their upper bound while the count is still on the device
     uint32_t segs = 0;                   // > 0: work items are flagged haystack segments (pre-filter ran)
+    ta_filter_out fo;
     static const bool no_filter = getenv("TA_NO_SEARCH_FILTER") != nullptr;  // testing: exact kernel on everything
     uint32_t *counter = ctx->d_flags + 2;
     unsigned long long *d_count = (unsigned long long *)(ctx->d_flags + 4);
@@ -475,11 +481,15 @@ static int search_device(ta_ctx *ctx, cudaStream_t st, const uint8_t *d_needle, 
     if (!no_filter && needle_len <= 64 && !anchored && ku < needle_len) {
         const uint64_t nseg = max_hay ? (max_hay + TA_SEARCH_SUB - 1) / TA_SEARCH_SUB : 1;
         if ((uint64_t)n * nseg <= 0xFFFFFFF0ull && nseg <= 65535) {
-            if ((rc = ta_dev_reserve(ctx, ctx->d_work[0], n * nseg * sizeof(uint32_t))) != TA_OK) return rc;
+            // list capacity: every TA_SEARCH_SUB granule of every haystack (the scanning filters' worst case), which also
+            // bounds what the q-gram resolve kernel can append (<= 8 distinct 16-byte granules per queue entry, queue
+            // capacity n * max_hay / 4096 + 4096: n * nseg / 4 + 32768 entries)
+            if ((rc = ta_dev_reserve(ctx, ctx->d_work[0], (n * nseg + 32768) * sizeof(uint32_t))) != TA_OK) return rc;
             rc = ta_launch_search_filter(ctx, d_needle, (uint32_t)needle_len, d_hay, d_off, n, max_hay, ku,
-                                         costs.transpose != 0, (uint32_t *)ctx->d_work[0].p, counter, &segs, st);
+                                         costs.transpose != 0, (uint32_t *)ctx->d_work[0].p, counter, &fo, st);
+            segs = fo.segs;
             if (rc == TA_OK) {
-                work_n = n * nseg;
+                work_n = n * nseg + 32768;
                 d_work_n = counter;
                 d_idx = (const uint32_t *)ctx->d_work[0].p;
             } else if (rc == TA_ERR_TOO_LARGE) {
@@ -547,6 +557,7 @@ static int search_device(ta_ctx *ctx, cudaStream_t st, const uint8_t *d_needle, 
         SearchArgs sa;
         sa.needle = d_needle, sa.hay = d_hay, sa.hay_off = d_off, sa.idx = d_idx, sa.n = work_n, sa.n_dev = d_work_n;
         sa.segs = segs, sa.warm = (uint32_t)needle_len + k / costs.gap + 2u;
+        sa.gran = fo.gran, sa.alt_flag = fo.alt_flag, sa.alt_segs = fo.alt_segs, sa.alt_gran = fo.alt_gran;
         static const int env_split = getenv("TA_WAVE_SPLIT") ? atoi(getenv("TA_WAVE_SPLIT")) : 0;  // 1, 2, 4, 8 (testing)
         sa.split = (env_split == 1 || env_split == 2 || env_split == 4 || env_split == 8) ? (uint32_t)env_split : 2u;
         sa.needle_len = (uint32_t)needle_len, sa.k = k;

@@ -60,6 +60,15 @@ void ta_multi_shutdown(ta_ctx *ctx);
 
 // Concatenates per-shard (items, offsets) outputs -- shard r covers units bound[r] .. bound[r + 1] and its arrays came
 // from ta_out_alloc -- into one pair of caller-owned arrays; frees the shard arrays.
+// what ta_launch_search_filter (lev_bitpar.cu) queued: a device list of codes haystack * segs + granule, `gran` bytes of
+// end positions per granule.  If alt_flag is non-null and set ON THE DEVICE when the exact kernel runs, the list was
+// written by the fallback filter instead and holds alt_segs / alt_gran codes.
+struct ta_filter_out {
+    uint32_t segs = 0, gran = 0;
+    const uint32_t *alt_flag = nullptr;
+    uint32_t alt_segs = 0, alt_gran = 0;
+};
+
 template <typename T>
 int ta_concat_lists(int parts, const std::vector<size_t> &bound, size_t n, std::vector<T *> &items,
                     std::vector<uint64_t *> &offs, T **out_items, uint64_t **out_off) {
