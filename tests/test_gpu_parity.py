@@ -160,6 +160,25 @@ def test_hamming_search_random(eng):
         eng.hamming_search_batch(b"de", hay, hoff, 1, 0)
 
 
+@pytest.mark.parametrize("nlen", [49 * 1024 + 3, 240 * 1024 + 5])
+def test_hamming_search_large_needles(eng, nlen):
+    """needles beyond the default 48 KB of dynamic shared memory (opt-in) and beyond what an SM has at all (the needle
+    is then read from global memory); the reference takes any length (src/hamming.rs:440-520)"""
+    rng = np.random.default_rng(nlen)
+    needle = rng.integers(1, 255, size=nlen, dtype=np.uint8)
+    a = rng.integers(1, 255, size=nlen + 300, dtype=np.uint8)
+    a[100:100 + nlen] = needle
+    a[100 + 17] ^= 1
+    a[100 + nlen - 1] ^= 2
+    b = rng.integers(1, 255, size=nlen - 1, dtype=np.uint8)   # shorter than the needle: no match
+    c = needle.copy()                                          # exactly the needle
+    hay, hoff = _pack([a.tobytes(), b.tobytes(), c.tobytes()])
+    for k, st in ((2, 0), (1, 1), (5, 1)):
+        got, goff = eng.hamming_search_batch(needle.tobytes(), hay, hoff, k, st)
+        want, woff = orc.hamming_search_batch(needle.tobytes(), hay, hoff, k, st, threads=2)
+        assert np.array_equal(goff, woff) and np.array_equal(got, want), (nlen, k, st)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # error behaviour of the boundary
 def test_hamming_search_naive_accepts_nul_bytes(eng):

@@ -27,15 +27,20 @@ struct HHit {
     uint64_t start;
 };
 
+template <bool SMEM>  // needle staged in shared memory (the rule), or read through L1 / L2 when it does not fit
 __global__ void __launch_bounds__(256) hamming_search_kernel(const uint8_t *__restrict__ needle, uint32_t N,
                                                              const uint8_t *__restrict__ hay,
                                                              const uint64_t *__restrict__ hay_off, size_t n,
                                                              uint64_t max_hay, uint32_t k, HHit *__restrict__ hits,
                                                              unsigned long long *__restrict__ hit_count,
                                                              unsigned long long hit_cap, uint32_t *__restrict__ nul_flag) {
-    extern __shared__ uint8_t sneedle[];
-    for (uint32_t q = threadIdx.x; q < N; q += blockDim.x) sneedle[q] = needle[q];
-    __syncthreads();
+    extern __shared__ uint8_t sneedle_buf[];
+    const uint8_t *sneedle = needle;
+    if (SMEM) {
+        for (uint32_t q = threadIdx.x; q < N; q += blockDim.x) sneedle_buf[q] = needle[q];
+        __syncthreads();
+        sneedle = sneedle_buf;
+    }
     // blockIdx.y walks haystacks (grid-stride), blockIdx.x * blockDim.x + threadIdx.x walks positions
     for (size_t h = blockIdx.y; h < n; h += gridDim.y) {
         const uint64_t h0 = hay_off[h], H = hay_off[h + 1] - h0;
@@ -155,9 +160,20 @@ static int hamming_search_impl(ta_ctx *ctx, bool check_nul, const uint8_t *needl
                 if ((rc = ta_dev_reserve(ctx, ctx->d_work[1], cap * sizeof(HHit))) != TA_OK) return rc;
                 TA_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st));
                 TA_CUDA(ctx, cudaMemsetAsync(nul_flag, 0, sizeof(uint32_t), st));
-                hamming_search_kernel<<<dim3(gx, gy), 256, (needle_len + 15) & ~(size_t)15, st>>>(
-                    (const uint8_t *)ctx->d_b[0].p, (uint32_t)needle_len, d_hay, (const uint64_t *)ctx->d_aoff[0].p, n,
-                    max_hay, k, (HHit *)ctx->d_work[1].p, d_count, cap, nul_flag);
+                // needles above 48 KB opt in to more dynamic shared memory; above the device's limit (227 KB) the kernel
+                // reads the needle from global memory (such needles used to fail at launch)
+                const size_t nsmem = (needle_len + 15) & ~(size_t)15;
+                if (nsmem <= (size_t)ctx->smem_optin) {
+                    if (nsmem > 48 * 1024)
+                        TA_CUDA(ctx, cudaFuncSetAttribute(hamming_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nsmem));
+                    hamming_search_kernel<true><<<dim3(gx, gy), 256, nsmem, st>>>(
+                        (const uint8_t *)ctx->d_b[0].p, (uint32_t)needle_len, d_hay, (const uint64_t *)ctx->d_aoff[0].p, n,
+                        max_hay, k, (HHit *)ctx->d_work[1].p, d_count, cap, nul_flag);
+                } else {
+                    hamming_search_kernel<false><<<dim3(gx, gy), 256, 0, st>>>(
+                        (const uint8_t *)ctx->d_b[0].p, (uint32_t)needle_len, d_hay, (const uint64_t *)ctx->d_aoff[0].p, n,
+                        max_hay, k, (HHit *)ctx->d_work[1].p, d_count, cap, nul_flag);
+                }
                 ctx->launches++;
                 TA_CUDA(ctx, cudaGetLastError());
                 TA_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags + 4, ctx->d_flags + 4, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
