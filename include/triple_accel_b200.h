@@ -178,7 +178,15 @@ int ta_hamming_search_naive_batch(ta_ctx *ctx, const uint8_t *needle, size_t nee
 
 /* ---- device-resident entry points (kernel-only; all pointers are device pointers on ctx's device) ---------- */
 /* `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  Calls are asynchronous.
- * `max_len` is an upper bound on the length of any string in the batch (picks the kernel variant). */
+ * `max_len` is an upper bound on the length of any string in the batch (picks the kernel variant).
+ * Ordering: the kernels use scratch buffers that belong to the context (counters, index lists, wide-band and
+ * search workspaces), so all work submitted through ONE context must be ordered by the caller -- use one stream per
+ * context, or make a later call's stream wait on the earlier one; two streams that should overlap need two contexts
+ * (contexts are cheap: a few streams, events and lazily grown buffers).
+ * Buffers: the string buffers must be readable from the 16-byte boundary at or below their first byte to the
+ * 16-byte boundary at or above their last one (the general-cost kernel stages whole aligned 16-byte vectors);
+ * anything returned by cudaMalloc / a caching allocator satisfies this, a tight sub-allocation inside a larger
+ * buffer does too as long as it does not end in the buffer's last 15 bytes. */
 int ta_hamming_batch_dev(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b,
                          const uint64_t *b_off, size_t n, uint32_t *out, void *stream);
 int ta_levenshtein_k_batch_dev(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b,
