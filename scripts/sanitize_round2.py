@@ -9,6 +9,7 @@ import sys
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+os.environ.setdefault("TA_SEARCH_FILTER", "qgram")  # the dispatcher takes the q-gram scan from 64 MB per call: force it here
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import _oracle as orc  # noqa: E402

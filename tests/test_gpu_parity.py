@@ -554,7 +554,10 @@ def test_search_filter_long_needles_and_transpositions(eng):
 
 
 def test_search_qgram_filter(eng):
-    """the aligned-word (4-gram) pre-filter: needles of up to 64 bytes whose k + 1 (2k + 1) pieces are >= 7 bytes.  Alphabets of 2 / 4
+    """the aligned-word (4-gram) pre-filter: needles of up to 64 bytes whose k + 1 (2k + 1) pieces are >= 7 bytes.
+    The dispatcher takes it from 64 MB (8 MB for needles > 32) of haystacks per call -- test_search_qgram_big_batch runs
+    it at that size; here the forced-variant run (TA_SEARCH_FILTER=qgram) is what exercises it, the plain run pins the
+    scanning filters on the same inputs.  Alphabets of 2 / 4
     symbols make every word a candidate (the queue, the whole-piece compare and the verification do the work; big
     batches overflow the queue and take the shift-and fallback), 256 symbols is the case it is built for; haystacks
     are ragged, start at every alignment, and include empty and shorter-than-a-word ones."""
@@ -578,6 +581,26 @@ def test_search_qgram_filter(eng):
                 got, goff = eng.levenshtein_search_batch(needle, hay, hoff, k, st, costs)
                 want, woff = orc.levenshtein_search_batch(needle, hay, hoff, k, st, costs, threads=8)
                 assert np.array_equal(goff, woff) and np.array_equal(got, want), (nlen, k, costs, alpha, st)
+
+
+@pytest.mark.parametrize("nlen,k,alpha", [(32, 3, 256), (64, 6, 256), (32, 3, 4)])
+def test_search_qgram_big_batch(eng, nlen, k, alpha):
+    """70 MB of haystacks: the default dispatch takes the q-gram scan (alphabet 4: its queue overflows and the fallback
+    kernel runs); the oracle checks a slice, the rest through the planted needles every haystack of the slice pattern
+    must report"""
+    from triple_accel_b200 import synth
+    n, hlen = 18000, 4096
+    needle = np.random.default_rng(nlen).integers(1, 256, size=nlen, dtype=np.uint8)
+    hay, hoff = synth.planted_haystacks(n, hlen, needle, plant_frac=0.05, max_edits=k, seed=nlen + alpha)
+    if alpha != 256:  # the same map on both sides keeps the planted copies planted
+        hay = (hay % alpha).astype(np.uint8)
+        needle = (needle % alpha).astype(np.uint8)
+    needle = needle.tobytes()
+    got, goff = eng.levenshtein_search_batch(needle, hay, hoff, k, 1)
+    chk = 600
+    want, woff = orc.levenshtein_search_batch(needle, np.asarray(hay)[: chk * hlen], np.asarray(hoff)[: chk + 1], k, 1, threads=8)
+    assert np.array_equal(goff[: chk + 1], woff) and np.array_equal(got[: int(woff[-1])], want)
+    assert int(goff[-1]) >= int(woff[-1])
 
 
 @pytest.mark.parametrize("nlen", [257, 301, 453, 1000])
@@ -804,14 +827,16 @@ SEARCH_TESTS = ("test_search_random or test_search_planted or test_kat_search or
     ({"TA_SEARCH_FILTER": "myers"}, SEARCH_TESTS),
     ({"TA_SEARCH_FILTER": "pigeon"}, SEARCH_TESTS),
     ({"TA_SEARCH_FILTER": "pigeon", "TA_PIGEON_STAGED": "0"}, SEARCH_TESTS),
-    ({"TA_QGRAM_QCAP": "1"}, SEARCH_TESTS),
+    ({"TA_SEARCH_FILTER": "qgram"}, SEARCH_TESTS),
+    ({"TA_SEARCH_FILTER": "qgram", "TA_QGRAM_QCAP": "1"}, SEARCH_TESTS),
 ], ids=["general-band-kernel", "diagonal-extension-kernel-forced", "u16-thread-per-pair-kernel-forced", "u16-thread-per-pair-kernel-on-unit-costs",
         "u16-thread-per-pair-kernel-single-stage", "u16-thread-per-pair-kernel-off", "diagonal-extension-kernel-off", "bitpar-simd-kernel", "bitpar-sliding-table-kernel",
         "bitpar-sliding-table-32bit-on-narrow-bands", "bitpar-block-table-one-pair-per-thread", "length-bucketing-pre-pass", "bitpar-block-table-256-entries",
         "bitpar-block-table-8-blocks", "bitpar-block-table-256-entries-8-blocks",
         "bitpar-table-2plane-kernel", "search-thread-kernel-nofilter", "search-wave-kernel-nofilter",
         "search-thread-kernel-filter", "search-global-rows-kernel-nofilter", "search-myers-filter-forced", "search-pigeonhole-filter-forced",
-        "search-pigeonhole-filter-lane-per-segment-loads", "search-qgram-filter-gives-up-and-falls-back"])
+        "search-pigeonhole-filter-lane-per-segment-loads", "search-qgram-filter-forced-on-small-batches",
+        "search-qgram-filter-gives-up-and-falls-back"])
 def test_every_kernel_variant_forced(env, select):
     """The dispatchers pick a kernel from the cost model, band width and batch size (bit-parallel vs general banded
     kernel; pre-filter + warp-wavefront vs thread-per-haystack exact search).  These switches force the variants

@@ -1159,6 +1159,11 @@ int ta_launch_search_filter(ta_ctx *ctx, const uint8_t *needle_dev, uint32_t nee
     bool qgram = needle_len <= 64 && pieces <= needle_len && needle_len / pieces >= 7 &&
                  pieces * (needle_len / pieces + 1 - 3) <= (uint32_t)QG_MAX;
     if (force && force[0] != 'q') qgram = false;
+    // Three launches more than the scanning filters: pays from ~64 MB of haystacks per call (needles <= 32: 0.45 us/MB
+    // for the shift-and kernel against 0.2 us/MB + ~20 us; 8-way strong scaling of cfg 4 leaves 51 MB per GPU and was
+    // 0.161 ms with the shift-and kernel, 0.174 ms with the scan) or ~8 MB (longer needles: the Myers filter takes
+    // 2.3 us/MB).  TA_SEARCH_FILTER=qgram takes it at any size (tests).
+    if (!(force && force[0] == 'q') && (uint64_t)n * max_hay < (needle_len <= 32 ? (64ull << 20) : (8ull << 20))) qgram = false;
     const uint32_t *only_if = nullptr;  // set when the shift-and kernel below is only the q-gram scan's fallback
     if (qgram) {
         // the resolve kernel confirms END POSITIONS, so it can flag much finer granules than the scanning filters: 16
