@@ -157,7 +157,7 @@ def reference_cpu_run(orc, op, a, ao, b, bo, k, costs, cnt, threads, length):
     return oracle_run(orc, op, a, ao, b, bo, k, costs, cnt, threads), "scalar oracle (port of the reference's scalar routine)"
 
 
-def dominant_kernel(op, k, costs, length):
+def dominant_kernel(op, k, costs, length, n_units=None):
     """name of the kernel the dispatcher picks for this workload (triple_accel_b200/csrc/api.cu: ta_launch_lev)"""
     if op == "hamming":
         return "hamming_kernel"
@@ -168,7 +168,8 @@ def dominant_kernel(op, k, costs, length):
         nlen = SEARCH_NEEDLE[0]
         pieces = (2 * k + 1) if costs[3] else (k + 1)
         forced = os.environ.get("TA_SEARCH_FILTER", "")
-        if nlen <= 64 and pieces <= nlen and nlen // pieces >= 7 and forced in ("", "qgram"):
+        big = n_units is None or n_units * length >= ((64 << 20) if nlen <= 32 else (8 << 20))  # lev_bitpar.cu dispatch
+        if nlen <= 64 and pieces <= nlen and nlen // pieces >= 7 and (forced == "qgram" or (forced == "" and big)):
             return "search_qgram_kernel (+ search_qgram_resolve_kernel, search_wave_kernel on the flagged 128-byte sub-segments)"
         if nlen <= 32 and pieces <= nlen and nlen // pieces >= 4 and forced != "myers":
             return "search_pigeon_staged_kernel (+ search_wave_kernel on the flagged 128-byte sub-segments)"
@@ -491,7 +492,7 @@ class Runner:
             "name": name, "scaling": scaling if world > 1 else "single-gpu", "ms_per_step": ms_step,
             "units_per_s": total_units / (ms_step * 1e-3), "value": value, "unit": "GCUPS", "steps": steps,
             "frac_hbm": achieved / self.peak, "achieved_gbs": achieved, "algorithmic_bytes_per_launch": alg_bytes,
-            "kernel": dominant_kernel(bop, k, costs, length), "gpu_launches": int(launches), "parity_ok": parity_ok,
+            "kernel": dominant_kernel(bop, k, costs, length, n), "gpu_launches": int(launches), "parity_ok": parity_ok,
             "parity_checked_units": chk,
         }
         cnt = self.ncu_counts.get(name)
