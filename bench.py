@@ -157,7 +157,7 @@ def reference_cpu_run(orc, op, a, ao, b, bo, k, costs, cnt, threads, length):
     return oracle_run(orc, op, a, ao, b, bo, k, costs, cnt, threads), "scalar oracle (port of the reference's scalar routine)"
 
 
-def dominant_kernel(op, k, costs, length, n_units=None):
+def dominant_kernel(op, k, costs, length, n_units=None, ragged=False):
     """name of the kernel the dispatcher picks for this workload (triple_accel_b200/csrc/api.cu: ta_launch_lev)"""
     if op == "hamming":
         return "hamming_kernel"
@@ -184,7 +184,8 @@ def dominant_kernel(op, k, costs, length, n_units=None):
         w_bound = (min(k, length * max(costs[0], costs[1]) + costs[2]) - costs[2]) // costs[1] + 1 + (2 if costs[3] else 0)
         return "lev_diag16_kernel" if w_bound <= 32 else "lev_band_kernel"
     if band <= 9 and not costs[3]:
-        return "lev_bitpar_duo_kernel"
+        tiled = {"0": False, "1": True}.get(os.environ.get("TA_DUO_TILED", ""), ragged)
+        return "lev_bitpar_duo_tiled_kernel" if tiled else "lev_bitpar_duo_kernel"
     if band <= 25:
         return "lev_bitpar_blk_kernel<C=%d>" % (16 if band <= 17 else 8)
     return "lev_bitpar_tab_kernel<%s>" % ("u32" if band <= 32 else "u64")
@@ -429,6 +430,9 @@ class Runner:
         d_a, d_ao, d_b, d_bo = to_dev(a), to_dev(ao), to_dev(b), to_dev(bo)
         d_out = torch.empty(max(n, 1), dtype=torch.int32, device=self.dev)
         last = {}
+        # the device-resident entry points cannot look at the offsets: the caller says whether the lengths vary
+        # (ta_set_length_hint; the host-buffer calls of the e2e leg decide from the offsets themselves)
+        eng.set_length_hint(True if op == "lev_k_ragged" else None)
 
         def step_dev():
             if bop == "hamming":
@@ -492,7 +496,7 @@ class Runner:
             "name": name, "scaling": scaling if world > 1 else "single-gpu", "ms_per_step": ms_step,
             "units_per_s": total_units / (ms_step * 1e-3), "value": value, "unit": "GCUPS", "steps": steps,
             "frac_hbm": achieved / self.peak, "achieved_gbs": achieved, "algorithmic_bytes_per_launch": alg_bytes,
-            "kernel": dominant_kernel(bop, k, costs, length, n), "gpu_launches": int(launches), "parity_ok": parity_ok,
+            "kernel": dominant_kernel(bop, k, costs, length, n, op == "lev_k_ragged"), "gpu_launches": int(launches), "parity_ok": parity_ok,
             "parity_checked_units": chk,
         }
         cnt = self.ncu_counts.get(name)

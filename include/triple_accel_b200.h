@@ -102,6 +102,15 @@ int ta_device(ta_ctx *ctx);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 uint64_t ta_launch_count(ta_ctx *ctx);
 
+/* Length hint for the unit-cost distance kernels of this ctx.  Batches whose pairs differ in length by more than a
+ * 16-byte class (say 96..160 bytes) run ~20 % faster when the kernel orders each tile of pairs by length first
+ * (lev_bitpar_duo_tiled_kernel); equal-length batches are ~5 % faster without that pass.  The host-buffer entry
+ * points see the offsets and decide per batch; the *_dev entry points cannot (the offsets are on the device), so the
+ * caller may say: ragged = 1 (lengths vary), 0 (equal lengths), -1 (default: host-buffer calls decide from the
+ * offsets, *_dev calls assume equal lengths).  Results never depend on the hint.  On a multi-device ctx it applies
+ * to every device. */
+int ta_set_length_hint(ta_ctx *ctx, int ragged);
+
 /* Pinned host memory for fast H2D/D2H of batch buffers (optional: any host pointer is accepted). */
 void *ta_host_alloc(size_t bytes);
 void ta_host_free(void *p);

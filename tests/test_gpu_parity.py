@@ -728,6 +728,44 @@ def test_traceback_long_strings_unbounded_k(eng):
                 assert dist[i] == wd and got == [tuple(e) for e in we], (i, costs, exp)
 
 
+@pytest.mark.parametrize("n", [1, 2047, 2048, 2049, 70001])
+def test_lev_duo_ragged_tiles(eng, n):
+    """two pairs per thread behind the tile-local length ordering (lev_bitpar_duo_tiled_kernel): ragged batches with
+    empty strings, batch sizes around the 2048-pair tile, one-class tiles (identity order) and many-class tiles, k <= 8"""
+    from triple_accel_b200 import synth
+    for lo, hi, seed in ((0, 200, 1), (128, 128, 2), (96, 160, 3), (1, 17, 4)):
+        a, ao, b, bo = synth.edited_pairs(n, lo, hi, 8, seed=seed + n, allow_swap=False)
+        for k in (8, 3):
+            got = eng.levenshtein_k_batch(a, ao, b, bo, k)
+            want = orc.levenshtein_k_batch(a, ao, b, bo, k, threads=8)
+            assert np.array_equal(got, want), (n, lo, hi, k)
+
+
+def test_length_hint_changes_the_kernel_not_the_result(eng):
+    """ta_set_length_hint: device-resident calls take the tile-ordered kernel only when told that lengths vary; the
+    host-buffer calls decide from the offsets.  Same distances either way."""
+    import torch
+    from triple_accel_b200 import synth
+    a, ao, b, bo = synth.edited_pairs(30000, 40, 200, 8, seed=99, allow_swap=False)
+    want = orc.levenshtein_k_batch(a, ao, b, bo, 8, threads=8)
+    dev = torch.device("cuda:0")
+
+    def td(x):
+        return torch.from_numpy(x.view(np.int64) if x.dtype == np.uint64 else x).to(dev)
+    d_a, d_ao, d_b, d_bo = td(a), td(ao), td(b), td(bo)
+    d_out = torch.empty(len(ao) - 1, dtype=torch.int32, device=dev)
+    try:
+        for hint in (True, False, None):
+            eng.set_length_hint(hint)
+            d_out.fill_(7)
+            eng.levenshtein_k_batch_dev(d_a, d_ao, d_b, d_bo, 8, (1, 1, 0, 0), 200, d_out)
+            torch.cuda.synchronize()
+            assert np.array_equal(d_out.cpu().numpy().view(np.uint32), want), hint
+            assert np.array_equal(eng.levenshtein_k_batch(a, ao, b, bo, 8), want), hint
+    finally:
+        eng.set_length_hint(None)
+
+
 def test_full_size_properties(eng):
     """BASELINE.json sizes (1 M pairs, len 128, k = 8 and 16; 1 M x len 512 Damerau is covered by the bench's parity
     check) through size-independent properties: symmetry, identity, the edit budget as an upper bound, monotonicity
@@ -797,7 +835,7 @@ def test_cpp_header_mirror(tmp_path):
     assert r.returncode == 0 and "hpp ok" in r.stdout, r.stdout + r.stderr
 
 
-LEV_TESTS = "test_lev_k_mutated or test_lev_k_random_short or test_nul_bytes or test_lev_exp"
+LEV_TESTS = "test_lev_k_mutated or test_lev_k_random_short or test_nul_bytes or test_lev_exp or test_lev_duo_ragged_tiles"
 FR_TESTS = LEV_TESTS + " or test_lev_fr_long_strings or test_lev_full_matrix"
 SEARCH_TESTS = ("test_search_random or test_search_planted or test_kat_search or test_search_qgram_filter or "
                 "test_search_filter_long_needles_and_transpositions or test_search_segment_warmup")
@@ -815,6 +853,8 @@ SEARCH_TESTS = ("test_search_random or test_search_planted or test_kat_search or
     ({"TA_BITPAR": "tab"}, LEV_TESTS),
     ({"TA_BITPAR": "tab", "TA_BITPAR_BITS": "32"}, LEV_TESTS),
     ({"TA_BLK_DUO": "0", "TA_EXP_FIRST_K": "30"}, LEV_TESTS),
+    ({"TA_DUO_TILED": "0"}, LEV_TESTS + " or test_full_size"),
+    ({"TA_DUO_TILED": "1"}, LEV_TESTS + " or test_full_size"),
     ({"TA_LEN_BUCKETS": "1"}, LEV_TESTS + " or test_full_size"),
     ({"TA_BLK_PLANES": "0"}, LEV_TESTS),
     ({"TA_BLK_PLANES": "1", "TA_BLK_C": "8"}, LEV_TESTS),
@@ -831,7 +871,7 @@ SEARCH_TESTS = ("test_search_random or test_search_planted or test_kat_search or
     ({"TA_SEARCH_FILTER": "qgram", "TA_QGRAM_QCAP": "1"}, SEARCH_TESTS),
 ], ids=["general-band-kernel", "diagonal-extension-kernel-forced", "u16-thread-per-pair-kernel-forced", "u16-thread-per-pair-kernel-on-unit-costs",
         "u16-thread-per-pair-kernel-single-stage", "u16-thread-per-pair-kernel-off", "diagonal-extension-kernel-off", "bitpar-simd-kernel", "bitpar-sliding-table-kernel",
-        "bitpar-sliding-table-32bit-on-narrow-bands", "bitpar-block-table-one-pair-per-thread", "length-bucketing-pre-pass", "bitpar-block-table-256-entries",
+        "bitpar-sliding-table-32bit-on-narrow-bands", "bitpar-block-table-one-pair-per-thread", "bitpar-duo-kernel-without-tile-ordering", "bitpar-duo-kernel-tile-ordered-always", "length-bucketing-pre-pass", "bitpar-block-table-256-entries",
         "bitpar-block-table-8-blocks", "bitpar-block-table-256-entries-8-blocks",
         "bitpar-table-2plane-kernel", "search-thread-kernel-nofilter", "search-wave-kernel-nofilter",
         "search-thread-kernel-filter", "search-global-rows-kernel-nofilter", "search-myers-filter-forced", "search-pigeonhole-filter-forced",

@@ -45,6 +45,7 @@ SIGNATURES = {
     "ta_multi_uses_nccl": (_int, [_vp]),
     "ta_multi_needle_broadcasts": (C.c_uint64, [_vp]),
     "ta_trim": (None, []),
+    "ta_set_length_hint": (_int, [_vp, _int]),
     "ta_shutdown": (None, [_vp]),
     "ta_strerror": (C.c_char_p, [_int]),
     "ta_last_error": (C.c_char_p, [_vp]),

@@ -148,6 +148,11 @@ class Engine:
     def needle_broadcasts(self):
         return int(self._lib.ta_multi_needle_broadcasts(self._h))
 
+    def set_length_hint(self, ragged):
+        """ta_set_length_hint: True = the pairs' lengths vary (tile-ordered kernel), False = equal lengths, None = default
+        (host-buffer calls decide from the offsets, device-resident calls assume equal lengths).  Never changes results."""
+        self._check(self._lib.ta_set_length_hint(self._h, -1 if ragged is None else int(bool(ragged))))
+
     def close(self):
         if getattr(self, "_h", None):
             self._lib.ta_shutdown(self._h)

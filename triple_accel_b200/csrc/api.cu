@@ -132,7 +132,7 @@ void ta_shutdown(ta_ctx *ctx) {
 static void destroy_ctx_resources(ta_ctx *ctx) {
     DevBuf *dev[] = {&ctx->d_a[0], &ctx->d_a[1], &ctx->d_b[0], &ctx->d_b[1], &ctx->d_aoff[0], &ctx->d_aoff[1],
                      &ctx->d_boff[0], &ctx->d_boff[1], &ctx->d_out[0], &ctx->d_out[1], &ctx->d_work[0],
-                     &ctx->d_work[1], &ctx->d_work[2], &ctx->d_work[3]};
+                     &ctx->d_work[1], &ctx->d_work[2], &ctx->d_work[3], &ctx->d_work[4]};
     for (DevBuf *b : dev)
         if (b->p) cudaFree(b->p);
     for (DevBuf &b : ctx->h_pin)
@@ -223,6 +223,15 @@ void ta_free(void *p) {
     free(h);
 }
 
+int ta_set_length_hint(ta_ctx *ctx, int ragged) {
+    if (!ctx) return TA_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->len_hint = ragged < 0 ? -1 : (ragged ? 1 : 0);
+    if (ctx->multi)
+        for (int r = 0; r < ta_device_count(ctx); r++) ta_multi_sub(ctx, r)->len_hint = ctx->len_hint;
+    return TA_OK;
+}
+
 void ta_trim(void) {  // hands the parked output blocks back to the allocator
     std::lock_guard<std::mutex> lock(g_out_mu);
     for (int i = 0; i < OUT_SLOTS; i++) {
@@ -265,17 +274,21 @@ namespace {
 struct BatchStats {
     uint64_t a_bytes = 0, b_bytes = 0;
     uint32_t max_len = 0;
+    bool ragged = false;  // more than 1/8 of the pairs are in another 16-byte length class than the first pair
 };
 
 // validates monotone offsets, computes totals; returns TA_OK or an error
 int scan_offsets(const uint64_t *a_off, const uint64_t *b_off, size_t n, bool need_equal, BatchStats &st) {
-    uint64_t max_len = 0, bad = 0, mismatch = 0;
+    uint64_t max_len = 0, bad = 0, mismatch = 0, other_class = 0;
+    const uint64_t cls0 = n ? std::max(a_off[1] - a_off[0], b_off[1] - b_off[0]) >> 4 : 0;
     for (size_t i = 0; i < n; i++) {  // branch-free so that it vectorises
         const uint64_t la = a_off[i + 1] - a_off[i], lb = b_off[i + 1] - b_off[i];
         bad |= (uint64_t)(a_off[i + 1] < a_off[i]) | (uint64_t)(b_off[i + 1] < b_off[i]);
         max_len = std::max(max_len, std::max(la, lb));
         mismatch |= la ^ lb;
+        other_class += (uint64_t)((std::max(la, lb) >> 4) != cls0);
     }
+    st.ragged = other_class * 8 > n;
     if (bad) return TA_ERR_BAD_ARG;
     if (max_len > TA_MAX_STRING_LEN && !need_equal) return TA_ERR_TOO_LARGE;  // DP cells are u32; Hamming has no such limit
     st.a_bytes = a_off[n] - a_off[0];
@@ -431,6 +444,7 @@ int run_pairs(ta_ctx *ctx, Op op, const uint8_t *a, const uint64_t *a_off, const
         cudaStreamSynchronize(cp);
         return rc;
     }
+    ctx->batch_ragged = ctx->len_hint < 0 ? bs.ragged : ctx->len_hint != 0;
     if (op == OP_HAMMING) TA_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, sizeof(uint32_t), st));
     for (int c = 0; c < chunks && rc == TA_OK; c++) {
         const size_t lo = bound[c], cn = bound[c + 1] - bound[c];
@@ -589,6 +603,7 @@ int trace_batch(ta_ctx *ctx, bool exp_mode, const uint8_t *a, const uint64_t *a_
             TA_CUDA(ctx, cudaSetDevice(ctx->device));
             BatchStats bs;
             int r = scan_offsets(a_off, b_off, n, false, bs);
+            ctx->batch_ragged = ctx->len_hint < 0 ? bs.ragged : ctx->len_hint != 0;
             if (r != TA_OK) return r;
             if ((bs.a_bytes && !a) || (bs.b_bytes && !b)) return TA_ERR_BAD_ARG;
             cudaStream_t st = ctx->stream;
@@ -695,6 +710,7 @@ int ta_levenshtein_k_batch_dev(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_
     if (max_len > TA_MAX_STRING_LEN) return TA_ERR_TOO_LARGE;
     std::lock_guard<std::mutex> lock(ctx->mu);
     TA_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->batch_ragged = ctx->len_hint > 0;
     return ta_launch_lev(ctx, a, a_off, b, b_off, n, nullptr, k, costs, max_len, out, (cudaStream_t)stream);
 }
 
@@ -709,6 +725,7 @@ int ta_levenshtein_exp_batch_dev(ta_ctx *ctx, const uint8_t *a, const uint64_t *
     if (max_len > TA_MAX_STRING_LEN || n > 0xFFFFFFF0ull) return TA_ERR_TOO_LARGE;
     std::lock_guard<std::mutex> lock(ctx->mu);
     TA_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->batch_ragged = ctx->len_hint > 0;
     return exp_rounds_dev(ctx, a, a_off, b, b_off, n, costs, max_len, out, (cudaStream_t)stream);
 }
 

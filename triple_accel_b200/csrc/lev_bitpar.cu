@@ -191,6 +191,205 @@ __global__ void __launch_bounds__(128, 3) lev_bitpar_duo_kernel(const uint8_t *_
 }
 
 
+// The same two-pairs-per-thread routine behind a tile-local ordering (round 2; taken for ragged batches, see
+// ta_set_length_hint; TA_DUO_TILED=0|1 forces one of the two kernels).  A thread's two pairs can only share a recurrence when they have the same number of 16-column supersteps, and
+// a warp runs as long as its longest pair -- on ragged batches (lengths 96..160) every warp fell back to the single-pair
+// path and waited for its longest lane: 0.32 ms per 1 M pairs against 0.20 ms for equal lengths.  A global counting
+// sort fixes that (TA_LEN_BUCKETS=1, below) but costs three launches, ~30 us, on every batch.  Here each CTA takes a
+// TILE of DUO_TILE consecutive pairs, counts them by length class (longer length / 16) in shared memory, and -- unless
+// one class holds the whole tile, the case of equal-length batches, which keep their order -- places the tile's pair
+// indices in class order (2 bytes per pair).  Round r of the tile then gives thread t the sorted positions
+// 2 (128 r + t) and + 1: a thread's two pairs and a warp's 64 pairs are neighbours in length.  The pass costs ~12
+// instructions per pair (a pair is ~4 000) and the offsets it reads are read again, from L1 / L2, when the pair is run.
+constexpr int DUO_TILE = 3072;   // most pairs per tile (2-byte slots in shared memory); a multiple of 256 = one round
+constexpr int DUO_CLASSES = 64;  // length classes (longer length / 16, clamped)
+constexpr int DUO_SLOTS = DUO_TILE + DUO_CLASSES;  // slots of a tile's order: every class starts at an even position
+__global__ void __launch_bounds__(128, 3) lev_bitpar_duo_tiled_kernel(const uint8_t *__restrict__ a,
+                                                                      const uint64_t *__restrict__ a_off,
+                                                                      const uint8_t *__restrict__ b,
+                                                                      const uint64_t *__restrict__ b_off,
+                                                                      const uint32_t *__restrict__ idx, size_t n, uint32_t k,
+                                                                      uint16_t *__restrict__ order_ws,
+                                                                      uint32_t *__restrict__ out) {
+    extern __shared__ __align__(16) uint8_t tabs_raw[];
+    uint32_t *tabs = (uint32_t *)tabs_raw;
+    const uint32_t nt = blockDim.x;  // 128
+    // Not one byte of shared memory beyond the match tables: 3 CTAs x 64 KB fit the 196 KB carve-out, 3 x 70 KB need the
+    // 228 KB one, and the 32 KB of L1 that costs made every batch 15 % slower (the streams of 12 warps x 32 lanes live
+    // in L1 between their 16-byte reads).  So the tile's order goes to a global scratch slice of this CTA (2 bytes per
+    // pair, read back through L1) and the class counters borrow the first 64 words of the tables, which are all-zero
+    // between pairs and are zeroed again before the first pair of the tile.
+    uint16_t *order = order_ws + (size_t)blockIdx.x * DUO_SLOTS;  // tile-local pair indices in class order
+    uint32_t *hist = tabs;                                        // [DUO_CLASSES] counts, then write cursors
+    volatile uint32_t *tile_ident = tabs + DUO_CLASSES;           // two more borrowed words: identity flag, slots in use
+    uint8_t *tab = (uint8_t *)(tabs + threadIdx.x);
+    const uint32_t pitch = nt * 4u;
+    bool tables_clean = false;
+    // Work split: the batch is cut into rounds of 256 pairs (128 threads x 2); CTA b takes a contiguous range of rounds,
+    // every CTA within one round of the others (an equal share rounded UP to whole rounds left 3 of 148 SMs idle), and cuts
+    // its range into tiles of <= DUO_TILE pairs.
+    const size_t rounds_total = (n + 255) / 256;
+    const size_t rq = rounds_total / gridDim.x, rrem = rounds_total % gridDim.x;
+    const size_t r_lo = (size_t)blockIdx.x * rq + (blockIdx.x < rrem ? blockIdx.x : rrem);
+    const size_t r_cnt = rq + (blockIdx.x < rrem ? 1 : 0);
+    const size_t n_tiles = (r_cnt + DUO_TILE / 256 - 1) / (DUO_TILE / 256);
+    auto len_class_of = [&](size_t w) -> uint32_t {
+        const size_t pair = idx ? (size_t)idx[w] : w;
+        const uint64_t la = a_off[pair + 1] - a_off[pair], lb = b_off[pair + 1] - b_off[pair];
+        const uint64_t c = (la > lb ? la : lb) >> 4;
+        return c < (uint64_t)(DUO_CLASSES - 1) ? (uint32_t)c : (uint32_t)(DUO_CLASSES - 1);
+    };
+    for (size_t tile = 0; tile < n_tiles; tile++) {
+        const size_t t_lo = r_lo + r_cnt * tile / n_tiles, t_hi = r_lo + r_cnt * (tile + 1) / n_tiles;  // rounds
+        const size_t base = t_lo * 256;
+        const size_t end = t_hi * 256 < n ? t_hi * 256 : n;
+        const uint32_t cnt = (uint32_t)(end - base);
+        // ---- order the tile by length class ----------------------------------------------------------------------
+        // classes of pairs tid + 128 j (j < 24) as bytes of pk[] (0xFF = none); the offsets are fetched 12 pairs at a time
+        // so that a thread waits for two round trips per tile, not for one per pair (that was 18 us per pass), and the
+        // first fetch of the kernel is in flight while the match tables are zeroed.  (Measured against this: thread t
+        // taking 18 CONSECUTIVE pairs -- 50 loads of neighbouring low words, classes from register differences, ~150
+        // instructions instead of ~900 -- was 7 % slower on every workload; the whole kernel is sensitive to where its
+        // unrolled body lands in the instruction cache.)
+        uint32_t pk[DUO_TILE / 128 / 4];
+#pragma unroll
+        for (int q = 0; q < DUO_TILE / 128 / 4; q++) pk[q] = 0xFFFFFFFFu;
+#pragma unroll
+        for (int g = 0; g < 2; g++) {
+            uint32_t c[12];
+#pragma unroll
+            for (int u = 0; u < 12; u++) {
+                const uint32_t i = threadIdx.x + 128u * (uint32_t)(g * 12 + u);
+                c[u] = i < cnt ? len_class_of(base + i) : 0xFFu;
+            }
+            if (g == 0) {
+                if (!tables_clean) {
+                    for (uint32_t q = threadIdx.x; q < 128u * nt; q += nt) tabs[q] = 0;
+                    tables_clean = true;
+                }
+                __syncthreads();  // tables (and with them the borrowed counters) are zero
+            }
+#pragma unroll
+            for (int u = 0; u < 12; u++) {
+                const int j = g * 12 + u;
+                // equal-length batches: the 32 lanes of a warp count into the same word -- one atomic for the warp
+                const uint32_t c_first = __shfl_sync(0xffffffffu, c[u], 0);
+                if (__all_sync(0xffffffffu, c[u] == c_first)) {
+                    if ((threadIdx.x & 31u) == 0 && c_first != 0xFFu) atomicAdd(&hist[c_first], 32u);
+                } else if (c[u] != 0xFFu) {
+                    atomicAdd(&hist[c[u]], 1u);
+                }
+                pk[j >> 2] = (pk[j >> 2] & ~(0xFFu << (8 * (j & 3)))) | (c[u] << (8 * (j & 3)));
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {  // one warp: is the tile one class?  else exclusive scan of the 64 counts -> cursors
+            const uint32_t c0 = hist[threadIdx.x], c1 = hist[threadIdx.x + 32];
+            const bool one = __any_sync(0xffffffffu, c0 == cnt || c1 == cnt);
+            // every class starts at an EVEN position (a thread takes positions 2s and 2s + 1, so its two pairs are always
+            // of one class); a class with an odd count leaves its last slot empty (0xFFFF) and that thread lends its one
+            // pair to the idle half.  A thread straddling two classes sent its whole warp down the single-pair path,
+            // and that code evicted the paired path from the instruction cache of its SM.
+            const uint32_t e0 = (c0 + 1u) & ~1u, e1 = (c1 + 1u) & ~1u;
+            uint32_t s0 = e0, s1 = e1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t0 = __shfl_up_sync(0xffffffffu, s0, o), t1 = __shfl_up_sync(0xffffffffu, s1, o);
+                if ((int)threadIdx.x >= o) s0 += t0, s1 += t1;
+            }
+            const uint32_t tot0 = __shfl_sync(0xffffffffu, s0, 31), tot1 = __shfl_sync(0xffffffffu, s1, 31);
+            const uint32_t b0 = s0 - e0, b1 = tot0 + s1 - e1;  // first slot of classes t and t + 32
+            hist[threadIdx.x] = b0;
+            hist[threadIdx.x + 32] = b1;
+            if (!one) {
+                if (c0 & 1u) order[b0 + c0] = 0xFFFFu;
+                if (c1 & 1u) order[b1 + c1] = 0xFFFFu;
+            }
+            if (threadIdx.x == 0) {
+                *tile_ident = one ? 1u : 0u;
+                tile_ident[1] = one ? cnt : tot0 + tot1;  // slots in use
+            }
+        }
+        __syncthreads();
+        const bool ident = *tile_ident != 0u;
+        const uint32_t plen = tile_ident[1];
+        if (!ident) {
+#pragma unroll
+            for (int j = 0; j < DUO_TILE / 128; j++) {
+                const uint32_t cj = (pk[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+                if (cj != 0xFFu) order[atomicAdd(&hist[cj], 1u)] = (uint16_t)(threadIdx.x + 128u * (uint32_t)j);
+            }
+            __threadfence_block();  // the slots are read by other threads of the CTA
+            __syncthreads();
+        }
+        __syncthreads();                                           // everyone has read tile_ident
+        if (threadIdx.x <= DUO_CLASSES + 1) hist[threadIdx.x] = 0;  // hand the borrowed words back to the tables
+        __syncthreads();
+        // ---- the rounds of the tile ------------------------------------------------------------------------------
+        // sorted position -> pair (valid = false: an empty slot or past the end)
+        auto ref_at = [&](uint32_t pos, bool &valid) -> PairRef {
+            uint32_t local = pos;
+            valid = pos < plen;
+            if (valid && !ident) {
+                local = (uint32_t)((volatile uint16_t *)order)[pos];
+                valid = local != 0xFFFFu;
+            }
+            return load_pair_ref(a_off, b_off, idx, valid ? base + local : n, n);
+        };
+        uint32_t slot = threadIdx.x;
+        bool has0, has1, nh0, nh1;
+        PairRef cur0 = ref_at(2 * slot, has0), cur1 = ref_at(2 * slot + 1, has1);
+        for (; 2 * (slot - threadIdx.x) < plen; slot += nt) {
+            const PairRef nx0 = ref_at(2 * (slot + nt), nh0), nx1 = ref_at(2 * (slot + nt) + 1, nh1);  // in flight during this item
+            const uint8_t *pa0 = a + cur0.a0, *pb0 = b + cur0.b0, *pa1 = a + cur1.a0, *pb1 = b + cur1.b0;
+            uint64_t la0 = cur0.alen, lb0 = cur0.blen, la1 = cur1.alen, lb1 = cur1.blen;
+            uint32_t mk0 = 0, mk1 = 0, r0 = 0, r1 = 0;
+            const bool dp0 = has0 && bitpar::unit_costs_prepare(pa0, la0, pb0, lb0, k, mk0, &r0);
+            const bool dp1 = has1 && bitpar::unit_costs_prepare(pa1, la1, pb1, lb1, k, mk1, &r1);
+            // A lane with only ONE pair to compute (odd class count at a class boundary, the last pair of the batch, a
+            // partner whose answer needs no DP) lends it to the other half and discards that result: the warp stays on
+            // the paired path instead of taking the single-pair path for all its lanes.
+            if (dp0 && !dp1) pa1 = pa0, pb1 = pb0, la1 = la0, lb1 = lb0, mk1 = mk0;
+            if (dp1 && !dp0) pa0 = pa1, pb0 = pb1, la0 = la1, lb0 = lb1, mk0 = mk1;
+            // the choice is made per WARP, as in the kernel above
+            const bool can_pair = (dp0 || dp1) && (lb0 >> 4) == (lb1 >> 4);
+            const bool skip = !dp0 && !dp1;
+            if (__all_sync(__activemask(), can_pair || skip) && can_pair) {
+                bitpar::NextHint hint;
+                hint.p[0] = nx0.alen ? a + nx0.a0 : nullptr;
+                hint.p[1] = nx0.blen ? b + nx0.b0 : nullptr;
+                hint.p[2] = nx1.alen ? a + nx1.a0 : nullptr;
+                hint.p[3] = nx1.blen ? b + nx1.b0 : nullptr;
+                hint.len[0] = nx0.alen, hint.len[1] = nx0.blen, hint.len[2] = nx1.alen, hint.len[3] = nx1.blen;
+                uint32_t t0 = 0, t1 = 0;
+                bitpar::distance_duo(pa0, (int)la0, pb0, (int)lb0, mk0, pa1, (int)la1, pb1, (int)lb1, mk1, tab, pitch, t0, t1,
+                                     &hint);
+                if (dp0) r0 = t0 <= mk0 ? t0 : 0xFFFFFFFFu;
+                if (dp1) r1 = t1 <= mk1 ? t1 : 0xFFFFFFFFu;
+            } else {
+#pragma unroll 1
+                for (int q = 0; q < 2; q++) {
+                    if (q == 0 ? dp0 : dp1) {
+                        const uint32_t mk = q == 0 ? mk0 : mk1;
+                        uint32_t rr = bitpar::distance_blk<false, 1, 16>(q == 0 ? pa0 : pa1, (int)(q == 0 ? la0 : la1),
+                                                                         q == 0 ? pb0 : pb1, (int)(q == 0 ? lb0 : lb1), mk, tab, pitch);
+                        rr = rr <= mk ? rr : 0xFFFFFFFFu;
+                        if (q == 0)
+                            r0 = rr;
+                        else
+                            r1 = rr;
+                    }
+                }
+            }
+            if (has0) out[cur0.pair] = r0;
+            if (has1) out[cur1.pair] = r1;
+            cur0 = nx0, cur1 = nx1;
+            has0 = nh0, has1 = nh1;
+        }
+        __syncthreads();  // `order` and the borrowed words are rewritten for the next tile
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Length bucketing (experimental, TA_LEN_BUCKETS=1): a counting sort of the pair indices by (longer length) / 16, so
 // that neighbouring work items have the same number of 16-column supersteps -- pairs can then share a thread in the
@@ -303,6 +502,21 @@ int ta_launch_lev_bitpar(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, c
         static const int blk_duo = getenv("TA_BLK_DUO") ? atoi(getenv("TA_BLK_DUO")) : 1;
         if (use_blk && blk_duo && !costs.transpose && wmax <= 9 && blk_planes == 1 && blk_c == 0) {
             const int nt = 128;
+            // tile-local ordering by length class when the batch is ragged (decided per batch by the entry points, see
+            // ta_set_length_hint; TA_DUO_TILED=0|1 forces one kernel)
+            static const int env_tiled = getenv("TA_DUO_TILED") ? atoi(getenv("TA_DUO_TILED")) : -1;
+            if (env_tiled >= 0 ? env_tiled != 0 : ctx->batch_ragged) {
+                const size_t smem = (size_t)128 * nt * 4;
+                const size_t rounds = (n + 255) / 256;  // the kernel splits them evenly over its CTAs
+                const unsigned blocks = (unsigned)std::min<size_t>(rounds, (size_t)ctx->sm_count * 3);
+                int rc = ta_dev_reserve(ctx, ctx->d_work[4], (size_t)blocks * DUO_SLOTS * sizeof(uint16_t));
+                if (rc != TA_OK) return rc;
+                TA_CUDA(ctx, cudaFuncSetAttribute(lev_bitpar_duo_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                lev_bitpar_duo_tiled_kernel<<<blocks, nt, smem, st>>>(a, a_off, b, b_off, idx, n, k, (uint16_t *)ctx->d_work[4].p, out);
+                ctx->launches++;
+                TA_CUDA(ctx, cudaGetLastError());
+                return TA_OK;
+            }
             const size_t smem = (size_t)128 * nt * 4;
             const size_t items = (n + 1) / 2;
             const unsigned blocks = (unsigned)std::min<size_t>((items + nt - 1) / nt, (size_t)ctx->sm_count * 3);

@@ -30,8 +30,10 @@ struct ta_ctx {
     cudaStream_t stream2 = nullptr;  // H2D of the next chunk
     static constexpr int MAX_CHUNKS = 8;
     cudaEvent_t ev_h2d[MAX_CHUNKS] = {};  // "chunk c is in device memory"
-    DevBuf d_a[2], d_b[2], d_aoff[2], d_boff[2], d_out[2], d_work[4];
+    DevBuf d_a[2], d_b[2], d_aoff[2], d_boff[2], d_out[2], d_work[5];
     DevBuf h_pin[4];         // pinned staging for pageable inputs / outputs
+    int len_hint = -1;          // ta_set_length_hint: -1 auto, 0 equal lengths, 1 ragged
+    bool batch_ragged = false;  // decided per batch by the entry points, read by the unit-cost dispatcher
     uint32_t *d_flags = nullptr;  // [0] = deferred error code of *_dev kernels, [1..] scratch counters
     uint32_t *h_flags = nullptr;  // pinned mirror
     uint64_t launches = 0;
