@@ -39,6 +39,8 @@ extern "C" {
     pub fn ta_device_count(ctx: *mut TaCtx) -> c_int;
     pub fn ta_multi_uses_nccl(ctx: *mut TaCtx) -> c_int;
     pub fn ta_trim();
+    /// 1 = the pairs' lengths vary (tile-ordered kernel), 0 = equal lengths, -1 = default; never changes results
+    pub fn ta_set_length_hint(ctx: *mut TaCtx, ragged: c_int) -> c_int;
     pub fn ta_shutdown(ctx: *mut TaCtx);
     pub fn ta_strerror(code: c_int) -> *const c_char;
     pub fn ta_last_error(ctx: *mut TaCtx) -> *const c_char;
