@@ -58,6 +58,12 @@ def test_multi_ctx_ragged_and_tiny(meng):
     a, ao, b, bo = synth.ragged_mutated_pairs(5003, 0, 300, 6, seed=24, templates=5003)
     got = meng.levenshtein_k_batch(a, ao, b, bo, 6)
     assert np.array_equal(got, orc.levenshtein_k_batch(a, ao, b, bo, 6, threads=8))
+    try:  # the length hint reaches every device of the context and never changes a result
+        for hint in (True, False):
+            meng.set_length_hint(hint)
+            assert np.array_equal(meng.levenshtein_k_batch(a, ao, b, bo, 6), got)
+    finally:
+        meng.set_length_hint(None)
     for n in (1, 2, 3):
         sa, sao, sb, sbo = synth.mutated_pairs(n, 40, 3, seed=n)
         assert np.array_equal(meng.levenshtein_k_batch(sa, sao, sb, sbo, 5), orc.levenshtein_k_batch(sa, sao, sb, sbo, 5))
