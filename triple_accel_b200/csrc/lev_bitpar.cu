@@ -1401,9 +1401,8 @@ int ta_launch_search_filter(ta_ctx *ctx, const uint8_t *needle_dev, uint32_t nee
         uint32_t *sub_flags = (uint32_t *)ctx->d_work[2].p;
         uint32_t *chunk_ctr = (uint32_t *)((uint8_t *)ctx->d_work[2].p + flag_bytes);
         QCand *queue = (QCand *)((uint8_t *)ctx->d_work[2].p + flag_bytes + ctr_bytes);
-        uint32_t *qcount = ctx->d_flags + 16, *gave_up = ctx->d_flags + 17;
+        uint32_t *qcount = ctx->d_flags + 6, *gave_up = ctx->d_flags + 7;  // zeroed by search_device with its own counters
         TA_CUDA(ctx, cudaMemsetAsync(sub_flags, 0, flag_bytes + ctr_bytes, st));
-        TA_CUDA(ctx, cudaMemsetAsync(qcount, 0, 2 * sizeof(uint32_t), st));  // queue length, gave-up flag
         // one wave of resident CTAs, chunks handed out dynamically.  Four loads per thread and round, 4 CTAs/SM (64
         // registers): measured against 2 loads x 5 CTAs, 8 x 3 and 4 x 5 (spills) -- 0.302 / 0.308 / 0.315 / 0.346 ms
         // for the whole search step; TA_QGRAM_CTAS changes the grid (2 and 3 CTAs/SM: 0.316 / 0.310 ms)

@@ -470,7 +470,8 @@ static int search_device(ta_ctx *ctx, cudaStream_t st, const uint8_t *d_needle, 
     static const bool no_filter = getenv("TA_NO_SEARCH_FILTER") != nullptr;  // testing: exact kernel on everything
     uint32_t *counter = ctx->d_flags + 2;
     unsigned long long *d_count = (unsigned long long *)(ctx->d_flags + 4);
-    TA_CUDA(ctx, cudaMemsetAsync(counter, 0, 4 * sizeof(uint32_t), st));  // item counter, pad, 64-bit hit counter
+    // item counter, pad, 64-bit hit counter, and the q-gram filter's queue length and gave-up flag (d_flags + 6, + 7)
+    TA_CUDA(ctx, cudaMemsetAsync(counter, 0, 6 * sizeof(uint32_t), st));
     // The pre-filters work with unit costs.  For any other cost model they run with the number of edit OPERATIONS a
     // match can contain: an alignment of weighted cost <= k has at most ku = k / min(mismatch, gap, transpose) operations,
     // so its end position also ends a unit-cost alignment of cost <= ku -- the flagged sub-segments are a superset of
