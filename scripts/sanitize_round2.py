@@ -29,6 +29,15 @@ a, ao, b, bo = synth.edited_pairs(17000, 0, 90, 8, seed=5, allow_swap=True, alph
 for costs, k in (((2, 1, 3, 0), 16), ((2, 2, 1, 3), 9), ((1, 1, 0, 1), 6), ((5, 4, 3, 0), 30)):
     got = eng.levenshtein_k_batch(a, ao, b, bo, k, costs)
     assert np.array_equal(got, orc.levenshtein_k_batch(a, ao, b, bo, k, costs, threads=4)), ("diag16", costs, k)
+# two pairs per thread behind the tile-local length ordering: ragged lengths incl. empty strings, sizes around a tile,
+# an equal-length batch (one-class tiles keep their order); the host-buffer call decides from the offsets, the hint forces
+for n_pairs, lo, hi in ((5000, 0, 220), (3073, 96, 160), (2500, 128, 128)):
+    a, ao, b, bo = synth.edited_pairs(n_pairs, lo, hi, 8, seed=n_pairs, allow_swap=False)
+    want = orc.levenshtein_k_batch(a, ao, b, bo, 8, threads=4)
+    for hint in (None, True):
+        eng.set_length_hint(hint)
+        assert np.array_equal(eng.levenshtein_k_batch(a, ao, b, bo, 8), want), ("duo tiled", n_pairs, hint)
+eng.set_length_hint(None)
 # search: weighted costs through the pre-filter, long needle on the global-rows kernel
 needle, hay, hoff = synth.needle_haystacks(200, 3000, 32, plant_frac=0.2, max_edits=3, seed=9)
 for costs in ((2, 1, 3, 0), (2, 2, 1, 3)):
