@@ -436,7 +436,7 @@ class Runner:
 
         def step_dev():
             if bop == "hamming":
-                eng.hamming_batch_dev(d_a, d_ao, d_b, d_bo, d_out)
+                eng.hamming_batch_dev(d_a, d_ao, d_b, d_bo, d_out, mean_len=length)
             elif bop == "exp":
                 eng.levenshtein_exp_batch_dev(d_a, d_ao, d_b, d_bo, costs, max_len, d_out)
             elif bop == "search":

@@ -198,6 +198,10 @@ int ta_hamming_search_naive_batch(ta_ctx *ctx, const uint8_t *needle, size_t nee
  * buffer does too as long as it does not end in the buffer's last 15 bytes. */
 int ta_hamming_batch_dev(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b,
                          const uint64_t *b_off, size_t n, uint32_t *out, void *stream);
+/* The same with the mean string length from the caller (lanes per pair follow it: 1 lane per 16 bytes, up to a warp;
+ * ta_hamming_batch_dev cannot read the device offsets and assumes 64 bytes).  Any value gives the same results. */
+int ta_hamming_batch_dev_len(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b,
+                             const uint64_t *b_off, size_t n, uint32_t mean_len, uint32_t *out, void *stream);
 int ta_levenshtein_k_batch_dev(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b,
                                const uint64_t *b_off, size_t n, uint32_t k, ta_costs costs, uint32_t max_len,
                                uint32_t *out, void *stream);

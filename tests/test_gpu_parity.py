@@ -479,6 +479,11 @@ def test_device_resident_entry_points(eng):
     eng.hamming_batch_dev(t[0], t[1], t[2], t[3], out2)
     eng.dev_status()
     assert np.array_equal(out2.cpu().numpy().view(np.uint32), orc.hamming_batch(a2, ao2, b2, bo2))
+    for mean_len in (1, 16, 64, 300, 5000):  # ta_hamming_batch_dev_len: lanes per pair follow the caller's mean length
+        out2.fill_(9)
+        eng.hamming_batch_dev(t[0], t[1], t[2], t[3], out2, mean_len=mean_len)
+        eng.dev_status()
+        assert np.array_equal(out2.cpu().numpy().view(np.uint32), orc.hamming_batch(a2, ao2, b2, bo2)), mean_len
     # a length mismatch on the device path is reported by ta_dev_status
     eng.hamming_batch_dev(t[0], t[1], tb, tbo, out2)
     with pytest.raises(AssertionError):

@@ -71,6 +71,7 @@ SIGNATURES = {
     "ta_hamming_search_naive_batch": (_int, [_vp, _vp, _sz, _vp, _vp, _sz, _u32, _int,
                                              C.POINTER(C.POINTER(ta_match)), C.POINTER(C.POINTER(C.c_uint64))]),
     "ta_hamming_batch_dev": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "ta_hamming_batch_dev_len": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, C.c_uint32, _vp, _vp]),
     "ta_levenshtein_k_batch_dev": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, _u32, ta_costs, _u32, _vp, _vp]),
     "ta_levenshtein_exp_batch_dev": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, ta_costs, _u32, _vp, _vp]),
     "ta_levenshtein_search_batch_dev": (_int, [_vp, _vp, _sz, _vp, _vp, _sz, C.c_uint64, _u32, _int, ta_costs, _int,

@@ -302,8 +302,13 @@ class Engine:
         import torch
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def hamming_batch_dev(self, a, a_off, b, b_off, out, stream=None):
+    def hamming_batch_dev(self, a, a_off, b, b_off, out, stream=None, mean_len=None):
         n = a_off.numel() - 1
+        if mean_len:  # lanes per pair follow the mean length (the library cannot read device offsets)
+            self._check(self._lib.ta_hamming_batch_dev_len(self._h, a.data_ptr(), a_off.data_ptr(), b.data_ptr(),
+                                                           b_off.data_ptr(), n, int(mean_len), out.data_ptr(),
+                                                           self._stream(stream)))
+            return out
         self._check(self._lib.ta_hamming_batch_dev(self._h, a.data_ptr(), a_off.data_ptr(), b.data_ptr(),
                                                    b_off.data_ptr(), n, out.data_ptr(), self._stream(stream)))
         return out

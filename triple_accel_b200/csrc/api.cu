@@ -696,7 +696,18 @@ int ta_hamming_batch_dev(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, c
     std::lock_guard<std::mutex> lock(ctx->mu);
     TA_CUDA(ctx, cudaSetDevice(ctx->device));
     // mean length is unknown without reading device offsets; 64-byte strings and up use >= 4 lanes per pair
+    // (ta_hamming_batch_dev_len takes it from the caller)
     return ta_launch_hamming(ctx, a, a_off, b, b_off, n, 64, out, ctx->d_flags, (cudaStream_t)stream);
+}
+
+int ta_hamming_batch_dev_len(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b,
+                             const uint64_t *b_off, size_t n, uint32_t mean_len, uint32_t *out, void *stream) {
+    if (!ctx || ctx->multi) return TA_ERR_BAD_ARG;
+    if (n == 0) return TA_OK;
+    if (!a_off || !b_off || !out) return TA_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    TA_CUDA(ctx, cudaSetDevice(ctx->device));
+    return ta_launch_hamming(ctx, a, a_off, b, b_off, n, mean_len ? mean_len : 64, out, ctx->d_flags, (cudaStream_t)stream);
 }
 
 int ta_levenshtein_k_batch_dev(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, const uint8_t *b,
