@@ -64,7 +64,7 @@ WORKLOADS = {
     "search_n64_h4096": ("search", 100_000, 4096, 6, (1, 1, 0, 0), "strong",
                          "levenshtein_search needle len=64 (seven pieces of 9), 100k haystacks len=4096, k=6, Best, 1% planted hits"),
     "search_affine_n32_h4096": ("search", 20_000, 4096, 6, (2, 1, 3, 0), "strong",
-                                "levenshtein_search EditCosts(2,1,3,None): no pre-filter, exact (cost, length) kernel over whole "
+                                "levenshtein_search EditCosts(2,1,3,None): unit-cost pre-filter with the operation-count bound, exact (cost, length) kernel on the flagged "
                                 "haystacks; needle len=32, 20k haystacks len=4096, k=6, Best"),
     "hamming_len64": ("hamming", 10_000, 64, 0, (1, 1, 0, 0), "weak", "hamming, 10k pairs len=64 (plumbing case)"),
     "hamming_len4096": ("hamming", 262_144, 4096, 0, (1, 1, 0, 0), "weak", "hamming, 256Ki pairs len=4096"),
@@ -76,7 +76,8 @@ SEARCH_OPTS = {  # needle length, SearchType (0 All, 1 Best) of the search workl
 HEADLINE = "lev_k8_len128"
 # the other BASELINE configs and north-star lines, reported in the `configs` array of the default line
 CONFIG_ARRAY = ["lev_k16_len128", "lev_k16_len4096", "hamming_len64", "exp_len1024", "search_n32_h4096",
-                "rdamerau_k16_len512", "lev_k8_len128_R", "lev_k8_ragged96_160", "affine_k16_len128"]
+                "rdamerau_k16_len512", "lev_k8_len128_R", "lev_k8_ragged96_160", "affine_k16_len128",
+                "search_all_n32_h4096", "search_n64_h4096", "search_affine_n32_h4096"]
 REF_THREADS = 16  # the reference arm and cpu_baseline use min(16, host threads): comparable between boxes
 
 
@@ -163,14 +164,17 @@ def dominant_kernel(op, k, costs, length, n_units=None, ragged=False):
         return "hamming_kernel"
     unit = tuple(costs[:3]) == (1, 1, 0) and costs[3] <= 1
     if op == "search":
-        if not unit:
-            return "search_exact_kernel (thread per haystack, no pre-filter)"
         nlen = SEARCH_NEEDLE[0]
+        # weighted costs run the unit-cost pre-filters with the number of edit operations a match can hold (search.cu)
+        ku = k if unit else k // min(c for c in (costs[0], costs[1], costs[3]) if c)
+        if ku >= nlen or nlen > 64:
+            return "search_exact_kernel / search_wave_kernel on whole haystacks (no pre-filter)"
+        k = ku
         pieces = (2 * k + 1) if costs[3] else (k + 1)
         forced = os.environ.get("TA_SEARCH_FILTER", "")
         big = n_units is None or n_units * length >= ((64 << 20) if nlen <= 32 else (8 << 20))  # lev_bitpar.cu dispatch
         if nlen <= 64 and pieces <= nlen and nlen // pieces >= 7 and (forced == "qgram" or (forced == "" and big)):
-            return "search_qgram_kernel (+ search_qgram_resolve_kernel, search_wave_kernel on the flagged 128-byte sub-segments)"
+            return "search_qgram_kernel (+ search_qgram_resolve_kernel, search_wave_kernel on the flagged 16-byte granules)"
         if nlen <= 32 and pieces <= nlen and nlen // pieces >= 4 and forced != "myers":
             return "search_pigeon_staged_kernel (+ search_wave_kernel on the flagged 128-byte sub-segments)"
         return "search_filter_kernel (+ search_wave_kernel on the flagged 128-byte sub-segments)"
