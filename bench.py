@@ -46,6 +46,8 @@ WORKLOADS = {
     "lev_k8_ragged96_160": ("lev_k_ragged", 1_000_000, 128, 8, (1, 1, 0, 0), "weak",
                             "levenshtein_simd_k k=8, 1M pairs, |a| ~ U[96,160] (mean 128), unit costs, set M: neighbouring "
                             "pairs have unrelated lengths (arbitrary alignment, ragged tails)"),
+    "lev_k16_ragged96_160": ("lev_k_ragged", 1_000_000, 128, 16, (1, 1, 0, 0), "weak",
+                             "levenshtein_simd_k k=16, 1M pairs, |a| ~ U[96,160], unit costs, set M (one pair per thread)"),
     "rdamerau_k16_len512": ("lev_k", 1_000_000, 512, 16, (1, 1, 0, 1), "strong",
                             "RDAMERAU_COSTS k=16, 1M pairs len=512, set M (U[0,16] edits incl. swaps), one batch over all GPUs"),
     "lev_k16_len4096": ("lev_k", 262_144, 4096, 16, (1, 1, 0, 0), "weak",
@@ -76,7 +78,7 @@ SEARCH_OPTS = {  # needle length, SearchType (0 All, 1 Best) of the search workl
 HEADLINE = "lev_k8_len128"
 # the other BASELINE configs and north-star lines, reported in the `configs` array of the default line
 CONFIG_ARRAY = ["lev_k16_len128", "lev_k16_len4096", "hamming_len64", "exp_len1024", "search_n32_h4096",
-                "rdamerau_k16_len512", "lev_k8_len128_R", "lev_k8_ragged96_160", "affine_k16_len128",
+                "rdamerau_k16_len512", "lev_k8_len128_R", "lev_k8_ragged96_160", "lev_k16_ragged96_160", "affine_k16_len128",
                 "search_all_n32_h4096", "search_n64_h4096", "search_affine_n32_h4096"]
 REF_THREADS = 16  # the reference arm and cpu_baseline use min(16, host threads): comparable between boxes
 
@@ -191,7 +193,8 @@ def dominant_kernel(op, k, costs, length, n_units=None, ragged=False):
         tiled = {"0": False, "1": True}.get(os.environ.get("TA_DUO_TILED", ""), ragged)
         return "lev_bitpar_duo_tiled_kernel" if tiled else "lev_bitpar_duo_kernel"
     if band <= 25:
-        return "lev_bitpar_blk_kernel<C=%d>" % (16 if band <= 17 else 8)
+        tiled = {"0": False, "1": True}.get(os.environ.get("TA_BLK_TILED", ""), ragged)
+        return "lev_bitpar_blk%s_kernel<C=%d>" % ("_tiled" if tiled else "", 16 if band <= 17 else 8)
     return "lev_bitpar_tab_kernel<%s>" % ("u32" if band <= 32 else "u64")
 
 

@@ -740,10 +740,10 @@ def test_lev_duo_ragged_tiles(eng, n):
     from triple_accel_b200 import synth
     for lo, hi, seed in ((0, 200, 1), (128, 128, 2), (96, 160, 3), (1, 17, 4)):
         a, ao, b, bo = synth.edited_pairs(n, lo, hi, 8, seed=seed + n, allow_swap=False)
-        for k in (8, 3):
-            got = eng.levenshtein_k_batch(a, ao, b, bo, k)
-            want = orc.levenshtein_k_batch(a, ao, b, bo, k, threads=8)
-            assert np.array_equal(got, want), (n, lo, hi, k)
+        for k, costs in ((8, (1, 1, 0, 0)), (3, (1, 1, 0, 0)), (16, (1, 1, 0, 0)), (8, (1, 1, 0, 1)), (22, (1, 1, 0, 1))):
+            got = eng.levenshtein_k_batch(a, ao, b, bo, k, costs)  # k > 8 / transpositions: the one-pair-per-thread kernels
+            want = orc.levenshtein_k_batch(a, ao, b, bo, k, costs, threads=8)
+            assert np.array_equal(got, want), (n, lo, hi, k, costs)
 
 
 def test_length_hint_changes_the_kernel_not_the_result(eng):
@@ -860,6 +860,8 @@ SEARCH_TESTS = ("test_search_random or test_search_planted or test_kat_search or
     ({"TA_BLK_DUO": "0", "TA_EXP_FIRST_K": "30"}, LEV_TESTS),
     ({"TA_DUO_TILED": "0"}, LEV_TESTS + " or test_full_size"),
     ({"TA_DUO_TILED": "1"}, LEV_TESTS + " or test_full_size"),
+    ({"TA_BLK_TILED": "1"}, LEV_TESTS + " or test_full_size"),
+    ({"TA_BLK_TILED": "0", "TA_DUO_TILED": "0"}, LEV_TESTS),
     ({"TA_LEN_BUCKETS": "1"}, LEV_TESTS + " or test_full_size"),
     ({"TA_BLK_PLANES": "0"}, LEV_TESTS),
     ({"TA_BLK_PLANES": "1", "TA_BLK_C": "8"}, LEV_TESTS),
@@ -876,7 +878,7 @@ SEARCH_TESTS = ("test_search_random or test_search_planted or test_kat_search or
     ({"TA_SEARCH_FILTER": "qgram", "TA_QGRAM_QCAP": "1"}, SEARCH_TESTS),
 ], ids=["general-band-kernel", "diagonal-extension-kernel-forced", "u16-thread-per-pair-kernel-forced", "u16-thread-per-pair-kernel-on-unit-costs",
         "u16-thread-per-pair-kernel-single-stage", "u16-thread-per-pair-kernel-off", "diagonal-extension-kernel-off", "bitpar-simd-kernel", "bitpar-sliding-table-kernel",
-        "bitpar-sliding-table-32bit-on-narrow-bands", "bitpar-block-table-one-pair-per-thread", "bitpar-duo-kernel-without-tile-ordering", "bitpar-duo-kernel-tile-ordered-always", "length-bucketing-pre-pass", "bitpar-block-table-256-entries",
+        "bitpar-sliding-table-32bit-on-narrow-bands", "bitpar-block-table-one-pair-per-thread", "bitpar-duo-kernel-without-tile-ordering", "bitpar-duo-kernel-tile-ordered-always", "bitpar-block-table-tile-ordered-always", "bitpar-no-tile-ordering", "length-bucketing-pre-pass", "bitpar-block-table-256-entries",
         "bitpar-block-table-8-blocks", "bitpar-block-table-256-entries-8-blocks",
         "bitpar-table-2plane-kernel", "search-thread-kernel-nofilter", "search-wave-kernel-nofilter",
         "search-thread-kernel-filter", "search-global-rows-kernel-nofilter", "search-myers-filter-forced", "search-pigeonhole-filter-forced",

@@ -390,6 +390,124 @@ __global__ void __launch_bounds__(128, 3) lev_bitpar_duo_tiled_kernel(const uint
     }
 }
 
+// The block-table kernel (one pair per thread) behind the same tile-local ordering, for ragged batches (bands of 10 ..
+// 25 diagonals, transpositions): a warp runs as long as its longest pair, and in class order its 32 pairs are neighbours
+// in length.  Same bookkeeping as lev_bitpar_duo_tiled_kernel: contiguous rounds (of 128 pairs here) per CTA, tiles of
+// <= DUO_TILE pairs, class counters borrowed from the clean match tables, the order in a global scratch slice.
+template <bool TRANS, int C>
+__global__ void __launch_bounds__(128) lev_bitpar_blk_tiled_kernel(const uint8_t *__restrict__ a,
+                                                                   const uint64_t *__restrict__ a_off,
+                                                                   const uint8_t *__restrict__ b,
+                                                                   const uint64_t *__restrict__ b_off,
+                                                                   const uint32_t *__restrict__ idx, size_t n, uint32_t k,
+                                                                   uint16_t *__restrict__ order_ws,
+                                                                   uint32_t *__restrict__ out) {
+    extern __shared__ __align__(16) uint8_t tabs_raw[];
+    uint32_t *tabs = (uint32_t *)tabs_raw;
+    const uint32_t nt = blockDim.x;  // 128
+    uint16_t *order = order_ws + (size_t)blockIdx.x * DUO_SLOTS;
+    uint32_t *hist = tabs;
+    volatile uint32_t *tile_ident = tabs + DUO_CLASSES;
+    uint8_t *tab = (uint8_t *)(tabs + threadIdx.x);
+    const uint32_t pitch = nt * 4u;
+    bool tables_clean = false;
+    const size_t rounds_total = (n + 127) / 128;
+    const size_t rq = rounds_total / gridDim.x, rrem = rounds_total % gridDim.x;
+    const size_t r_lo = (size_t)blockIdx.x * rq + (blockIdx.x < rrem ? blockIdx.x : rrem);
+    const size_t r_cnt = rq + (blockIdx.x < rrem ? 1 : 0);
+    const size_t n_tiles = (r_cnt + DUO_TILE / 128 - 1) / (DUO_TILE / 128);
+    auto len_class_of = [&](size_t w) -> uint32_t {
+        const size_t pair = idx ? (size_t)idx[w] : w;
+        const uint64_t la = a_off[pair + 1] - a_off[pair], lb = b_off[pair + 1] - b_off[pair];
+        const uint64_t c = (la > lb ? la : lb) >> 4;
+        return c < (uint64_t)(DUO_CLASSES - 1) ? (uint32_t)c : (uint32_t)(DUO_CLASSES - 1);
+    };
+    for (size_t tile = 0; tile < n_tiles; tile++) {
+        const size_t t_lo = r_lo + r_cnt * tile / n_tiles, t_hi = r_lo + r_cnt * (tile + 1) / n_tiles;  // rounds
+        const size_t base = t_lo * 128;
+        const size_t end = t_hi * 128 < n ? t_hi * 128 : n;
+        const uint32_t cnt = (uint32_t)(end - base);
+        uint32_t pk[DUO_TILE / 128 / 4];
+#pragma unroll
+        for (int q = 0; q < DUO_TILE / 128 / 4; q++) pk[q] = 0xFFFFFFFFu;
+#pragma unroll
+        for (int g = 0; g < 2; g++) {
+            uint32_t c[12];
+#pragma unroll
+            for (int u = 0; u < 12; u++) {
+                const uint32_t i = threadIdx.x + 128u * (uint32_t)(g * 12 + u);
+                c[u] = i < cnt ? len_class_of(base + i) : 0xFFu;
+            }
+            if (g == 0) {
+                if (!tables_clean) {
+                    for (uint32_t q = threadIdx.x; q < 128u * nt; q += nt) tabs[q] = 0;
+                    tables_clean = true;
+                }
+                __syncthreads();
+            }
+#pragma unroll
+            for (int u = 0; u < 12; u++) {
+                const int j = g * 12 + u;
+                const uint32_t c_first = __shfl_sync(0xffffffffu, c[u], 0);
+                if (__all_sync(0xffffffffu, c[u] == c_first)) {
+                    if ((threadIdx.x & 31u) == 0 && c_first != 0xFFu) atomicAdd(&hist[c_first], 32u);
+                } else if (c[u] != 0xFFu) {
+                    atomicAdd(&hist[c[u]], 1u);
+                }
+                pk[j >> 2] = (pk[j >> 2] & ~(0xFFu << (8 * (j & 3)))) | (c[u] << (8 * (j & 3)));
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const uint32_t c0 = hist[threadIdx.x], c1 = hist[threadIdx.x + 32];
+            const bool one = __any_sync(0xffffffffu, c0 == cnt || c1 == cnt);
+            uint32_t s0 = c0, s1 = c1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t0 = __shfl_up_sync(0xffffffffu, s0, o), t1 = __shfl_up_sync(0xffffffffu, s1, o);
+                if ((int)threadIdx.x >= o) s0 += t0, s1 += t1;
+            }
+            const uint32_t tot0 = __shfl_sync(0xffffffffu, s0, 31);
+            hist[threadIdx.x] = s0 - c0;
+            hist[threadIdx.x + 32] = tot0 + s1 - c1;
+            if (threadIdx.x == 0) *tile_ident = one ? 1u : 0u;
+        }
+        __syncthreads();
+        const bool ident = *tile_ident != 0u;
+        if (!ident) {
+#pragma unroll
+            for (int j = 0; j < DUO_TILE / 128; j++) {
+                const uint32_t cj = (pk[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+                if (cj != 0xFFu) order[atomicAdd(&hist[cj], 1u)] = (uint16_t)(threadIdx.x + 128u * (uint32_t)j);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x <= DUO_CLASSES) hist[threadIdx.x] = 0;  // hand the borrowed words back to the tables
+        __syncthreads();
+        auto ref_at = [&](uint32_t pos) -> PairRef {  // sorted position -> pair (w = n: none)
+            if (pos >= cnt) return load_pair_ref(a_off, b_off, idx, n, n);
+            return load_pair_ref(a_off, b_off, idx, base + (ident ? pos : (uint32_t)((volatile uint16_t *)order)[pos]), n);
+        };
+        uint32_t slot = threadIdx.x;
+        PairRef cur = ref_at(slot), nxt = ref_at(slot + nt);
+        for (; slot - threadIdx.x < cnt; slot += nt) {
+            const PairRef nn = ref_at(slot + 2 * nt);  // in flight during this pair
+            prefetch_l2(a + nxt.a0, nxt.alen);
+            prefetch_l2(b + nxt.b0, nxt.blen);
+            bitpar::NextHint hint;
+            hint.p[0] = nxt.alen ? a + nxt.a0 : nullptr;
+            hint.p[1] = nxt.blen ? b + nxt.b0 : nullptr;
+            hint.p[2] = hint.p[3] = nullptr;
+            hint.len[0] = nxt.alen, hint.len[1] = nxt.blen, hint.len[2] = hint.len[3] = 0;
+            if (slot < cnt)
+                out[cur.pair] = bitpar::pair_unit_costs_blk<TRANS, 1, C>(a + cur.a0, cur.alen, b + cur.b0, cur.blen, k, tab, pitch, &hint);
+            cur = nxt;
+            nxt = nn;
+        }
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Length bucketing (experimental, TA_LEN_BUCKETS=1): a counting sort of the pair indices by (longer length) / 16, so
 // that neighbouring work items have the same number of 16-column supersteps -- pairs can then share a thread in the
@@ -528,6 +646,27 @@ int ta_launch_lev_bitpar(ta_ctx *ctx, const uint8_t *a, const uint64_t *a_off, c
         }
         if (use_blk) {
             const int C = (wmax <= 17 && blk_c != 8) ? 16 : 8;
+            static const int env_blk_tiled = getenv("TA_BLK_TILED") ? atoi(getenv("TA_BLK_TILED")) : -1;
+            if ((env_blk_tiled >= 0 ? env_blk_tiled != 0 : ctx->batch_ragged) && blk_planes == 1 && env_threads == 0) {
+                // ragged batch: tile-local ordering by length class (see lev_bitpar_blk_tiled_kernel; TA_BLK_TILED=0|1 forces)
+                const int tnt = 128;
+                const size_t tsmem = (size_t)128 * tnt * 4;
+                const size_t rounds = (n + 127) / 128;
+                const unsigned tblocks = (unsigned)std::min<size_t>(rounds, (size_t)ctx->sm_count * 3);
+                int rc = ta_dev_reserve(ctx, ctx->d_work[4], (size_t)tblocks * DUO_SLOTS * sizeof(uint16_t));
+                if (rc != TA_OK) return rc;
+                void (*tk)(const uint8_t *, const uint64_t *, const uint8_t *, const uint64_t *, const uint32_t *, size_t, uint32_t,
+                           uint16_t *, uint32_t *);
+                if (C == 16)
+                    tk = costs.transpose ? lev_bitpar_blk_tiled_kernel<true, 16> : lev_bitpar_blk_tiled_kernel<false, 16>;
+                else
+                    tk = costs.transpose ? lev_bitpar_blk_tiled_kernel<true, 8> : lev_bitpar_blk_tiled_kernel<false, 8>;
+                TA_CUDA(ctx, cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+                tk<<<tblocks, tnt, tsmem, st>>>(a, a_off, b, b_off, idx, n, k, (uint16_t *)ctx->d_work[4].p, out);
+                ctx->launches++;
+                TA_CUDA(ctx, cudaGetLastError());
+                return TA_OK;
+            }
             const int nt = env_threads ? env_threads : (blk_planes ? 128 : 224);
             const size_t smem = (size_t)(blk_planes ? 128 : 256) * nt * 4;
             const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (size_t)(ctx->smem_optin + 1024) / (smem + 1024)));
