@@ -34,9 +34,11 @@ for costs, k in (((2, 1, 3, 0), 16), ((2, 2, 1, 3), 9), ((1, 1, 0, 1), 6), ((5, 
 for n_pairs, lo, hi in ((5000, 0, 220), (3073, 96, 160), (2500, 128, 128)):
     a, ao, b, bo = synth.edited_pairs(n_pairs, lo, hi, 8, seed=n_pairs, allow_swap=False)
     want = orc.levenshtein_k_batch(a, ao, b, bo, 8, threads=4)
+    want16 = orc.levenshtein_k_batch(a, ao, b, bo, 16, (1, 1, 0, 1), threads=4)
     for hint in (None, True):
         eng.set_length_hint(hint)
         assert np.array_equal(eng.levenshtein_k_batch(a, ao, b, bo, 8), want), ("duo tiled", n_pairs, hint)
+        assert np.array_equal(eng.levenshtein_k_batch(a, ao, b, bo, 16, (1, 1, 0, 1)), want16), ("blk tiled", n_pairs, hint)
 eng.set_length_hint(None)
 # search: weighted costs through the pre-filter, long needle on the global-rows kernel
 needle, hay, hoff = synth.needle_haystacks(200, 3000, 32, plant_frac=0.2, max_edits=3, seed=9)
