@@ -588,15 +588,15 @@ def test_search_qgram_filter(eng):
                 assert np.array_equal(goff, woff) and np.array_equal(got, want), (nlen, k, costs, alpha, st)
 
 
-@pytest.mark.parametrize("nlen,k,alpha", [(32, 3, 256), (64, 6, 256), (32, 3, 4)])
-def test_search_qgram_big_batch(eng, nlen, k, alpha):
+@pytest.mark.parametrize("nlen,k,alpha,plant", [(32, 3, 256, 0.05), (64, 6, 256, 0.05), (32, 3, 4, 0.05), (32, 3, 256, 1.0)])
+def test_search_qgram_big_batch(eng, nlen, k, alpha, plant):
     """70 MB of haystacks: the default dispatch takes the q-gram scan (alphabet 4: its queue overflows and the fallback
-    kernel runs); the oracle checks a slice, the rest through the planted needles every haystack of the slice pattern
+    kernel runs; plant = 1.0: a match in EVERY haystack must still fit the queue); the oracle checks a slice, the rest through the planted needles every haystack of the slice pattern
     must report"""
     from triple_accel_b200 import synth
     n, hlen = 18000, 4096
     needle = np.random.default_rng(nlen).integers(1, 256, size=nlen, dtype=np.uint8)
-    hay, hoff = synth.planted_haystacks(n, hlen, needle, plant_frac=0.05, max_edits=k, seed=nlen + alpha)
+    hay, hoff = synth.planted_haystacks(n, hlen, needle, plant_frac=plant, max_edits=k, seed=nlen + alpha)
     if alpha != 256:  # the same map on both sides keeps the planted copies planted
         hay = (hay % alpha).astype(np.uint8)
         needle = (needle % alpha).astype(np.uint8)

@@ -1527,11 +1527,12 @@ int ta_launch_search_filter(ta_ctx *ctx, const uint8_t *needle_dev, uint32_t nee
         const uint32_t qgran = fine ? QG_GRAN : (uint32_t)TA_SEARCH_SUB;
         const uint64_t nbits = (uint64_t)n * qsubs;
         const size_t words = (size_t)((nbits + 31) / 32);
-        // queue: one entry per exact 4-gram match; a few per real occurrence on high-entropy input.  More than one per
-        // 1024 haystack words means common 4-grams (text, DNA): give up and let the shift-and kernel do it.
+        // queue: one entry per exact 4-gram match; ~7 per real occurrence of a 32-byte needle on high-entropy input, so
+        // 16 per 4 KB leave room for a match in every haystack.  More than that (one per 64 haystack words) means common
+        // 4-grams (DNA: ~80 per 4 KB): give up and let the shift-and kernel do it.
         static const long env_cap = getenv("TA_QGRAM_QCAP") ? atol(getenv("TA_QGRAM_QCAP")) : 0;  // testing: force the fallback
         const uint64_t total_bytes = (uint64_t)n * max_hay;  // upper bound of the flat range
-        const uint32_t qcap = env_cap > 0 ? (uint32_t)env_cap : (uint32_t)std::min<uint64_t>(total_bytes / 4096 + 4096, 1u << 24);
+        const uint32_t qcap = env_cap > 0 ? (uint32_t)env_cap : (uint32_t)std::min<uint64_t>(total_bytes / TA_QGRAM_BYTES_PER_ENTRY + 4096, 1u << 24);
         // workspace: [sub-segment flags | chunk counters, one 128-byte line each | queue]; one memset clears the first two
         const size_t flag_bytes = (words * sizeof(uint32_t) + 127) & ~(size_t)127;
         const size_t ctr_bytes = (size_t)QG_REGIONS * 128;

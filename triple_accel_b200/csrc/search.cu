@@ -482,15 +482,16 @@ static int search_device(ta_ctx *ctx, cudaStream_t st, const uint8_t *d_needle, 
     if (!no_filter && needle_len <= 64 && !anchored && ku < needle_len) {
         const uint64_t nseg = max_hay ? (max_hay + TA_SEARCH_SUB - 1) / TA_SEARCH_SUB : 1;
         if ((uint64_t)n * nseg <= 0xFFFFFFF0ull && nseg <= 65535) {
-            // list capacity: every TA_SEARCH_SUB granule of every haystack (the scanning filters' worst case), which also
-            // bounds what the q-gram resolve kernel can append (<= 8 distinct 16-byte granules per queue entry, queue
-            // capacity n * max_hay / 4096 + 4096: n * nseg / 4 + 32768 entries)
-            if ((rc = ta_dev_reserve(ctx, ctx->d_work[0], (n * nseg + 32768) * sizeof(uint32_t))) != TA_OK) return rc;
+            // list capacity: every TA_SEARCH_SUB granule of every haystack (the scanning filters' worst case), or what the
+            // q-gram resolve kernel can append (<= 8 distinct 16-byte granules per queue entry)
+            const uint64_t qgram_items = 8ull * std::min<uint64_t>((uint64_t)n * max_hay / TA_QGRAM_BYTES_PER_ENTRY + 4096, 1ull << 24);
+            const size_t list_cap = (size_t)std::max<uint64_t>((uint64_t)n * nseg, qgram_items);
+            if ((rc = ta_dev_reserve(ctx, ctx->d_work[0], list_cap * sizeof(uint32_t))) != TA_OK) return rc;
             rc = ta_launch_search_filter(ctx, d_needle, (uint32_t)needle_len, d_hay, d_off, n, max_hay, ku,
                                          costs.transpose != 0, (uint32_t *)ctx->d_work[0].p, counter, &fo, st);
             segs = fo.segs;
             if (rc == TA_OK) {
-                work_n = n * nseg + 32768;
+                work_n = list_cap;
                 d_work_n = counter;
                 d_idx = (const uint32_t *)ctx->d_work[0].p;
             } else if (rc == TA_ERR_TOO_LARGE) {

@@ -62,6 +62,10 @@ void ta_multi_shutdown(ta_ctx *ctx);
 
 // Concatenates per-shard (items, offsets) outputs -- shard r covers units bound[r] .. bound[r + 1] and its arrays came
 // from ta_out_alloc -- into one pair of caller-owned arrays; frees the shard arrays.
+// q-gram search filter: queue capacity = haystack bytes / this + 4096 entries (lev_bitpar.cu); search.cu sizes the
+// exact kernel's item list from it (<= 8 distinct 16-byte granules per queue entry)
+#define TA_QGRAM_BYTES_PER_ENTRY 256
+
 // what ta_launch_search_filter (lev_bitpar.cu) queued: a device list of codes haystack * segs + granule, `gran` bytes of
 // end positions per granule.  If alt_flag is non-null and set ON THE DEVICE when the exact kernel runs, the list was
 // written by the fallback filter instead and holds alt_segs / alt_gran codes.
